@@ -1,0 +1,180 @@
+/*
+ * mermaid_b200.h -- C ABI of libmermaid_b200.so (sm_100a CUDA, B200).
+ *
+ * One data-parallel hot path of data-mermaid/mermaid-classifier, rebuilt for B200:
+ * point-patch crop -> normalise -> EfficientNet-B0 -> 1280-d features -> MLP/Platt head.
+ *
+ * Every entry point replaces a Python-level call of the reference (there is no native
+ * interface in the reference; the FFI a maintainer would add is the ctypes stub shown
+ * in INTEGRATION.md).  Each declaration cites the reference code it stands in for
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  "dev" pointers are CUDA device
+ *     pointers on the extractor's device, "host" pointers are ordinary host memory.
+ *   - the caller owns every input/output buffer; handles own weights and workspaces.
+ *   - every call returns an int status (MC_OK == 0); mc_last_error() gives the
+ *     thread-local message of the last failure.
+ *   - calls taking `stream` (a cudaStream_t passed as void*, NULL = default stream)
+ *     are asynchronous on that stream and never call cudaDeviceSynchronize; calls
+ *     with `_host` in the name synchronise the stream before returning because they
+ *     hand back host results.
+ *   - handles are not thread-safe: one handle per (device, stream).
+ */
+#ifndef MERMAID_B200_H
+#define MERMAID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_ABI_VERSION 1
+
+/* status codes; the Python wrapper maps them to the reference's exception types */
+#define MC_OK 0
+#define MC_ERR_BAD_ARG 1       /* ValueError                                              */
+#define MC_ERR_POINT_BOUNDS 2  /* spacer RowColumnInvalidError (check_extract_inputs)     */
+#define MC_ERR_DATA_LIMIT 3    /* spacer DataLimitError (check_extract_inputs)            */
+#define MC_ERR_CUDA 4          /* RuntimeError                                            */
+#define MC_ERR_UNSUPPORTED 5   /* RuntimeError                                            */
+#define MC_ERR_NOMEM 6         /* MemoryError                                             */
+
+/* arithmetic modes of the backbone */
+#define MC_MODE_FP32 0 /* fp32 activations, fp32-accurate arithmetic (parity config C1/C2) */
+#define MC_MODE_BF16 1 /* bf16 activations + bf16 tensor-core GEMMs, fp32 accumulate (C3)  */
+
+#define MC_FEATURE_DIM 1280
+#define MC_CROP_SIZE 224
+
+typedef struct mc_extractor mc_extractor;
+typedef struct mc_head mc_head;
+typedef struct mc_mlp mc_mlp;
+
+/* A decoded RGB8 image, HWC, rows `row_pitch` bytes apart. */
+typedef struct mc_image {
+  const uint8_t* data;
+  int32_t height;
+  int32_t width;
+  int64_t row_pitch;
+} mc_image;
+
+/* A point annotation: index into the image table + (row, col) of the patch centre. */
+typedef struct mc_point {
+  int32_t image;
+  int32_t row;
+  int32_t col;
+} mc_point;
+
+int mc_abi_version(void);
+const char* mc_last_error(void);
+
+/* ---- synthetic inputs (bench/test data generator; same integer hash as
+ *      mermaid_classifier_b200/synth.py::synth_image) ------------------------------- */
+int mc_synth_image(uint8_t* img_dev, int32_t height, int32_t width, int64_t row_pitch,
+                   uint32_t seed, uint32_t image_id, void* stream);
+
+/* ---- A1: spacer.task_utils.check_extract_inputs (call site:
+ *      mermaid_classifier/pyspacer/annotation.py:240).  Host-only validation. -------- */
+int mc_check_extract_inputs(int32_t height, int32_t width, const int32_t* rowcols_host,
+                            int64_t n_points, int64_t max_pixels, int64_t max_points);
+
+/* ---- A2: spacer crop_patches / crop_simple (invoked through extractor(img, rowcols),
+ *      mermaid_classifier/pyspacer/annotation.py:241).  Bit-exact reflect-padded gather:
+ *      patches_dev[k][i][j][c] = img[R(row_k-112+i, H)][R(col_k-112+j, W)][c]. ---------- */
+int mc_crop_patches(const mc_image* images_host, int32_t n_images, const mc_point* points_host,
+                    int64_t n_points, uint8_t* patches_dev /* n x 224 x 224 x 3 */, void* stream);
+
+/* ---- A3: torch_extractors.transformation() (scripts/build_feature_bucket.py:420-431):
+ *      ToTensor + Normalize, HWC u8 -> CHW fp32.  Exposed for the parity gate only; the
+ *      extraction path fuses it into the stem kernel. -------------------------------- */
+int mc_normalize_patches(const uint8_t* patches_dev, int64_t n, float* out_dev /* n x 3 x 224 x 224 */,
+                         void* stream);
+
+/* ---- EfficientNetExtractor (spacer.extractors; constructed at
+ *      mermaid_classifier/pyspacer/annotation.py:236-238 and
+ *      scripts/build_feature_bucket.py:854-859).
+ *      `params_host`: BN-folded parameters packed by
+ *      mermaid_classifier_b200/weights.py::pack_backbone (fp32, canonical order);
+ *      `n_params` must equal mc_backbone_param_count(). ------------------------------ */
+int64_t mc_backbone_param_count(void);
+int mc_extractor_create(const float* params_host, int64_t n_params, int32_t mode, int32_t device,
+                        int32_t max_batch, mc_extractor** out);
+int mc_extractor_destroy(mc_extractor* h);
+int mc_extractor_mode(const mc_extractor* h);
+int64_t mc_extractor_launches(const mc_extractor* h); /* kernels launched so far by this handle */
+
+/* ---- A2+A3+A4: extractor.__call__(image, rowcols) (annotation.py:241) for a table of
+ *      device-resident images: crop + normalise + EfficientNet-B0 extract_features.
+ *      feats_dev is n_points x 1280 fp32, row k = point k.  Any n_points; the library
+ *      walks it in sub-batches of at most max_batch patches. ------------------------- */
+int mc_extract_points(mc_extractor* h, const mc_image* images_host, int32_t n_images,
+                      const mc_point* points_host, int64_t n_points, float* feats_dev, void* stream);
+
+/* ---- A3+A4: TorchExtractor.patches_to_features(patch_list)
+ *      (scripts/build_feature_bucket.py:415-446) for pre-cropped 224x224x3 u8 patches. */
+int mc_extract_patches(mc_extractor* h, const uint8_t* patches_dev, int64_t n, float* feats_dev,
+                       void* stream);
+
+/* ---- The reference-facing call with HOST buffers: one image + its rowcols in, features
+ *      out (spacer.tasks.extract_features minus storage I/O,
+ *      scripts/build_feature_bucket.py:775).  H2D of the image, D2H of the features and a
+ *      stream synchronise happen inside.  rowcols_host is n x 2 int32 (row, col). ------- */
+int mc_extract_image_host(mc_extractor* h, const uint8_t* img_host, int32_t height, int32_t width,
+                          int64_t row_pitch, const int32_t* rowcols_host, int64_t n_points,
+                          float* feats_host, void* stream);
+
+/* Debug/parity tap: during the NEXT extract call, copy one internal NHWC activation of the
+ * first sub-batch to `out_dev` as fp32 (at most `capacity` elements).
+ * layer: 0 = stem, 1+4*b+{0,1,2,3} = block b {expand, depthwise, SE gate, block out},
+ * 65 = head conv (pre-pool).  layer < 0 disarms the tap. */
+int mc_extractor_set_tap(mc_extractor* h, int32_t layer, float* out_dev, int64_t capacity);
+
+/* ---- A6: CalibratedHead (mermaid_classifier/pyspacer/inference/head.py:25-89) behind
+ *      Predictor.predict_proba (inference/loader.py:30-35).
+ *      weights_host[i] is (dims[i+1] x dims[i]) row-major fp32, biases_host[i] dims[i+1];
+ *      a/b are the per-class Platt parameters, or NULL for the uncalibrated softmax path
+ *      of TorchMLPClassifier._forward_probs (torch_classifier.py:332-370). ------------ */
+int mc_head_create(int32_t n_layers, const int32_t* dims /* n_layers + 1 */,
+                   const float* const* weights_host, const float* const* biases_host,
+                   const float* platt_a_host, const float* platt_b_host, int32_t device,
+                   mc_head** out);
+int mc_head_destroy(mc_head* h);
+
+/* features_dev: n x dims[0] fp32.  Any of the outputs may be NULL.
+ *   proba_dev  : n x K float64 (predict_proba)
+ *   labels_dev : n int32, np.argmax tie-break (lowest index)
+ *   topk_*     : n x topk, descending, stable (annotation.py:253-259) */
+int mc_head_scores(mc_head* h, const float* features_dev, int64_t n, double* proba_dev,
+                   int32_t* labels_dev, int32_t topk, int32_t* topk_idx_dev, float* topk_val_dev,
+                   void* stream);
+int mc_head_scores_host(mc_head* h, const float* features_host, int64_t n, double* proba_host,
+                        int32_t* labels_host, void* stream);
+int64_t mc_head_launches(const mc_head* h); /* kernels launched so far by this handle */
+
+/* ---- A7: TorchMLPClassifier.partial_fit inner loop
+ *      (mermaid_classifier/pyspacer/torch_classifier.py:226-303): per mini-batch
+ *      weighted CE + 0.5*alpha/mb*sum(W^2), backward, Adam.  Parameters live on the
+ *      device; X/y for one partial_fit chunk are passed already shuffled. ------------- */
+int mc_mlp_create(int32_t n_layers, const int32_t* dims, const float* const* weights_host,
+                  const float* const* biases_host, const float* class_weight_host /* K or NULL */,
+                  float lr, float alpha, float beta1, float beta2, float eps, int32_t device,
+                  mc_mlp** out);
+int mc_mlp_destroy(mc_mlp* h);
+/* Runs ceil(n / batch) Adam steps over x_dev (n x dims[0]) / y_dev (n int32 class indices);
+ * *loss_out_host receives the loss_curve_ entry (sample-weighted mean regularised loss).
+ * grad_sync: optional callback invoked on the stream after each backward with the flat
+ * gradient buffer (device, n_grad floats) -- the data-parallel all-reduce hook. */
+typedef void (*mc_grad_sync_fn)(float* grad_dev, int64_t n_grad, void* stream, void* user);
+int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, int64_t n, int32_t batch,
+                       int32_t global_batch, mc_grad_sync_fn grad_sync, void* user,
+                       double* loss_out_host, void* stream);
+int mc_mlp_get_params(mc_mlp* h, float* const* weights_host, float* const* biases_host);
+int64_t mc_mlp_steps(const mc_mlp* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MERMAID_B200_H */

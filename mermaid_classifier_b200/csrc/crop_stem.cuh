@@ -1,0 +1,158 @@
+// K1 (point-patch gather / reflect crop / normalise) and K2 (stem conv) kernels.
+//
+// Reference semantics restated (see oracle/crop.py):
+//   patch[i][j][c] = img[R(row-112+i, H)][R(col-112+j, W)][c]   (np.pad mode='reflect')
+//   x[c][i][j]     = (u8/255 - mean[c]) / std[c]                (ToTensor + Normalize)
+//   stem           = swish(bn0(conv3x3 s2, TF-SAME pad (0,1)))  (lukemelas EfficientNet)
+// The normalisation is a 3x256-entry lookup table computed on the host in fp32 with the
+// exact op order torch uses, so the device result is bit-identical by construction.
+#pragma once
+#include "common.cuh"
+
+namespace mc {
+
+// ---- synthetic image (bench/test input generator) ------------------------------------
+__global__ void synth_image_kernel(uint8_t* img, int H, int W, int64_t pitch, uint32_t key) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  const uint32_t pos = mix32(((uint32_t)y << 16) | (uint32_t)x);
+  const uint32_t ramp = (((uint32_t)x & 63u) + ((uint32_t)y & 63u)) >> 2;
+  uint8_t* p = img + (int64_t)y * pitch + (int64_t)x * 3;
+#pragma unroll
+  for (uint32_t c = 0; c < 3; ++c) {
+    const uint32_t cell =
+        mix32(key ^ (((uint32_t)y >> 6) * 0x85EBCA77u) ^ (((uint32_t)x >> 6) * 0xC2B2AE3Du) ^ (c * 0x27D4EB2Fu));
+    const uint32_t base = 40u + ((((cell >> 8) & 0xFFFFu) * 160u) >> 16);
+    const uint32_t noise = mix32((key + c * 0x632BE5ABu) ^ pos) & 31u;
+    p[c] = (uint8_t)(base + ramp + noise - 16u);
+  }
+}
+
+// ---- K1 stand-alone: bit-exact crop (parity gate + pre-cropped patch producer) ---------
+// grid (224 patch rows, n points), 224 threads: thread j copies pixel (i, j).
+__global__ void crop_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__ points,
+                            uint8_t* __restrict__ out) {
+  const int i = blockIdx.x;
+  const int64_t k = blockIdx.y;
+  const mc_point pt = points[k];
+  const mc_image im = images[pt.image];
+  const int y = reflect_idx(pt.row - 112 + i, im.height);
+  const uint8_t* src_row = im.data + (int64_t)y * im.row_pitch;
+  __shared__ uint8_t row_s[224 * 3];
+  for (int j = threadIdx.x; j < 224; j += blockDim.x) {
+    const int x = reflect_idx(pt.col - 112 + j, im.width);
+    const uint8_t* s = src_row + (int64_t)x * 3;
+    row_s[j * 3 + 0] = s[0];
+    row_s[j * 3 + 1] = s[1];
+    row_s[j * 3 + 2] = s[2];
+  }
+  __syncthreads();
+  // coalesced 4-byte stores of the 672-byte output row
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + (k * 224 + i) * 672);
+  const uint32_t* srs = reinterpret_cast<const uint32_t*>(row_s);
+  for (int t = threadIdx.x; t < 168; t += blockDim.x) dst[t] = srs[t];
+}
+
+// ---- A3 stand-alone: ToTensor + Normalize (parity gate only) ---------------------------
+__global__ void normalize_kernel(const uint8_t* __restrict__ patches, const float* __restrict__ lut,
+                                 float* __restrict__ out, int64_t n_pix_total) {
+  // one thread per (patch, i, j)
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pix_total) return;
+  const int64_t k = t / (224 * 224);
+  const int64_t ij = t % (224 * 224);
+  const uint8_t* p = patches + t * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[(k * 3 + c) * (224 * 224) + ij] = lut[c * 256 + p[c]];
+}
+
+// ---- fused K1+K2: gather + normalise + stem conv3x3/s2 + BN + swish --------------------
+// One CTA = one 16x16 tile of the 112x112 stem output of one patch (grid 49 x n).
+// The 33x33x3 input window is gathered straight from the source image (reflect),
+// normalised through the LUT into shared memory, and each thread produces the 32 output
+// channels of one output pixel; the tile is then written out NHWC, fully coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256) stem_kernel(const mc_image* __restrict__ images,
+                                                   const mc_point* __restrict__ points,
+                                                   const float* __restrict__ w,      // [27][32]
+                                                   const float* __restrict__ scale,  // [32]
+                                                   const float* __restrict__ bias,   // [32]
+                                                   const float* __restrict__ lut,    // [3][256]
+                                                   T* __restrict__ out) {            // [n][112][112][32]
+  constexpr int TS = 16, IN = 2 * TS + 1;  // 33
+  __shared__ float in_s[IN][IN * 3 + 1];
+  __shared__ float w_s[27 * 32];
+  __shared__ float lut_s[768];
+  __shared__ float sc_s[32], bi_s[32];
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int oy0 = (tile / 7) * TS, ox0 = (tile % 7) * TS;
+  const int64_t k = blockIdx.y;
+  const mc_point pt = points[k];
+  const mc_image im = images[pt.image];
+
+  for (int t = tid; t < 27 * 32; t += 256) w_s[t] = w[t];
+  for (int t = tid; t < 768; t += 256) lut_s[t] = lut[t];
+  if (tid < 32) {
+    sc_s[tid] = scale[tid];
+    bi_s[tid] = bias[tid];
+  }
+  __syncthreads();
+  // gather: IN rows x IN pixels x 3 bytes
+  for (int t = tid; t < IN * IN; t += 256) {
+    const int r = t / IN, cpx = t % IN;
+    const int pi = 2 * oy0 + r, pj = 2 * ox0 + cpx;  // patch coordinates; 224 == the SAME zero pad
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (pi < 224 && pj < 224) {
+      const int y = reflect_idx(pt.row - 112 + pi, im.height);
+      const int x = reflect_idx(pt.col - 112 + pj, im.width);
+      const uint8_t* s = im.data + (int64_t)y * im.row_pitch + (int64_t)x * 3;
+      v0 = lut_s[s[0]];
+      v1 = lut_s[256 + s[1]];
+      v2 = lut_s[512 + s[2]];
+    }
+    in_s[r][cpx * 3 + 0] = v0;
+    in_s[r][cpx * 3 + 1] = v1;
+    in_s[r][cpx * 3 + 2] = v2;
+  }
+  __syncthreads();
+
+  const int ty = tid / TS, tx = tid % TS;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = in_s[2 * ty + ky][(2 * tx + kx) * 3 + ci];
+        const float4* wr = reinterpret_cast<const float4*>(&w_s[((ky * 3 + kx) * 3 + ci) * 32]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 wv = wr[q];
+          acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  T* o = out + (((k * 112 + (oy0 + ty)) * 112) + (ox0 + tx)) * 32;
+  constexpr int VN = Vec<T>::N;
+#pragma unroll
+  for (int q = 0; q < 32 / VN; ++q) {
+    Vec<T> v;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const int c = q * VN + e;
+      v.v[e] = silu_f(fmaf(acc[c], sc_s[c], bi_s[c]));
+    }
+    v.store(o + q * VN);
+  }
+}
+
+}  // namespace mc

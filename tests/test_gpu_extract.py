@@ -1,0 +1,198 @@
+"""GPU parity tests for the extraction path (crop -> normalize -> EfficientNet-B0 features),
+through the C ABI, against the CPU oracle.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from mermaid_classifier_b200 import _lib, synth
+from mermaid_classifier_b200.extractor import (
+    EfficientNetExtractor,
+    crop_patches_device,
+    normalize_patches_device,
+    synth_image_device,
+)
+from oracle import crop as ocrop
+from oracle import effnet as oeff
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances (BASELINE.json north_star)
+FP32_MAX_ABS = 1e-3
+FP32_MIN_COS = 0.99999
+BF16_MIN_COS = 0.995   # looser bound for the bf16 mode (reference's own device gate is 0.999 on TF32 GPUs)
+BF16_MAX_ABS = 0.15
+
+
+def cosines(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return (a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1) + 1e-12)
+
+
+@pytest.fixture(scope="module")
+def ext32(backbone_sd):
+    e = EfficientNetExtractor(state_dict=backbone_sd, mode="fp32", max_batch=24)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def ext16(backbone_sd):
+    e = EfficientNetExtractor(state_dict=backbone_sd, mode="bf16", max_batch=24)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("hw", [(300, 400), (64, 1000), (3000, 4000)])
+def test_synth_image_device_bit_exact(hw):
+    H, W = hw
+    for image_id in (0, 7):
+        dev = synth_image_device(synth.DEFAULT_SEED, image_id, H, W).cpu().numpy()
+        ref = synth.synth_image(synth.DEFAULT_SEED, image_id, H, W)
+        assert np.array_equal(dev, ref)
+
+
+@pytest.mark.parametrize("hw", [(600, 800), (224, 224), (100, 37), (5, 3), (1, 7), (113, 500)])
+def test_crop_bit_exact(hw):
+    H, W = hw
+    im = synth.synth_image(3, 1, H, W)
+    pts = synth.synth_points(3, 1, H, W, 12, corners=True)
+    want = ocrop.crop_patches(im, pts)
+    dev_im = torch.from_numpy(im).cuda()
+    p3 = np.array([(0, r, c) for r, c in pts], dtype=np.int32)
+    got = crop_patches_device([dev_im], p3).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_crop_multi_image_and_pitch():
+    ims = [synth.synth_image(5, i, 300 + 17 * i, 280 + 31 * i) for i in range(3)]
+    # second image lives inside a wider buffer (row pitch > 3*W)
+    wide = torch.zeros((ims[1].shape[0], ims[1].shape[1] + 9, 3), dtype=torch.uint8, device="cuda")
+    wide[:, : ims[1].shape[1]] = torch.from_numpy(ims[1]).cuda()
+    dev = [torch.from_numpy(ims[0]).cuda(), wide[:, : ims[1].shape[1]], torch.from_numpy(ims[2]).cuda()]
+    pts, want = [], []
+    for i, im in enumerate(ims):
+        rc = synth.synth_points(5, i, im.shape[0], im.shape[1], 5, corners=True)
+        pts += [(i, r, c) for r, c in rc]
+        want.append(ocrop.crop_patches(im, rc))
+    got = crop_patches_device(dev, np.array(pts, dtype=np.int32)).cpu().numpy()
+    assert np.array_equal(got, np.concatenate(want))
+
+
+def test_normalize_bit_exact():
+    rng = np.random.default_rng(0)
+    p = rng.integers(0, 256, (4, 224, 224, 3), dtype=np.uint8)
+    p[0, 0, 0] = (0, 128, 255)
+    got = normalize_patches_device(torch.from_numpy(p).cuda()).cpu().numpy()
+    assert np.array_equal(got, ocrop.normalize_patches(p))
+
+
+def test_point_validation_errors(ext32):
+    im = synth.synth_image(1, 0, 300, 300)
+    with pytest.raises(_lib.RowColumnInvalidError):
+        ext32.extract_array(im, [(300, 0)])
+    with pytest.raises(_lib.RowColumnInvalidError):
+        ext32.extract_array(im, [(0, -1)])
+    with pytest.raises(ValueError):
+        ext32.extract_array(im.astype(np.float32), [(0, 0)])
+    assert ext32.extract_array(im, []).shape == (0, 1280)
+
+
+def _nchw(t, n, h, c):
+    return t[: n * h * h * c].reshape(n, h, h, c).permute(0, 3, 1, 2).cpu()
+
+
+def test_layer_taps_fp32(ext32, backbone_sd):
+    """Layer-by-layer agreement with the oracle's activations (stem, every block's expand /
+    depthwise / gate / output, head conv)."""
+    im = synth.synth_image(synth.DEFAULT_SEED, 2, 500, 640)
+    pts = synth.synth_points(synth.DEFAULT_SEED, 2, 500, 640, 5, corners=True)
+    x = torch.from_numpy(ocrop.normalize_patches(ocrop.crop_patches(im, pts)))
+    taps = {}
+    oeff.extract_features(backbone_sd, x, taps)
+    n = len(pts)
+    dev_im = torch.from_numpy(im).cuda()
+    p3 = np.array([(0, r, c) for r, c in pts], dtype=np.int32)
+    blocks = oeff.b0_blocks()
+    checks = [(0, "stem", 112, 32)]
+    for b in blocks:
+        h_in = {0: 112, 1: 112, 2: 56, 3: 56, 4: 28, 5: 28, 6: 14, 7: 14, 8: 14, 9: 14, 10: 14, 11: 14, 12: 7, 13: 7, 14: 7, 15: 7}[b.index]
+        h_out = (h_in + b.stride - 1) // b.stride
+        if b.expand != 1:
+            checks.append((1 + 4 * b.index, f"b{b.index}.expand", h_in, b.c_mid))
+        checks.append((2 + 4 * b.index, f"b{b.index}.dw", h_out, b.c_mid))
+        checks.append((3 + 4 * b.index, f"b{b.index}.gate", 1, b.c_mid))
+        checks.append((4 + 4 * b.index, f"b{b.index}.out", h_out, b.c_out))
+    checks.append((65, "head", 7, 1280))
+    buf = torch.empty(n * 112 * 112 * 96, dtype=torch.float32, device="cuda")
+    for layer, name, hh, cc in checks:
+        ext32.set_tap(layer, buf)
+        ext32.extract_device([dev_im], p3)
+        torch.cuda.synchronize()
+        got = _nchw(buf, n, hh, cc)
+        want = taps[name]
+        err = (got - want).abs().max().item()
+        scale = want.abs().max().item()
+        assert err <= 2e-4 * max(1.0, scale), f"{name}: max abs err {err} (scale {scale})"
+
+
+def test_features_fp32_parity_c1_shape(ext32, backbone_sd):
+    """Parity gate in the shape of BASELINE config 1 (scaled to a CPU-seconds oracle run):
+    one image, sorted unique points incl. the four corners, fp32."""
+    H, W = 1500, 2000
+    im = synth.synth_image(synth.DEFAULT_SEED, 0, H, W)
+    pts = synth.synth_points(synth.DEFAULT_SEED, 0, H, W, 40, corners=True)
+    want = oeff.extract_features_batched(
+        backbone_sd, torch.from_numpy(ocrop.normalize_patches(ocrop.crop_patches(im, pts))), 10).numpy()
+    feats, msg = ext32(im, pts)
+    got = np.stack([feats.get_array(rc) for rc in pts])
+    assert got.shape == (len(pts), 1280) and feats.valid_rowcol and feats.feature_dim == 1280
+    assert np.abs(got - want).max() <= FP32_MAX_ABS
+    assert cosines(got, want).min() >= FP32_MIN_COS
+    assert msg.runtime > 0
+
+
+def test_patches_to_features_equals_call(ext32):
+    im = synth.synth_image(9, 4, 400, 400)
+    pts = synth.synth_points(9, 4, 400, 400, 7, corners=True)
+    a = ext32.extract_array(im, pts)
+    patches = list(ocrop.crop_patches(im, pts))
+    feats, remote = ext32.patches_to_features(patches)
+    assert remote is False and len(feats) == len(pts) and len(feats[0]) == 1280
+    assert np.array_equal(np.asarray(feats, dtype=np.float32), a)  # same kernels, same bits
+
+
+def test_subbatching_and_determinism(ext32):
+    """More points than max_batch -> several sub-batches; results independent of batching and
+    bit-reproducible run to run (no atomics on the path)."""
+    im = synth.synth_image(11, 0, 700, 900)
+    pts = synth.synth_points(11, 0, 700, 900, 60)
+    a = ext32.extract_array(im, pts)
+    b = ext32.extract_array(im, pts)
+    assert np.array_equal(a, b)
+    c = ext32.extract_array(im, pts[:10])
+    assert np.array_equal(a[:10], c)
+    assert ext32.launches > 0
+
+
+def test_verify_device_numerics_procedure(ext32, backbone_sd):
+    """The reference's own device gate (scripts/build_feature_bucket.py:451-502): 8 random
+    224x224 uint8 patches, seed 42, min cosine vs CPU >= 0.999 -- here held to 0.99999."""
+    rng = np.random.default_rng(seed=42)
+    patches = [rng.integers(0, 255, (224, 224, 3), dtype=np.uint8) for _ in range(8)]
+    got = np.asarray(ext32.patches_to_features(patches)[0])
+    want = oeff.extract_features(backbone_sd, torch.from_numpy(ocrop.normalize_patches(np.stack(patches)))).numpy()
+    assert cosines(got, want).min() >= FP32_MIN_COS
+    assert np.abs(got - want).max() <= FP32_MAX_ABS
+
+
+def test_features_bf16_mode(ext16, backbone_sd):
+    im = synth.synth_image(synth.DEFAULT_SEED, 5, 800, 800)
+    pts = synth.synth_points(synth.DEFAULT_SEED, 5, 800, 800, 24, corners=True)
+    want = oeff.extract_features(
+        backbone_sd, torch.from_numpy(ocrop.normalize_patches(ocrop.crop_patches(im, pts)))).numpy()
+    got = ext16.extract_array(im, pts)
+    cs = cosines(got, want)
+    assert cs.min() >= BF16_MIN_COS, cs.min()
+    assert np.abs(got - want).max() <= BF16_MAX_ABS
