@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const mc_image* __restrict__ 
                                                    T* __restrict__ out) {            // [n][112][112][32]
   constexpr int TS = 16, IN = 2 * TS + 1;  // 33
   __shared__ float in_s[IN][IN * 3 + 1];
-  __shared__ float w_s[27 * 32];
+  __shared__ __align__(16) float w_s[27 * 32];
   __shared__ float lut_s[768];
   __shared__ float sc_s[32], bi_s[32];
   const int tid = threadIdx.x;

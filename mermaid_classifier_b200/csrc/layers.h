@@ -8,6 +8,7 @@
 //     se_reduce: W[c_se][c_mid], b[c_se];  se_expand: W[c_mid][c_se], b[c_mid]
 //     project:   W[c_out][c_mid], scale[c_out], bias[c_out]
 //   head:   W[1280][320], scale[1280], bias[1280]
+// Every segment is zero-padded to a multiple of 4 floats so each starts 16-byte aligned.
 // scale/bias are the inference-form BatchNorm folded to y = conv * scale + bias
 // (eps = 1e-3; pyspacer's vendored lukemelas EfficientNet).
 #pragma once
@@ -49,9 +50,10 @@ inline NetCfg make_b0() {
                                    {1, 3, 1, 6, 192, 320}};
   NetCfg net;
   int64_t off = 0;
+  // every segment starts on a 16-byte boundary (float4 loads)
   auto take = [&](int64_t n) {
     int64_t o = off;
-    off += n;
+    off += (n + 3) / 4 * 4;
     return o;
   };
   net.w_stem = take(27 * 32);

@@ -74,7 +74,9 @@ def pack_backbone(sd: dict) -> np.ndarray:
     parts: list[np.ndarray] = []
 
     def add(x):
-        parts.append(np.ascontiguousarray(np.asarray(x, dtype=np.float32)).reshape(-1))
+        flat = np.ascontiguousarray(np.asarray(x, dtype=np.float32)).reshape(-1)
+        pad = (-flat.size) % 4  # every segment starts 16-byte aligned (csrc/layers.h)
+        parts.append(np.concatenate([flat, np.zeros(pad, np.float32)]) if pad else flat)
 
     # stem: [co][ci][ky][kx] -> [ky][kx][ci][co]
     add(sd["_conv_stem.weight"].float().permute(2, 3, 1, 0).contiguous().numpy())
