@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- point-patches/sec of the mermaid-classifier hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1], "C2"): per GPU, 1,000 synthetic 4000x3000 RGB images x 100
+point annotations -> crop/normalise -> EfficientNet-B0 fp32 features -> MLP(200,100)/Platt head
+labels.  One *step* is one pass over that workload.  Images are generated ON the device by the
+integer-hash generator (bit-identical to the NumPy form the oracle uses); weights are the seeded
+synthetic checkpoint (`synth.synth_backbone_state_dict`).
+
+Numbers on the JSON line
+  value     : whole-job point-patches/s with every input already resident in HBM.
+  e2e       : the same workload through the host-buffer path: every step copies every image from
+              pinned host memory to the device, and copies features + labels back.
+  roofline  : the dominant kernel, timed with CUDA events on the launching stream during the
+              timed steps, against the measured HBM peak in MEASURED_PEAKS.json.
+  cpu_baseline : the oracle (CPU restatement of the pyspacer path) on a bounded sample of the
+              same workload on this box's host cores.
+With --impl reference the CPU path alone is timed (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H_IMG, W_IMG = 3000, 4000
+METRIC = "point-patches/sec (EffNet-B0 1280-d features + head)"
+
+# Algorithmic HBM bytes per patch per layer (DESIGN.md "Roofline"): activations read + written,
+# weights amortised; e = element size (4 in fp32 mode, 2 in bf16 mode).
+B0 = [  # (k, stride, expand, c_in, c_out, h_in)
+    (3, 1, 1, 32, 16, 112), (3, 2, 6, 16, 24, 112), (3, 1, 6, 24, 24, 56), (5, 2, 6, 24, 40, 56),
+    (5, 1, 6, 40, 40, 28), (3, 2, 6, 40, 80, 28), (3, 1, 6, 80, 80, 14), (3, 1, 6, 80, 80, 14),
+    (5, 1, 6, 80, 112, 14), (5, 1, 6, 112, 112, 14), (5, 1, 6, 112, 112, 14), (5, 2, 6, 112, 192, 14),
+    (5, 1, 6, 192, 192, 7), (5, 1, 6, 192, 192, 7), (5, 1, 6, 192, 192, 7), (3, 1, 6, 192, 320, 7),
+]
+
+
+def layer_bytes(e: int) -> dict[int, tuple[str, float]]:
+    """layer id (mc_extractor_profile ids) -> (name, algorithmic bytes per patch)."""
+    out = {0: ("stem(crop+norm+conv3x3s2)", 224 * 224 * 3 + 112 * 112 * 32 * e)}
+    for b, (k, s, ex, ci, co, h) in enumerate(B0):
+        ho = (h + s - 1) // s
+        cm = ci * ex
+        if ex != 1:
+            out[1 + 4 * b] = (f"b{b}.expand", h * h * (ci + cm) * e)
+        out[2 + 4 * b] = (f"b{b}.depthwise", (h * h + ho * ho) * cm * e)
+        out[3 + 4 * b] = (f"b{b}.se", cm * 4 * 2)
+        skip = s == 1 and ci == co
+        out[4 + 4 * b] = (f"b{b}.project", ho * ho * (cm + co * (2 if skip else 1)) * e)
+    out[65] = ("conv_head", 49 * (320 + 1280) * e)
+    out[66] = ("avgpool", 49 * 1280 * e + 1280 * 4)
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows: list[list[str]] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2])), power.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------
+# CPU path (oracle) -- used ONLY for cpu_baseline / --impl reference
+# ---------------------------------------------------------------------------------------
+def cpu_reference_run(n_images: int, n_points: int, warmup_images: int = 1, batch_size: int = 10) -> dict:
+    """Restated pyspacer CPU path on host cores: whole-image np.pad(reflect) -> slices ->
+    ToTensor/Normalize per patch -> EfficientNet-B0 fp32 at pyspacer's batch size -> head."""
+    from mermaid_classifier_b200 import synth
+    from oracle import crop as ocrop
+    from oracle import effnet as oeff
+    from oracle import head as ohead
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synth_backbone_state_dict()
+    w, bb, a, b, _ = synth.synth_head(1280, (200, 100), 500, seed=0)
+
+    def one(image_id: int):
+        im = synth.synth_image(synth.DEFAULT_SEED, image_id, H_IMG, W_IMG)
+        pts = synth.synth_points(synth.DEFAULT_SEED, image_id, H_IMG, W_IMG, n_points)
+        t0 = time.perf_counter()
+        patches = ocrop.crop_patches_padded(im, pts)  # the literal pyspacer form (whole-image pad)
+        x = torch.from_numpy(ocrop.normalize_patches(np.stack(patches)))
+        feats = oeff.extract_features_batched(sd, x, batch_size).numpy()
+        proba = ohead.calibrated_proba(feats, w, bb, a, b)
+        _ = proba.argmax(1)
+        return time.perf_counter() - t0, len(pts)
+
+    for i in range(warmup_images):
+        one(10_000 + i)
+    t, n = 0.0, 0
+    for i in range(n_images):
+        dt, k = one(i)
+        t += dt
+        n += k
+    return {"value": n / t, "unit": "point-patches/s", "cores": cores, "kind": "port",
+            "sample": f"{n_images} synthetic {W_IMG}x{H_IMG} images x {n_points} points, batch {batch_size}, "
+                      f"torch {torch.get_num_threads()} threads (image synthesis untimed)",
+            "seconds": t, "patches": n}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    ms = []
+    n_total = 0
+    sample = None
+    for step in range(args.warmup + args.steps):
+        r = cpu_reference_run(n_images=args.ref_images, n_points=args.points, warmup_images=0)
+        if step >= args.warmup:
+            ms.append(r["seconds"] * 1e3)
+            n_total += r["patches"]
+        sample = r
+    value = n_total / (sum(ms) / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "point-patches/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2 sample: {args.ref_images} image(s) x {args.points} points per step, CPU oracle port of the "
+                               "pyspacer path (whole-image reflect pad, batch 10) + MLP(200,100)/Platt head"},
+        "cpu_baseline": {"value": value, "unit": "point-patches/s", "cores": sample["cores"], "kind": "port",
+                         "sample": sample["sample"]},
+        "e2e": {"value": value, "unit": "point-patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# B200 path
+# ---------------------------------------------------------------------------------------
+def run_b200(args, rank: int, world: int, local: int):
+    from mermaid_classifier_b200 import _lib, synth
+    from mermaid_classifier_b200.extractor import EfficientNetExtractor, synth_image_device
+    from mermaid_classifier_b200.inference import DeviceHead
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_img, n_pts = args.images, args.points
+    sd = synth.synth_backbone_state_dict()
+    ext = EfficientNetExtractor(state_dict=sd, mode=args.mode, max_batch=args.batch, device=local)
+    w, bb, a, b, _ = synth.synth_head(1280, (200, 100), 500, seed=0)
+    head = DeviceHead([x.numpy() for x in w], [x.numpy() for x in bb], a.numpy(), b.numpy(), device=local)
+
+    # ---- inputs resident in HBM: n_img distinct images (36 MB each), rank-disjoint ids ----
+    img0 = rank * n_img
+    images = [synth_image_device(synth.DEFAULT_SEED, img0 + i, H_IMG, W_IMG) for i in range(n_img)]
+    pts_per_img = [synth.synth_points(synth.DEFAULT_SEED, img0 + i, H_IMG, W_IMG, n_pts) for i in range(n_img)]
+    points = np.array([(i, r, c) for i, rc in enumerate(pts_per_img) for r, c in rc], dtype=np.int32)
+    n_patches = points.shape[0]
+    feats = torch.empty((n_patches, 1280), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    lib = _lib.load()
+    h = ext._ensure_handle()
+
+    def step_resident():
+        ext.extract_device(images, points, out=feats)
+        return head.scores_device(feats)["labels"]
+
+    # ---- warm-up, with one fully profiled pass to find the dominant kernel ------------------
+    lbytes = layer_bytes(4 if args.mode == "fp32" else 2)
+    for i in range(args.warmup):
+        if i == args.warmup - 1:
+            _lib.check(lib.mc_extractor_profile(h, -2))
+        step_resident()
+    torch.cuda.synchronize()
+    ms_all = np.zeros(67)
+    cnt_all = np.zeros(67, dtype=np.int64)
+    _lib.check(lib.mc_extractor_profile_read(h, ms_all.ctypes.data, cnt_all.ctypes.data, 1))
+    dominant = int(np.argmax(ms_all))
+    _lib.check(lib.mc_extractor_profile(h, dominant))  # 2 events per sub-batch during the timed steps
+
+    # ---- timed: device-resident --------------------------------------------------------------
+    launches0 = ext.launches + head.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        labels = step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = ext.launches + head.launches - launches0
+    ms_dom = np.zeros(67)
+    cnt_dom = np.zeros(67, dtype=np.int64)
+    _lib.check(lib.mc_extractor_profile_read(h, ms_dom.ctypes.data, cnt_dom.ctypes.data, 1))
+    _lib.check(lib.mc_extractor_profile(h, -1))
+
+    # ---- timed: end to end from pinned host memory -----------------------------------------------
+    e2e = run_e2e(args, ext, head, pts_per_img, images, dev, barrier)
+
+    # ---- aggregate over ranks (max time) ------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e["ms_total"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    value = world * n_patches * args.steps / (ms_total / 1e3)
+    e2e_value = world * n_patches * args.steps / (ms_e2e / 1e3)
+
+    peak, peak_src = measured_peaks()
+    dom_name, dom_bytes = lbytes.get(dominant, (f"layer{dominant}", 0.0))
+    dom_launches = max(int(cnt_dom[dominant]), 1)
+    dom_ms = float(ms_dom[dominant]) / dom_launches
+    patches_per_launch = n_patches * args.steps / dom_launches
+    achieved = dom_bytes * patches_per_launch / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    share = float(ms_all[dominant] / ms_all.sum()) if ms_all.sum() > 0 else 0.0
+    table = sorted(((float(ms_all[i]), lbytes.get(i, (str(i), 0))[0]) for i in range(67) if ms_all[i] > 0), reverse=True)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "point-patches/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"C2: {n_img} synthetic {W_IMG}x{H_IMG} RGB images x {n_pts} points per GPU -> EfficientNet-B0 "
+                        f"{args.mode} features + MLP(200,100)/Platt head labels (500 classes)",
+            "patches_per_step_per_gpu": n_patches, "sub_batch": args.batch, "mode": args.mode,
+            "l2": f"inputs larger than L2: {n_img} distinct 36 MB images resident in HBM, streamed once per step",
+            "weights": "synthetic seeded EfficientNet-B0 checkpoint (pyspacer layout), synthetic head",
+        },
+        "e2e": {"value": e2e_value, "unit": "point-patches/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                "ms_per_step": ms_e2e / args.steps, "host_pool_images": e2e["pool"], "images_per_group": e2e["group"]},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_patch": dom_bytes, "avg_launch_ms": dom_ms,
+                     "patches_per_launch": patches_per_launch, "share_of_step": share,
+                     "top_kernels_ms_per_step": [[n, round(m, 3)] for m, n in table[:8]]},
+        "labels_checksum": int(labels.to(torch.int64).sum().item()),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_run(n_images=args.cpu_images, n_points=n_pts)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+
+
+def run_e2e(args, ext, head, pts_per_img, images_dev, dev, barrier) -> dict:
+    """Host-buffer path: every image is copied from pinned host memory each step, features and
+    labels are copied back.  Images are processed in groups (one extract call per group) on two
+    streams so the copy of group g+1 overlaps the compute of group g."""
+    n_img = len(pts_per_img)
+    pool = min(args.host_pool, n_img)
+    group = args.group
+    host = [torch.empty((H_IMG, W_IMG, 3), dtype=torch.uint8).pin_memory() for _ in range(pool)]
+    for i in range(pool):
+        host[i].copy_(images_dev[i])  # distinct synthetic images; image i of the step uses host[i % pool]
+    torch.cuda.synchronize()
+    n_slots = 2
+    stage = [[torch.empty((H_IMG, W_IMG, 3), dtype=torch.uint8, device=dev) for _ in range(group)] for _ in range(n_slots)]
+    max_pts = max(len(p) for p in pts_per_img) * group
+    feats_dev = [torch.empty((max_pts, 1280), dtype=torch.float32, device=dev) for _ in range(n_slots)]
+    feats_host = [torch.empty((max_pts, 1280), dtype=torch.float32).pin_memory() for _ in range(n_slots)]
+    labels_host = [torch.empty((max_pts,), dtype=torch.int32).pin_memory() for _ in range(n_slots)]
+    copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    copied = [torch.cuda.Event() for _ in range(n_slots)]
+    freed = [torch.cuda.Event() for _ in range(n_slots)]
+    groups = [list(range(g, min(g + group, n_img))) for g in range(0, n_img, group)]
+    gpts = [np.array([(j, r, c) for j, i in enumerate(g) for r, c in pts_per_img[i]], dtype=np.int32) for g in groups]
+    h2d = n_img * H_IMG * W_IMG * 3 + sum(p.nbytes for p in gpts)
+    d2h = sum(p.shape[0] for p in gpts) * (1280 * 4 + 4)
+
+    def one_step():
+        for gi, g in enumerate(groups):
+            s = gi % n_slots
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[s])
+                for j, i in enumerate(g):
+                    stage[s][j].copy_(host[i % pool], non_blocking=True)
+                copied[s].record(copy_stream)
+            with torch.cuda.stream(comp_stream):
+                comp_stream.wait_event(copied[s])
+                n = gpts[gi].shape[0]
+                ext.extract_device(stage[s][: len(g)], gpts[gi], out=feats_dev[s][:n])
+                freed[s].record(comp_stream)
+                lab = head.scores_device(feats_dev[s][:n])["labels"]
+                feats_host[s][:n].copy_(feats_dev[s][:n], non_blocking=True)
+                labels_host[s][:n].copy_(lab, non_blocking=True)
+        comp_stream.synchronize()
+
+    for s in range(n_slots):
+        freed[s].record(comp_stream)
+    one_step()  # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    return {"ms_total": max(e0.elapsed_time(e1), wall_ms), "h2d": int(h2d), "d2h": int(d2h), "pool": pool, "group": group}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--images", type=int, default=1000)
+    ap.add_argument("--points", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=500, help="patches per sub-batch")
+    ap.add_argument("--group", type=int, default=5, help="images per extract call on the e2e path")
+    ap.add_argument("--host-pool", type=int, default=64, help="distinct pinned host images cycled by the e2e path")
+    ap.add_argument("--cpu-images", type=int, default=3, help="images timed by the cpu_baseline leg")
+    ap.add_argument("--ref-images", type=int, default=1, help="images per step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+        run_b200(args, rank, world, local)
+    if world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,14 @@ int mc_extract_image_host(mc_extractor* h, const uint8_t* img_host, int32_t heig
  * 65 = head conv (pre-pool).  layer < 0 disarms the tap. */
 int mc_extractor_set_tap(mc_extractor* h, int32_t layer, float* out_dev, int64_t capacity);
 
+/* Per-layer CUDA-event timing on the launching stream.  layer: -1 off (default), -2 every
+ * layer, >= 0 that layer only (ids as for mc_extractor_set_tap; +2 = SE FCs, 66 = pool).
+ * While enabled, extract calls synchronise the stream before returning.
+ * mc_extractor_profile_read copies accumulated milliseconds / launch counts (67 entries each). */
+#define MC_N_LAYERS 67
+int mc_extractor_profile(mc_extractor* h, int32_t layer);
+int mc_extractor_profile_read(mc_extractor* h, double* ms_out, int64_t* count_out, int32_t reset);
+
 /* ---- A6: CalibratedHead (mermaid_classifier/pyspacer/inference/head.py:25-89) behind
  *      Predictor.predict_proba (inference/loader.py:30-35).
  *      weights_host[i] is (dims[i+1] x dims[i]) row-major fp32, biases_host[i] dims[i+1];

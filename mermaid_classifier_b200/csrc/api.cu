@@ -1,6 +1,7 @@
 // C ABI of libmermaid_b200.so: handles, workspaces, layer orchestration.
 // Declarations (with the reference interface each one replaces) live in include/mermaid_b200.h.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -16,6 +17,8 @@
 #include "pw_tc.cuh"
 
 using namespace mc;
+
+
 
 namespace {
 
@@ -107,11 +110,57 @@ struct mc_extractor {
   int tap_layer = -1;
   float* tap_out = nullptr;
   int64_t tap_cap = 0;
+  // per-layer CUDA-event profiler (mc_extractor_profile): -1 off, -2 every layer, >= 0 one layer
+  int prof_layer = -1;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_ids;
+  size_t prof_used = 0;
+  double prof_ms[MC_N_LAYERS] = {0};
+  int64_t prof_cnt[MC_N_LAYERS] = {0};
 };
 
 namespace {
 
 constexpr int MAX_BANDS = 14;
+
+struct ProfScope {
+  mc_extractor* h;
+  cudaStream_t st;
+  bool on;
+  size_t slot = 0;
+  ProfScope(mc_extractor* h_, int layer, cudaStream_t st_) : h(h_), st(st_) {
+    on = h->prof_layer == -2 || h->prof_layer == layer;
+    if (!on) return;
+    if (h->prof_used + 2 > h->prof_ev.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_ev.push_back(e);
+      }
+    }
+    slot = h->prof_used;
+    h->prof_used += 2;
+    h->prof_ids.push_back(layer);
+    cudaEventRecord(h->prof_ev[slot], st);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(h->prof_ev[slot + 1], st);
+  }
+};
+
+int prof_collect(mc_extractor* h, cudaStream_t st) {
+  if (h->prof_used == 0) return MC_OK;
+  MC_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < h->prof_ids.size(); ++i) {
+    float ms = 0.f;
+    MC_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    h->prof_ms[h->prof_ids[i]] += ms;
+    h->prof_cnt[h->prof_ids[i]] += 1;
+  }
+  h->prof_used = 0;
+  h->prof_ids.clear();
+  return MC_OK;
+}
 
 int rows_per_band(int hout) { return hout >= 56 ? 8 : (hout == 28 ? 7 : hout); }
 
@@ -129,18 +178,27 @@ int launch_dw(mc_extractor* h, const BlockCfg& b, const T* in, T* out, int nb, c
   int pt = std::max(1, std::min(256 / cgt, npos));
   dim3 block(cgt, pt), grid(nbands, nb);
   const size_t smem = (size_t)pt * C * sizeof(float);
+  const int bidx = (int)(&b - &h->net.blocks[0]);
+  ProfScope* ps_dw = new ProfScope(h, 2 + 4 * bidx, st);
 #define DW_ARGS in, P + b.w_dw, P + b.s_dw, P + b.b_dw, out, h->d_pool, C, b.h_in, b.h_out, b.pad, rpb, nbands
   if (b.k == 3 && b.stride == 1) dwconv_kernel<T, 3, 1, TW><<<grid, block, smem, st>>>(DW_ARGS);
   else if (b.k == 3 && b.stride == 2) dwconv_kernel<T, 3, 2, TW><<<grid, block, smem, st>>>(DW_ARGS);
   else if (b.k == 5 && b.stride == 1) dwconv_kernel<T, 5, 1, TW><<<grid, block, smem, st>>>(DW_ARGS);
   else if (b.k == 5 && b.stride == 2) dwconv_kernel<T, 5, 2, TW><<<grid, block, smem, st>>>(DW_ARGS);
-  else return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
+  else {
+    delete ps_dw;
+    return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
+  }
 #undef DW_ARGS
+  delete ps_dw;
   MC_CHECK_LAUNCH();
   h->launches++;
-  se_kernel<<<nb, 256, (C + b.c_se) * sizeof(float), st>>>(h->d_pool, nbands, 1.f / (float)(b.h_out * b.h_out),
-                                                          P + b.w_se1, P + b.b_se1, P + b.w_se2, P + b.b_se2,
-                                                          h->d_gate, C, b.c_se);
+  {
+    ProfScope ps(h, 3 + 4 * bidx, st);
+    se_kernel<<<nb, 256, (C + b.c_se) * sizeof(float), st>>>(h->d_pool, nbands, 1.f / (float)(b.h_out * b.h_out),
+                                                            P + b.w_se1, P + b.b_se1, P + b.w_se2, P + b.b_se2,
+                                                            h->d_gate, C, b.c_se);
+  }
   MC_CHECK_LAUNCH();
   h->launches++;
   return MC_OK;
@@ -178,8 +236,11 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
   T* D = (T*)h->bufD;
   T* Hb = (T*)h->bufH;
   int rc;
-  stem_kernel<T><<<dim3(49, nb), 256, 0, st>>>(h->d_images, h->d_points, P + net.w_stem, P + net.s_stem,
-                                               P + net.b_stem, h->d_lut, X);
+  {
+    ProfScope ps(h, 0, st);
+    stem_kernel<T><<<dim3(49, nb), 256, 0, st>>>(h->d_images, h->d_points, P + net.w_stem, P + net.s_stem,
+                                                 P + net.b_stem, h->d_lut, X);
+  }
   MC_CHECK_LAUNCH();
   h->launches++;
   if ((rc = tap<T>(h, 0, X, (int64_t)nb * 112 * 112 * 32, st))) return rc;
@@ -188,6 +249,7 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
     const int64_t Min = (int64_t)nb * b.h_in * b.h_in, Mout = (int64_t)nb * b.h_out * b.h_out;
     const T* dw_in = X;
     if (b.expand != 1) {
+      ProfScope ps(h, 1 + 4 * (int)bi, st);
       if (h->tc && pw_tc_has(h->tc, (int)bi * 2)) {
         if ((rc = pw_tc_run(h->tc, (int)bi * 2, X, nullptr, nullptr, E, Min, b.h_in * b.h_in, st))) return rc;
         h->launches++;
@@ -195,12 +257,13 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
                                                                  nullptr, E, Min, b.c_mid, b.c_in, 1, st)))
         return rc;
       dw_in = E;
-      if ((rc = tap<T>(h, 1 + 4 * (int)bi, E, Min * b.c_mid, st))) return rc;
     }
+    if (b.expand != 1 && (rc = tap<T>(h, 1 + 4 * (int)bi, E, Min * b.c_mid, st))) return rc;
     if ((rc = launch_dw<T>(h, b, dw_in, D, nb, st))) return rc;
     if ((rc = tap<T>(h, 2 + 4 * (int)bi, D, Mout * b.c_mid, st))) return rc;
     if ((rc = tap<float>(h, 3 + 4 * (int)bi, h->d_gate, (int64_t)nb * b.c_mid, st))) return rc;
     const int HW = b.h_out * b.h_out;
+    ProfScope ps_proj(h, 4 + 4 * (int)bi, st);
     if (h->tc && pw_tc_has(h->tc, (int)bi * 2 + 1)) {
       if ((rc = pw_tc_run(h->tc, (int)bi * 2 + 1, D, h->d_gate, b.skip ? X : nullptr, Y, Mout, HW, st))) return rc;
       h->launches++;
@@ -213,18 +276,26 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
                                                          nullptr, Y, Mout, b.c_out, b.c_mid, HW, st)))
         return rc;
     }
+    ps_proj.~ProfScope();
+    ps_proj.on = false;
     if ((rc = tap<T>(h, 4 + 4 * (int)bi, Y, Mout * b.c_out, st))) return rc;
     std::swap(X, Y);
   }
   const int64_t Mh = (int64_t)nb * 49;
+  ProfScope ps_head(h, 65, st);
   if (h->tc && pw_tc_has(h->tc, 32)) {
     if ((rc = pw_tc_run(h->tc, 32, X, nullptr, nullptr, Hb, Mh, 49, st))) return rc;
     h->launches++;
   } else if ((rc = launch_pw_simt<T, ACT_SILU, false, false>(h, X, P + net.w_head, P + net.s_head, P + net.b_head,
                                                              nullptr, nullptr, Hb, Mh, 1280, 320, 1, st)))
     return rc;
+  ps_head.~ProfScope();
+  ps_head.on = false;
   if ((rc = tap<T>(h, 65, Hb, Mh * 1280, st))) return rc;
-  avgpool_kernel<T><<<dim3(cdiv(1280, 128), nb), 128, 0, st>>>(Hb, feats_dev, 49, 1280);
+  {
+    ProfScope ps(h, 66, st);
+    avgpool_kernel<T><<<dim3(cdiv(1280, 128), nb), 128, 0, st>>>(Hb, feats_dev, 49, 1280);
+  }
   MC_CHECK_LAUNCH();
   h->launches++;
   return MC_OK;
@@ -367,7 +438,12 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
     mc_extractor_destroy(h);
     return fail(MC_ERR_CUDA, std::string("parameter upload: ") + cudaGetErrorString(e));
   }
-  if ((rc = pw_tc_build(&h->tc, h->net, params, mode, max_batch, device))) {
+  // MC_TC_MASK (hex, bit 2b = expand of block b, 2b+1 = project, 32 = head conv) selects which 1x1
+  // convs run on the tcgen05 kernel; default: all of them.  Bring-up / bisecting aid only.
+  unsigned long long tc_mask = ~0ull;
+  if (const char* env = getenv("MC_TC_MASK")) tc_mask = strtoull(env, nullptr, 16);
+  if ((rc = pw_tc_build(&h->tc, h->net, params, h->d_params, mode, max_batch, device, (unsigned)(tc_mask & 0xffffffffu),
+                        (unsigned)(tc_mask >> 32)))) {
     mc_extractor_destroy(h);
     return rc;
   }
@@ -379,6 +455,7 @@ int mc_extractor_destroy(mc_extractor* h) {
   if (!h) return MC_OK;
   DeviceGuard g(h->device);
   pw_tc_free(h->tc);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   void* ptrs[] = {h->d_params, h->d_lut, h->bufX, h->bufY,    h->bufE, h->bufD,
                   h->bufH,     h->d_pool, h->d_gate, h->d_images, h->d_points, h->d_img, h->d_feats};
   for (void* p : ptrs)
@@ -389,6 +466,26 @@ int mc_extractor_destroy(mc_extractor* h) {
 
 int mc_extractor_mode(const mc_extractor* h) { return h ? h->mode : -1; }
 int64_t mc_extractor_launches(const mc_extractor* h) { return h ? h->launches : 0; }
+
+int mc_extractor_profile(mc_extractor* h, int32_t layer) {
+  if (!h) return fail(MC_ERR_BAD_ARG, "null handle");
+  if (layer < -2 || layer >= MC_N_LAYERS) return fail(MC_ERR_BAD_ARG, "mc_extractor_profile: bad layer");
+  h->prof_layer = layer;
+  return MC_OK;
+}
+
+int mc_extractor_profile_read(mc_extractor* h, double* ms_out, int64_t* count_out, int32_t reset) {
+  if (!h || !ms_out || !count_out) return fail(MC_ERR_BAD_ARG, "null argument");
+  for (int i = 0; i < MC_N_LAYERS; ++i) {
+    ms_out[i] = h->prof_ms[i];
+    count_out[i] = h->prof_cnt[i];
+    if (reset) {
+      h->prof_ms[i] = 0;
+      h->prof_cnt[i] = 0;
+    }
+  }
+  return MC_OK;
+}
 
 int mc_extractor_set_tap(mc_extractor* h, int32_t layer, float* out_dev, int64_t capacity) {
   if (!h) return fail(MC_ERR_BAD_ARG, "null handle");
@@ -418,7 +515,7 @@ int mc_extract_points(mc_extractor* h, const mc_image* images, int32_t n_images,
     h->d_points = base;
     if (rc) return rc;
   }
-  return MC_OK;
+  return prof_collect(h, st);
 }
 
 int mc_extract_patches(mc_extractor* h, const uint8_t* patches_dev, int64_t n, float* feats_dev, void* stream) {

@@ -1,17 +1,649 @@
-// tcgen05 / TMEM / TMA pointwise GEMM (placeholder until the tensor-core path lands).
+// Pointwise (1x1 conv) GEMM on the 5th-generation tensor cores: tcgen05.mma with TMEM
+// accumulators, operands staged by TMA into 128B-swizzled shared memory.
+//
+//   out[m][n] = act( (sum_k A[m][k] * gate[m / HW][k] * W[n][k]) * scale[n] + bias[n] ) + res[m][n]
+//
+// A is the NHWC activation matrix (M = patches*H*W rows, K = C_in, K-major), W the conv weight
+// (N = C_out rows, K-major).  One persistent CTA per SM walks (m-tile, n-block) work items:
+//
+//   warp 0      TMA producer: A [128 x KC] and W [BN x KC] boxes into a ring of stages
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma.cta_group::1, M = 128, N = BN,
+//               accumulating over the K chunks into one of two TMEM accumulator stages
+//   warps 2-5   operand transform (only when needed): SE gate applied to the A tile in shared
+//               memory (project convs) and, in fp32 mode, the 3xTF32 split a = hi + lo
+//   warps 6-13  epilogue, two groups of four warps alternating over the TMEM stages:
+//               tcgen05.ld -> BN-fold scale/bias -> swish -> (+ residual) -> 16-byte stores
+//
+// bf16 mode: kind::f16 (bf16 x bf16 -> fp32), KC = 64.  fp32 mode: kind::tf32 with the
+// 3-term split  A_hi W_hi + A_lo W_hi + A_hi W_lo  (error ~2^-21, fp32-class), KC = 32.
+//
+// Every mbarrier wait carries a clock-based timeout that traps, so a protocol bug faults the
+// launch instead of hanging the GPU.
 #pragma once
+#include <cuda.h>
+
+#include <vector>
+
 #include "common.cuh"
 #include "layers.h"
 
 namespace mc {
-struct PwTcPlan {};
-inline int pw_tc_build(PwTcPlan** out, const NetCfg&, const float*, int, int, int) {
-  *out = nullptr;
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: ~4 s at 2 GHz, then trap (a faulted launch, never a hung GPU).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+template <bool TF32>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// mbarrier arrives when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base + t), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+}  // namespace ptx
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row (1024 B) swizzle atoms stacked
+// along M/N.  start address >> 4 | LBO(ignored)=1 | SBO = 1024 >> 4 | version 1 | SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 14 * 32;
+constexpr int TC_BM = 128;
+constexpr int TC_ACC_COLS = 256;  // TMEM columns per accumulator stage (2 stages = 512)
+
+struct PwTcArgs {
+  const float* scale;
+  const float* bias;
+  const float* gate;  // [n_img][K] or null
+  const void* res;    // [M][N] or null
+  void* out;          // [M][N]
+  int64_t M;
+  int N, K, HW, BN, n_blocks, k_chunks, act;
+  int64_t m_tiles;
+};
+
+template <typename T>
+struct TcCfg;
+template <>
+struct TcCfg<__nv_bfloat16> {
+  static constexpr bool TF32 = false;
+  static constexpr int KC = 64;       // elements per 128-byte row
+  static constexpr int UK = 16;       // K per MMA
+  static constexpr int BN_MAX = 256;
+  static constexpr int STAGES = 4;
+  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int W_BYTES = BN_MAX * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr uint32_t FMT = 1;  // BF16
+};
+template <>
+struct TcCfg<float> {
+  static constexpr bool TF32 = true;
+  static constexpr int KC = 32;
+  static constexpr int UK = 8;
+  static constexpr int BN_MAX = 128;
+  static constexpr int STAGES = 3;
+  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int W_BYTES = BN_MAX * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;  // A_hi, A_lo, W_hi, W_lo
+  static constexpr uint32_t FMT = 2;  // TF32
+};
+
+template <typename T>
+constexpr size_t tc_smem_bytes() {
+  return 1024 /*align slack*/ + (size_t)TcCfg<T>::STAGES * TcCfg<T>::STAGE_BYTES + 2 * 1280 * sizeof(float) + 256;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+             const __grid_constant__ CUtensorMap tmWlo, const PwTcArgs p) {
+  using Cfg = TcCfg<T>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  float* sc_s = (float*)(smem + (size_t)S * Cfg::STAGE_BYTES);
+  float* bi_s = sc_s + 1280;
+  uint64_t* bars = (uint64_t*)(bi_s + 1280);
+  uint64_t* full = bars;            // [S]   TMA landed
+  uint64_t* ready = bars + S;       // [S]   transform done (when a transform runs)
+  uint64_t* empty = bars + 2 * S;   // [S]   MMAs reading the stage retired
+  uint64_t* tfull = bars + 3 * S;   // [2]   accumulator complete
+  uint64_t* tempty = tfull + 2;     // [2]   accumulator drained
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool transform = Cfg::TF32 || p.gate != nullptr;
+  const int64_t items = p.m_tiles * p.n_blocks;
+
+  for (int i = threadIdx.x; i < p.N; i += TC_THREADS) {
+    sc_s[i] = p.scale[i];
+    bi_s[i] = p.bias[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&ready[s], 128);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 128);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    if (Cfg::TF32) ptx::prefetch_tmap(&tmWlo);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = Cfg::A_BYTES + (uint32_t)p.BN * 128u * (Cfg::TF32 ? 2u : 1u);
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int m0 = (int)(it / p.n_blocks) * TC_BM;
+        const int n0 = (int)(it % p.n_blocks) * p.BN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = stage_base + (size_t)s * Cfg::STAGE_BYTES;
+          ptx::mbar_expect_tx(&full[s], tx);
+          ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, m0);
+          if (Cfg::TF32) {
+            ptx::tma_load_2d(st + 2 * Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
+            ptx::tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &tmWlo, &full[s], kc * Cfg::KC, n0);
+          } else {
+            ptx::tma_load_2d(st + Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
+          }
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (Cfg::FMT << 7) | (Cfg::FMT << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int64_t li = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++li) {
+        const int as = (int)(li & 1);
+        const uint32_t use = (uint32_t)(li >> 1);
+        ptx::mbar_wait(&tempty[as], (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * TC_ACC_COLS;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          ptx::mbar_wait(transform ? &ready[s] : &full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
+          const int krem = p.K - kc * Cfg::KC;
+          const int ksteps = (min(krem, Cfg::KC) + Cfg::UK - 1) / Cfg::UK;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t acc = (kc | ks) != 0;
+            const uint32_t koff = (uint32_t)ks * 32u;  // UK elements = 32 bytes
+            if (Cfg::TF32) {
+              const uint64_t ahi = umma_desc_sw128(a_addr + koff);
+              const uint64_t alo = umma_desc_sw128(a_addr + Cfg::A_BYTES + koff);
+              const uint64_t whi = umma_desc_sw128(a_addr + 2 * Cfg::A_BYTES + koff);
+              const uint64_t wlo = umma_desc_sw128(a_addr + 2 * Cfg::A_BYTES + Cfg::W_BYTES + koff);
+              ptx::mma_ss<true>(d_tmem, alo, whi, idesc, acc);
+              ptx::mma_ss<true>(d_tmem, ahi, wlo, idesc, 1u);
+              ptx::mma_ss<true>(d_tmem, ahi, whi, idesc, 1u);
+            } else {
+              ptx::mma_ss<false>(d_tmem, umma_desc_sw128(a_addr + koff), umma_desc_sw128(a_addr + Cfg::A_BYTES + koff),
+                                 idesc, acc);
+            }
+          }
+          ptx::mma_commit(&empty[s]);
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        ptx::mma_commit(&tfull[as]);
+      }
+    }
+  } else if (warp < 6) {
+    // ============================ operand transform ================================
+    if (transform) {
+      const int r = threadIdx.x - 64;  // tile row owned by this thread
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int64_t m = (it / p.n_blocks) * TC_BM + r;
+        const float* grow = (p.gate != nullptr && m < p.M) ? p.gate + (m / p.HW) * p.K : nullptr;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          ptx::mbar_wait(&full[s], ph);
+          uint8_t* a_hi = stage_base + (size_t)s * Cfg::STAGE_BYTES + (size_t)r * 128;
+          const int k0 = kc * Cfg::KC;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // eight 16-byte chunks per 128-byte row
+            const int phys = (j ^ (r & 7)) * 16;
+            uint4 raw = *reinterpret_cast<uint4*>(a_hi + phys);
+            if (Cfg::TF32) {
+              float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+              const int k = k0 + j * 4;
+              if (grow != nullptr && k < p.K) {
+                const float4 g = *reinterpret_cast<const float4*>(grow + k);
+                v[0] *= g.x; v[1] *= g.y; v[2] *= g.z; v[3] *= g.w;
+              }
+              uint4 hi, lo;
+              uint32_t* hp = &hi.x;
+              uint32_t* lp = &lo.x;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t hbits = __float_as_uint(v[e]) & 0xFFFFE000u;  // exact TF32 value
+                hp[e] = hbits;
+                lp[e] = __float_as_uint(v[e] - __uint_as_float(hbits));      // exact remainder
+              }
+              *reinterpret_cast<uint4*>(a_hi + phys) = hi;
+              *reinterpret_cast<uint4*>(a_hi + Cfg::A_BYTES + phys) = lo;
+            } else {
+              const int k = k0 + j * 8;
+              if (grow != nullptr && k < p.K) {
+                const float4 g0 = *reinterpret_cast<const float4*>(grow + k);
+                const float4 g1 = *reinterpret_cast<const float4*>(grow + k + 4);
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+                float2 f;
+                f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
+                f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
+                f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
+                f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
+                *reinterpret_cast<uint4*>(a_hi + phys) = raw;
+              }
+            }
+          }
+          ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+          ptx::mbar_arrive(&ready[s]);
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ================================== epilogue ====================================
+    const int eg = (warp - 6) >> 2;   // epilogue group 0/1 <-> accumulator stage
+    const int quarter = warp & 3;     // TMEM lanes 32*quarter .. +31 are visible to this warp
+    const int row = quarter * 32 + lane;
+    int64_t li = 0;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++li) {
+      if ((int)(li & 1) != eg) continue;
+      const uint32_t use = (uint32_t)(li >> 1);
+      const int64_t m = (it / p.n_blocks) * TC_BM + row;
+      const int n0 = (int)(it % p.n_blocks) * p.BN;
+      ptx::mbar_wait(&tfull[eg], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)eg * TC_ACC_COLS;
+      const int ncols = min(p.BN, p.N - n0);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr + (uint32_t)c0, v);
+        if (m < p.M) {
+          const int n = n0 + c0;
+          const int valid = min(32, p.N - n);  // multiple of 8
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int nn = min(n + j, p.N - 1);
+            float t = fmaf(__uint_as_float(v[j]), sc_s[nn], bi_s[nn]);
+            if (p.act == 1) {
+              if (Cfg::TF32) t = t / (1.f + __expf(-t));
+              else t = 0.5f * t * (1.f + ptx::tanh_approx(0.5f * t));
+            }
+            y[j] = t;
+          }
+          if (Cfg::TF32) {
+            float* o = (float*)p.out + m * p.N + n;
+            const float* rs = p.res ? (const float*)p.res + m * p.N + n : nullptr;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q * 4 < valid) {
+                float4 w4 = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                if (rs) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(rs + 4 * q);
+                  w4.x += r4.x; w4.y += r4.y; w4.z += r4.z; w4.w += r4.w;
+                }
+                *reinterpret_cast<float4*>(o + 4 * q) = w4;
+              }
+            }
+          } else {
+            __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.N + n;
+            const __nv_bfloat16* rs = p.res ? (const __nv_bfloat16*)p.res + m * p.N + n : nullptr;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < valid) {
+                if (rs) {
+                  const uint4 r4 = *reinterpret_cast<const uint4*>(rs + 8 * q);
+                  const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(rh[e]);
+                    y[8 * q + 2 * e] += f.x;
+                    y[8 * q + 2 * e + 1] += f.y;
+                  }
+                }
+                uint4 w4;
+                __nv_bfloat162* wh = reinterpret_cast<__nv_bfloat162*>(&w4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) wh[e] = __floats2bfloat162_rn(y[8 * q + 2 * e], y[8 * q + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(o + 8 * q) = w4;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty[eg]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: per-layer plans (tensor maps + arguments)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// 2-D K-major map: dim0 = K (contiguous), dim1 = rows; box = (128 bytes of K) x box_rows; 128B swizzle; OOB -> 0.
+inline int make_map(CUtensorMap* map, bool f32, const void* base, int64_t rows, int K, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int es = f32 ? 4 : 2;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)K * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return MC_OK;
 }
-inline void pw_tc_free(PwTcPlan*) {}
-inline bool pw_tc_has(const PwTcPlan*, int) { return false; }
-inline int pw_tc_run(PwTcPlan*, int, const void*, const float*, const void*, void*, int64_t, int, cudaStream_t) {
-  return fail(MC_ERR_UNSUPPORTED, "tcgen05 path not built");
+
+struct PwTcLayer {
+  bool present = false;
+  int N = 0, K = 0, BN = 0, n_blocks = 0, k_chunks = 0, act = 0;
+  bool gated = false;
+  void* d_w = nullptr;    // bf16 weights, or fp32 hi part
+  void* d_wlo = nullptr;  // fp32 lo part
+  const float *scale = nullptr, *bias = nullptr;  // into the extractor's parameter blob
+  CUtensorMap tmW, tmWlo;
+  // activation maps are cached per source pointer (the ping-pong buffers alternate)
+  const void* a_ptr[2] = {nullptr, nullptr};
+  CUtensorMap tmA[2];
+};
+
+struct PwTcPlan {
+  int mode = 0, device = 0, num_sms = 148, max_batch = 0;
+  std::vector<PwTcLayer> layers;  // 2*b = expand of block b, 2*b+1 = project, 32 = head conv
+};
+
+inline bool pw_tc_has(const PwTcPlan* p, int id) { return p && id < (int)p->layers.size() && p->layers[id].present; }
+
+inline void pw_tc_free(PwTcPlan* p) {
+  if (!p) return;
+  for (auto& l : p->layers) {
+    if (l.d_w) cudaFree(l.d_w);
+    if (l.d_wlo) cudaFree(l.d_wlo);
+  }
+  delete p;
 }
+
+inline int pick_bn(int N, int bn_max) {
+  // smallest number of equal blocks with BN a multiple of 16 and <= bn_max
+  const int n16 = (N + 15) / 16 * 16;
+  int blocks = (n16 + bn_max - 1) / bn_max;
+  int bn = ((n16 / 16 + blocks - 1) / blocks) * 16;
+  return bn;
+}
+
+inline int pw_tc_add(PwTcPlan* plan, int id, const float* w_host, const float* d_scale, const float* d_bias, int N, int K,
+                     int act, bool gated) {
+  PwTcLayer& l = plan->layers[id];
+  const bool f32 = plan->mode == MC_MODE_FP32;
+  l.N = N;
+  l.K = K;
+  l.act = act;
+  l.gated = gated;
+  l.scale = d_scale;
+  l.bias = d_bias;
+  l.BN = pick_bn(N, f32 ? TcCfg<float>::BN_MAX : TcCfg<__nv_bfloat16>::BN_MAX);
+  l.n_blocks = (N + l.BN - 1) / l.BN;
+  const int kc = f32 ? TcCfg<float>::KC : TcCfg<__nv_bfloat16>::KC;
+  l.k_chunks = (K + kc - 1) / kc;
+  const size_t n = (size_t)N * K;
+  int rc;
+  if (f32) {
+    std::vector<float> hi(n), lo(n);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t bits;
+      memcpy(&bits, &w_host[i], 4);
+      bits &= 0xFFFFE000u;
+      float h;
+      memcpy(&h, &bits, 4);
+      hi[i] = h;
+      lo[i] = w_host[i] - h;
+    }
+    MC_CUDA(cudaMalloc(&l.d_w, n * 4));
+    MC_CUDA(cudaMalloc(&l.d_wlo, n * 4));
+    MC_CUDA(cudaMemcpy(l.d_w, hi.data(), n * 4, cudaMemcpyHostToDevice));
+    MC_CUDA(cudaMemcpy(l.d_wlo, lo.data(), n * 4, cudaMemcpyHostToDevice));
+    if ((rc = make_map(&l.tmW, true, l.d_w, N, K, l.BN)) || (rc = make_map(&l.tmWlo, true, l.d_wlo, N, K, l.BN))) return rc;
+  } else {
+    std::vector<__nv_bfloat16> wb(n);
+    for (size_t i = 0; i < n; ++i) wb[i] = __float2bfloat16_rn(w_host[i]);
+    MC_CUDA(cudaMalloc(&l.d_w, n * 2));
+    MC_CUDA(cudaMemcpy(l.d_w, wb.data(), n * 2, cudaMemcpyHostToDevice));
+    if ((rc = make_map(&l.tmW, false, l.d_w, N, K, l.BN))) return rc;
+    l.tmWlo = l.tmW;
+  }
+  l.present = true;
+  return MC_OK;
+}
+
+// `params_host` is the packed blob (csrc/layers.h); scale/bias pointers index the device copy.
+inline int pw_tc_build(PwTcPlan** out, const NetCfg& net, const float* params_host, const float* d_params, int mode,
+                       int max_batch, int device, unsigned layer_mask_lo, unsigned layer_mask_hi) {
+  *out = nullptr;
+  PwTcPlan* plan = new PwTcPlan();
+  plan->mode = mode;
+  plan->device = device;
+  cudaDeviceProp prop;
+  MC_CUDA(cudaGetDeviceProperties(&prop, device));
+  plan->num_sms = prop.multiProcessorCount;
+  plan->layers.resize(33);
+  const bool f32 = mode == MC_MODE_FP32;
+  if (f32) {
+    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<float>()));
+  } else {
+    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tc_smem_bytes<__nv_bfloat16>()));
+  }
+  auto enabled = [&](int id) { return id < 32 ? ((layer_mask_lo >> id) & 1u) != 0 : ((layer_mask_hi >> (id - 32)) & 1u) != 0; };
+  int rc = MC_OK;
+  for (size_t bi = 0; bi < net.blocks.size() && rc == MC_OK; ++bi) {
+    const BlockCfg& b = net.blocks[bi];
+    if (b.expand != 1 && enabled((int)bi * 2))
+      rc = pw_tc_add(plan, (int)bi * 2, params_host + b.w_exp, d_params + b.s_exp, d_params + b.b_exp, b.c_mid, b.c_in, 1, false);
+    if (rc == MC_OK && enabled((int)bi * 2 + 1))
+      rc = pw_tc_add(plan, (int)bi * 2 + 1, params_host + b.w_proj, d_params + b.s_proj, d_params + b.b_proj, b.c_out, b.c_mid,
+                     0, true);
+  }
+  if (rc == MC_OK && enabled(32))
+    rc = pw_tc_add(plan, 32, params_host + net.w_head, d_params + net.s_head, d_params + net.b_head, 1280, 320, 1, false);
+  if (rc != MC_OK) {
+    pw_tc_free(plan);
+    return rc;
+  }
+  plan->max_batch = max_batch;
+  *out = plan;
+  return MC_OK;
+}
+
+inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, const float* gate, const void* res, void* outp, int64_t M, int HW,
+                     cudaStream_t st) {
+  PwTcLayer& l = plan->layers[id];
+  const bool f32 = plan->mode == MC_MODE_FP32;
+  // tensor map of the activation source (cached: each layer only ever sees the ping-pong buffers)
+  int slot = -1;
+  for (int i = 0; i < 2; ++i)
+    if (l.a_ptr[i] == A) slot = i;
+  if (slot < 0) {
+    slot = l.a_ptr[0] == nullptr ? 0 : 1;
+    // rows = the buffer's capacity for this layer: rows past it are zero-filled by TMA, never read
+    int rc = make_map(&l.tmA[slot], f32, A, (int64_t)plan->max_batch * HW, l.K, TC_BM);
+    if (rc) return rc;
+    l.a_ptr[slot] = A;
+  }
+  PwTcArgs a;
+  a.scale = l.scale;
+  a.bias = l.bias;
+  a.gate = l.gated ? gate : nullptr;
+  a.res = res;
+  a.out = outp;
+  a.M = M;
+  a.N = l.N;
+  a.K = l.K;
+  a.HW = HW;
+  a.BN = l.BN;
+  a.n_blocks = l.n_blocks;
+  a.k_chunks = l.k_chunks;
+  a.act = l.act;
+  a.m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int64_t items = a.m_tiles * a.n_blocks;
+  const int grid = (int)std::min<int64_t>(items, plan->num_sms);
+  if (f32)
+    pw_tc_kernel<float><<<grid, TC_THREADS, tc_smem_bytes<float>(), st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+  else
+    pw_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, tc_smem_bytes<__nv_bfloat16>(), st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+  MC_CHECK_LAUNCH();
+  return MC_OK;
+}
+
 }  // namespace mc
