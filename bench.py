@@ -289,14 +289,25 @@ def run_b200(args, rank: int, world: int, local: int):
     value = world * n_patches * args.steps / (ms_total / 1e3)
     e2e_value = world * n_patches * args.steps / (ms_e2e / 1e3)
 
-    peak, peak_src = measured_peaks()
     dom_name, dom_bytes = lbytes.get(dominant, (f"layer{dominant}", 0.0))
     dom_launches = max(int(cnt_dom[dominant]), 1)
     dom_ms = float(ms_dom[dominant]) / dom_launches
     patches_per_launch = n_patches * args.steps / dom_launches
     achieved = dom_bytes * patches_per_launch / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     share = float(ms_all[dominant] / ms_all.sum()) if ms_all.sum() > 0 else 0.0
+    peak, peak_src = measured_peaks()
     table = sorted(((float(ms_all[i]), lbytes.get(i, (str(i), 0))[0]) for i in range(67) if ms_all[i] > 0), reverse=True)
+    if args.profile_out:
+        rows = ["layer_id,name,ms_per_step,launches,algorithmic_MB_per_patch,achieved_GBps,frac_of_hbm_peak,share_of_profiled_time"]
+        for i in range(67):
+            if cnt_all[i] == 0:
+                continue
+            name, by = lbytes.get(i, (str(i), 0.0))
+            gbps = by * n_patches / (ms_all[i] / 1e3) / 1e9 if ms_all[i] > 0 else 0.0
+            rows.append(f"{i},{name},{ms_all[i]:.3f},{cnt_all[i]},{by / 1e6:.4f},{gbps:.1f},{gbps / peak:.4f},{ms_all[i] / ms_all.sum():.4f}")
+        rows.append(f"total,,{ms_all.sum():.3f},{int(cnt_all.sum())},{sum(v[1] for v in lbytes.values()) / 1e6:.4f},"
+                    f"{sum(v[1] for v in lbytes.values()) * n_patches / (ms_all.sum() / 1e3) / 1e9:.1f},,1.0")
+        Path(args.profile_out).write_text("\n".join(rows) + "\n")
 
     line = {
         "metric": METRIC, "value": value, "unit": "point-patches/s", "n_gpus": world, "steps": args.steps,
@@ -399,6 +410,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=3, help="images timed by the cpu_baseline leg")
     ap.add_argument("--ref-images", type=int, default=1, help="images per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-layer CUDA-event table (one profiled warm-up step) here")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if args.warmup < 3 and args.impl == "b200":

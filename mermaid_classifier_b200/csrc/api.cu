@@ -96,6 +96,7 @@ struct mc_extractor {
   float* d_lut = nullptr;
   void *bufX = nullptr, *bufY = nullptr, *bufE = nullptr, *bufD = nullptr, *bufH = nullptr;
   float *d_pool = nullptr, *d_gate = nullptr;
+  __nv_bfloat16* d_gate_h = nullptr;  // bf16 copy of the SE gate (bf16 mode)
   mc_image* d_images = nullptr;
   int64_t cap_images = 0;
   mc_point* d_points = nullptr;
@@ -162,42 +163,48 @@ int prof_collect(mc_extractor* h, cudaStream_t st) {
   return MC_OK;
 }
 
-int rows_per_band(int hout) { return hout >= 56 ? 8 : (hout == 28 ? 7 : hout); }
+// largest divisor of cg that is <= 64
+int pick_cgt(int cg) {
+  for (int d = std::min(cg, 64); d >= 1; --d)
+    if (cg % d == 0) return d;
+  return 1;
+}
 
 template <typename T>
 int launch_dw(mc_extractor* h, const BlockCfg& b, const T* in, T* out, int nb, cudaStream_t st) {
-  constexpr int VN = Vec<T>::N;
-  constexpr int TW = sizeof(T) == 4 ? 4 : 2;
   const float* P = h->d_params;
-  const int C = b.c_mid, CG = C / VN;
-  int cgt = CG;
-  while (cgt > 256) cgt /= 2;
-  const int rpb = rows_per_band(b.h_out);
-  const int nbands = cdiv(b.h_out, rpb);
-  const int npos = rpb * cdiv(b.h_out, TW);
-  int pt = std::max(1, std::min(256 / cgt, npos));
-  dim3 block(cgt, pt), grid(nbands, nb);
-  const size_t smem = (size_t)pt * C * sizeof(float);
+  const int C = b.c_mid;
   const int bidx = (int)(&b - &h->net.blocks[0]);
-  ProfScope* ps_dw = new ProfScope(h, 2 + 4 * bidx, st);
-#define DW_ARGS in, P + b.w_dw, P + b.s_dw, P + b.b_dw, out, h->d_pool, C, b.h_in, b.h_out, b.pad, rpb, nbands
-  if (b.k == 3 && b.stride == 1) dwconv_kernel<T, 3, 1, TW><<<grid, block, smem, st>>>(DW_ARGS);
-  else if (b.k == 3 && b.stride == 2) dwconv_kernel<T, 3, 2, TW><<<grid, block, smem, st>>>(DW_ARGS);
-  else if (b.k == 5 && b.stride == 1) dwconv_kernel<T, 5, 1, TW><<<grid, block, smem, st>>>(DW_ARGS);
-  else if (b.k == 5 && b.stride == 2) dwconv_kernel<T, 5, 2, TW><<<grid, block, smem, st>>>(DW_ARGS);
-  else {
-    delete ps_dw;
-    return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
-  }
+  int nparts = 0;
+  {
+    ProfScope ps_dw(h, 2 + 4 * bidx, st);
+    // rolling-accumulator kernel: 4-channel groups, channel-sliced CTAs
+    const int CG = C / 4, cgt = pick_cgt(CG), cz = CG / cgt;
+    const int TW = 2;
+    const int nstrips = cdiv(b.h_out, TW);
+    const int pt_max = std::max(1, std::min(nstrips, 256 / cgt));
+    const int nx = cdiv(nstrips, pt_max);
+    const int pt = cdiv(nstrips, nx);  // balanced strip chunks (no mostly-idle trailing CTA)
+    const int rpb = b.h_out >= 112 ? 16 : (b.h_out >= 56 ? 14 : b.h_out);
+    const int nbands = cdiv(b.h_out, rpb);
+    nparts = nbands * nx;
+    dim3 block(cgt, pt), grid(nparts, nb, cz);
+    const size_t smem = ((size_t)b.k * b.k * cgt * 4 + (size_t)pt * cgt * 4) * sizeof(float);
+#define DW_ARGS in, P + b.w_dw, P + b.s_dw, P + b.b_dw, out, h->d_pool, C, b.h_in, b.h_out, b.pad, rpb, nx
+    if (b.k == 3 && b.stride == 1) dwconv_roll_kernel<T, 3, 1, 2><<<grid, block, smem, st>>>(DW_ARGS);
+    else if (b.k == 5 && b.stride == 1) dwconv_roll_kernel<T, 5, 1, 2><<<grid, block, smem, st>>>(DW_ARGS);
+    else if (b.k == 3 && b.stride == 2) dwconv_roll_kernel<T, 3, 2, 2><<<grid, block, smem, st>>>(DW_ARGS);
+    else if (b.k == 5 && b.stride == 2) dwconv_roll_kernel<T, 5, 2, 2><<<grid, block, smem, st>>>(DW_ARGS);
+    else return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
 #undef DW_ARGS
-  delete ps_dw;
+  }
   MC_CHECK_LAUNCH();
   h->launches++;
   {
     ProfScope ps(h, 3 + 4 * bidx, st);
-    se_kernel<<<nb, 256, (C + b.c_se) * sizeof(float), st>>>(h->d_pool, nbands, 1.f / (float)(b.h_out * b.h_out),
+    se_kernel<<<nb, 256, (C + b.c_se) * sizeof(float), st>>>(h->d_pool, nparts, 1.f / (float)(b.h_out * b.h_out),
                                                             P + b.w_se1, P + b.b_se1, P + b.w_se2, P + b.b_se2,
-                                                            h->d_gate, C, b.c_se);
+                                                            h->d_gate, h->d_gate_h, C, b.c_se);
   }
   MC_CHECK_LAUNCH();
   h->launches++;
@@ -265,7 +272,8 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
     const int HW = b.h_out * b.h_out;
     ProfScope ps_proj(h, 4 + 4 * (int)bi, st);
     if (h->tc && pw_tc_has(h->tc, (int)bi * 2 + 1)) {
-      if ((rc = pw_tc_run(h->tc, (int)bi * 2 + 1, D, h->d_gate, b.skip ? X : nullptr, Y, Mout, HW, st))) return rc;
+      const void* gp = h->mode == MC_MODE_BF16 ? (const void*)h->d_gate_h : (const void*)h->d_gate;
+      if ((rc = pw_tc_run(h->tc, (int)bi * 2 + 1, D, gp, b.skip ? X : nullptr, Y, Mout, HW, st))) return rc;
       h->launches++;
     } else if (b.skip) {
       if ((rc = launch_pw_simt<T, ACT_NONE, true, true>(h, D, P + b.w_proj, P + b.s_proj, P + b.b_proj, h->d_gate, X, Y,
@@ -428,7 +436,8 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
       (rc = dmalloc(&h->bufE, nb * net.max_mid * es)) || (rc = dmalloc(&h->bufD, nb * net.max_dw * es)) ||
       (rc = dmalloc(&h->bufH, nb * 49 * 1280 * es)) ||
       (rc = dmalloc((void**)&h->d_pool, nb * MAX_BANDS * net.max_c_mid * sizeof(float))) ||
-      (rc = dmalloc((void**)&h->d_gate, nb * net.max_c_mid * sizeof(float)))) {
+      (rc = dmalloc((void**)&h->d_gate, nb * net.max_c_mid * sizeof(float))) ||
+      (mode == MC_MODE_BF16 && (rc = dmalloc((void**)&h->d_gate_h, nb * net.max_c_mid * sizeof(__nv_bfloat16))))) {
     mc_extractor_destroy(h);
     return rc;
   }
@@ -457,7 +466,7 @@ int mc_extractor_destroy(mc_extractor* h) {
   pw_tc_free(h->tc);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   void* ptrs[] = {h->d_params, h->d_lut, h->bufX, h->bufY,    h->bufE, h->bufD,
-                  h->bufH,     h->d_pool, h->d_gate, h->d_images, h->d_points, h->d_img, h->d_feats};
+                  h->bufH,     h->d_pool, h->d_gate, h->d_gate_h, h->d_images, h->d_points, h->d_img, h->d_feats};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;

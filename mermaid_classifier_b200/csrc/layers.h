@@ -5,7 +5,7 @@
 //   block b (16 of them):
 //     expand (absent when expand_ratio == 1): W[c_mid][c_in], scale[c_mid], bias[c_mid]
 //     depthwise: W[k*k][c_mid], scale[c_mid], bias[c_mid]
-//     se_reduce: W[c_se][c_mid], b[c_se];  se_expand: W[c_mid][c_se], b[c_mid]
+//     se_reduce: W[c_se][c_mid], b[c_se];  se_expand: W^T[c_se][c_mid] (transposed), b[c_mid]
 //     project:   W[c_out][c_mid], scale[c_out], bias[c_out]
 //   head:   W[1280][320], scale[1280], bias[1280]
 // Every segment is zero-padded to a multiple of 4 floats so each starts 16-byte aligned.

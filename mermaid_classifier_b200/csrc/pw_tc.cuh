@@ -123,6 +123,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -141,18 +149,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // ---------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 14 * 32;
+constexpr int TC_EPI_GROUPS = 4;                       // epilogue warp groups (4 warps each)
+constexpr int TC_THREADS = (6 + 4 * TC_EPI_GROUPS) * 32;
 constexpr int TC_BM = 128;
 constexpr int TC_ACC_COLS = 256;  // TMEM columns per accumulator stage (2 stages = 512)
 
 struct PwTcArgs {
   const float* scale;
   const float* bias;
-  const float* gate;  // [n_img][K] or null
+  const void* gate;   // [n_img][K] (fp32 in fp32 mode, bf16 in bf16 mode) or null
   const void* res;    // [M][N] or null
   void* out;          // [M][N]
   int64_t M;
-  int N, K, HW, BN, n_blocks, k_chunks, act;
+  int N, K, HW, BN, n_blocks, k_chunks, act, stages;
   int64_t m_tiles;
 };
 
@@ -164,11 +173,10 @@ struct TcCfg<__nv_bfloat16> {
   static constexpr int KC = 64;       // elements per 128-byte row
   static constexpr int UK = 16;       // K per MMA
   static constexpr int BN_MAX = 256;
-  static constexpr int STAGES = 4;
   static constexpr int A_BYTES = TC_BM * 128;
-  static constexpr int W_BYTES = BN_MAX * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  static constexpr uint32_t FMT = 1;  // BF16
+  static constexpr int NA = 1, NW = 1;  // A / W operand copies per stage
+  static constexpr int EPI_COLS = 64;   // output columns staged per epilogue pass (128 bytes per row)
+  static constexpr uint32_t FMT = 1;    // BF16
 };
 template <>
 struct TcCfg<float> {
@@ -176,16 +184,26 @@ struct TcCfg<float> {
   static constexpr int KC = 32;
   static constexpr int UK = 8;
   static constexpr int BN_MAX = 128;
-  static constexpr int STAGES = 3;
   static constexpr int A_BYTES = TC_BM * 128;
-  static constexpr int W_BYTES = BN_MAX * 128;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;  // A_hi, A_lo, W_hi, W_lo
-  static constexpr uint32_t FMT = 2;  // TF32
+  static constexpr int NA = 2, NW = 2;  // A_hi, A_lo, W_hi, W_lo
+  static constexpr int EPI_COLS = 32;
+  static constexpr uint32_t FMT = 2;    // TF32
 };
 
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_BUDGET = 227 * 1024;
+constexpr int TC_EPI_BYTES = 4 * TC_EPI_GROUPS * 32 * 128;                      // one 32-row x 128-byte staging tile per epilogue warp
+constexpr int TC_FIXED_BYTES = 1024 /*align slack*/ + TC_EPI_BYTES + 2 * 1280 * 4 + 512;
+
+// bytes of one pipeline stage for a layer with BN output columns per block (1024-aligned)
 template <typename T>
-constexpr size_t tc_smem_bytes() {
-  return 1024 /*align slack*/ + (size_t)TcCfg<T>::STAGES * TcCfg<T>::STAGE_BYTES + 2 * 1280 * sizeof(float) + 256;
+constexpr int tc_stage_bytes(int BN) {
+  return TcCfg<T>::NA * TcCfg<T>::A_BYTES + TcCfg<T>::NW * ((BN * 128 + 1023) / 1024 * 1024);
+}
+template <typename T>
+inline int tc_num_stages(int BN) {
+  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES) / tc_stage_bytes<T>(BN);
+  return s > TC_MAX_STAGES ? TC_MAX_STAGES : s;
 }
 
 template <typename T>
@@ -193,35 +211,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmWlo, const PwTcArgs p) {
   using Cfg = TcCfg<T>;
-  constexpr int S = Cfg::STAGES;
+  const int S = p.stages;
+  const int W_BYTES = (p.BN * 128 + 1023) / 1024 * 1024;       // one W operand tile (1024-aligned)
+  const int STAGE_BYTES = Cfg::NA * Cfg::A_BYTES + Cfg::NW * W_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  float* sc_s = (float*)(smem + (size_t)S * Cfg::STAGE_BYTES);
+  uint8_t* epi_base = smem + (size_t)S * STAGE_BYTES;          // 8 x 4 KB, 1024-aligned
+  float* sc_s = (float*)(epi_base + TC_EPI_BYTES);
   float* bi_s = sc_s + 1280;
   uint64_t* bars = (uint64_t*)(bi_s + 1280);
-  uint64_t* full = bars;            // [S]   TMA landed
-  uint64_t* ready = bars + S;       // [S]   transform done (when a transform runs)
-  uint64_t* empty = bars + 2 * S;   // [S]   MMAs reading the stage retired
-  uint64_t* tfull = bars + 3 * S;   // [2]   accumulator complete
-  uint64_t* tempty = tfull + 2;     // [2]   accumulator drained
+  uint64_t* full = bars;                          // [S]   TMA landed
+  uint64_t* ready = bars + TC_MAX_STAGES;         // [S]   transform done (when a transform runs)
+  uint64_t* empty = bars + 2 * TC_MAX_STAGES;     // [S]   MMAs reading the stage retired
+  uint64_t* tfull = bars + 3 * TC_MAX_STAGES;     // [2]   accumulator complete
+  uint64_t* tempty = tfull + 4;                   // [<=4] accumulator drained
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // accumulator stages in TMEM: 4 x 128 columns when the block fits, else 2 x 256
+  const int NAS = p.BN <= 128 ? 4 : 2;
+  const int acc_cols = p.BN <= 128 ? 128 : 256;
   const bool transform = Cfg::TF32 || p.gate != nullptr;
   const int64_t items = p.m_tiles * p.n_blocks;
 
+  // bf16 swish uses x*sigmoid(x) = h + h*tanh(h) with h = x/2: fold the 1/2 into scale and bias
+  const float fold = (!Cfg::TF32 && p.act == 1) ? 0.5f : 1.f;
   for (int i = threadIdx.x; i < p.N; i += TC_THREADS) {
-    sc_s[i] = p.scale[i];
-    bi_s[i] = p.bias[i];
+    sc_s[i] = p.scale[i] * fold;
+    bi_s[i] = p.bias[i] * fold;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < TC_MAX_STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&ready[s], 128);
       ptx::mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&tfull[s], 1);
       ptx::mbar_init(&tempty[s], 128);
     }
@@ -247,12 +273,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n0 = (int)(it % p.n_blocks) * p.BN;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* st = stage_base + (size_t)s * Cfg::STAGE_BYTES;
+          uint8_t* st = stage_base + (size_t)s * STAGE_BYTES;
           ptx::mbar_expect_tx(&full[s], tx);
           ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, m0);
           if (Cfg::TF32) {
             ptx::tma_load_2d(st + 2 * Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
-            ptx::tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &tmWlo, &full[s], kc * Cfg::KC, n0);
+            ptx::tma_load_2d(st + 2 * Cfg::A_BYTES + W_BYTES, &tmWlo, &full[s], kc * Cfg::KC, n0);
           } else {
             ptx::tma_load_2d(st + Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
           }
@@ -272,15 +298,15 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t ph = 0;
       int64_t li = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++li) {
-        const int as = (int)(li & 1);
-        const uint32_t use = (uint32_t)(li >> 1);
+        const int as = (int)(li % NAS);
+        const uint32_t use = (uint32_t)(li / NAS);
         ptx::mbar_wait(&tempty[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * TC_ACC_COLS;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_cols);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           ptx::mbar_wait(transform ? &ready[s] : &full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
+          const uint32_t a_addr = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES);
           const int krem = p.K - kc * Cfg::KC;
           const int ksteps = (min(krem, Cfg::KC) + Cfg::UK - 1) / Cfg::UK;
           for (int ks = 0; ks < ksteps; ++ks) {
@@ -290,7 +316,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const uint64_t ahi = umma_desc_sw128(a_addr + koff);
               const uint64_t alo = umma_desc_sw128(a_addr + Cfg::A_BYTES + koff);
               const uint64_t whi = umma_desc_sw128(a_addr + 2 * Cfg::A_BYTES + koff);
-              const uint64_t wlo = umma_desc_sw128(a_addr + 2 * Cfg::A_BYTES + Cfg::W_BYTES + koff);
+              const uint64_t wlo = umma_desc_sw128(a_addr + 2 * Cfg::A_BYTES + W_BYTES + koff);
               ptx::mma_ss<true>(d_tmem, alo, whi, idesc, acc);
               ptx::mma_ss<true>(d_tmem, ahi, wlo, idesc, 1u);
               ptx::mma_ss<true>(d_tmem, ahi, whi, idesc, 1u);
@@ -312,50 +338,57 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ============================ operand transform ================================
     if (transform) {
       const int r = threadIdx.x - 64;  // tile row owned by this thread
+      const uint32_t row_off = (uint32_t)r * 128u;
+      const uint32_t xr = (uint32_t)(r & 7);
       int s = 0;
       uint32_t ph = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
         const int64_t m = (it / p.n_blocks) * TC_BM + r;
-        const float* grow = (p.gate != nullptr && m < p.M) ? p.gate + (m / p.HW) * p.K : nullptr;
+        const bool gated = p.gate != nullptr && m < p.M;
+        const T* grow = gated ? (const T*)p.gate + (m / p.HW) * p.K : nullptr;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          ptx::mbar_wait(&full[s], ph);
-          uint8_t* a_hi = stage_base + (size_t)s * Cfg::STAGE_BYTES + (size_t)r * 128;
           const int k0 = kc * Cfg::KC;
+          constexpr int EPCH = 16 / (int)sizeof(T);   // elements per 16-byte chunk
+          const int nch = min(8, (p.K - k0) / EPCH);  // chunks that hold real data (the rest is TMA zero fill)
+          // the gate row (L2-resident, one round trip) is fetched BEFORE waiting for the TMA data
+          uint4 g[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (gated && j < nch) g[j] = __ldg(reinterpret_cast<const uint4*>(grow + k0 + j * EPCH));
+          ptx::mbar_wait(&full[s], ph);
+          const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {  // eight 16-byte chunks per 128-byte row
-            const int phys = (j ^ (r & 7)) * 16;
-            uint4 raw = *reinterpret_cast<uint4*>(a_hi + phys);
-            if (Cfg::TF32) {
-              float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-              const int k = k0 + j * 4;
-              if (grow != nullptr && k < p.K) {
-                const float4 g = *reinterpret_cast<const float4*>(grow + k);
-                v[0] *= g.x; v[1] *= g.y; v[2] *= g.z; v[3] *= g.w;
-              }
-              uint4 hi, lo;
-              uint32_t* hp = &hi.x;
-              uint32_t* lp = &lo.x;
+            if (j < nch) {
+              const uint32_t phys = a_hi + (((uint32_t)j ^ xr) << 4);
+              uint4 raw = ptx::lds128(phys);
+              if (Cfg::TF32) {
+                float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+                if (gated) {
+                  v[0] *= __uint_as_float(g[j].x); v[1] *= __uint_as_float(g[j].y);
+                  v[2] *= __uint_as_float(g[j].z); v[3] *= __uint_as_float(g[j].w);
+                }
+                uint4 hi, lo;
+                uint32_t* hp = &hi.x;
+                uint32_t* lp = &lo.x;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const uint32_t hbits = __float_as_uint(v[e]) & 0xFFFFE000u;  // exact TF32 value
-                hp[e] = hbits;
-                lp[e] = __float_as_uint(v[e] - __uint_as_float(hbits));      // exact remainder
-              }
-              *reinterpret_cast<uint4*>(a_hi + phys) = hi;
-              *reinterpret_cast<uint4*>(a_hi + Cfg::A_BYTES + phys) = lo;
-            } else {
-              const int k = k0 + j * 8;
-              if (grow != nullptr && k < p.K) {
-                const float4 g0 = *reinterpret_cast<const float4*>(grow + k);
-                const float4 g1 = *reinterpret_cast<const float4*>(grow + k + 4);
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t hbits = __float_as_uint(v[e]) & 0xFFFFE000u;  // exact TF32 value
+                  hp[e] = hbits;
+                  lp[e] = __float_as_uint(v[e] - __uint_as_float(hbits));      // exact remainder
+                }
+                ptx::sts128(phys, hi);
+                ptx::sts128(phys + Cfg::A_BYTES, lo);
+              } else if (gated) {
                 __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-                float2 f;
-                f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
-                f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
-                f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
-                f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
-                *reinterpret_cast<uint4*>(a_hi + phys) = raw;
+                const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g[j]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], gh[e]);
+                ptx::sts128(phys, raw);
               }
+            } else if (Cfg::TF32) {
+              // zero-filled K tail: the lo copy must be zero too
+              ptx::sts128(a_hi + Cfg::A_BYTES + (((uint32_t)j ^ xr) << 4), make_uint4(0u, 0u, 0u, 0u));
             }
           }
           ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
@@ -369,78 +402,135 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ================================== epilogue ====================================
-    const int eg = (warp - 6) >> 2;   // epilogue group 0/1 <-> accumulator stage
+    const int eg = (warp - 6) >> 2;   // epilogue group: handles work items li with li % TC_EPI_GROUPS == eg
     const int quarter = warp & 3;     // TMEM lanes 32*quarter .. +31 are visible to this warp
-    const int row = quarter * 32 + lane;
     int64_t li = 0;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++li) {
-      if ((int)(li & 1) != eg) continue;
-      const uint32_t use = (uint32_t)(li >> 1);
-      const int64_t m = (it / p.n_blocks) * TC_BM + row;
+      // A group follows EVERY phase of the accumulator stage it serves (a parity wait is only
+      // meaningful for the current or the immediately preceding phase) but drains only its own items.
+      const int as = (int)(li % NAS);
+      if (as != eg % NAS) continue;
+      const uint32_t use = (uint32_t)(li / NAS);
       const int n0 = (int)(it % p.n_blocks) * p.BN;
-      ptx::mbar_wait(&tfull[eg], use & 1);
+      ptx::mbar_wait(&tfull[as], use & 1);
+      if ((int)(li % TC_EPI_GROUPS) != eg) continue;
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)eg * TC_ACC_COLS;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
       const int ncols = min(p.BN, p.N - n0);
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld32(taddr + (uint32_t)c0, v);
-        if (m < p.M) {
-          const int n = n0 + c0;
-          const int valid = min(32, p.N - n);  // multiple of 8
-          float y[32];
+      const int64_t m_warp = (it / p.n_blocks) * TC_BM + quarter * 32;   // first row of this warp
+      const int rows_valid = (p.M - m_warp) < 32 ? (int)(p.M - m_warp) : 32;        // <= 0 when the warp is past M
+      constexpr int EC = Cfg::EPI_COLS;                                   // columns per pass (128 B per row)
+      constexpr int EPC = 16 / (int)sizeof(T);                            // elements per 16-byte chunk
+      const uint32_t stg = ptx::smem_u32(epi_base) + (uint32_t)(warp - 6) * 4096u;  // 32 rows x 128 B, chunk-swizzled
+      const uint32_t my_row = stg + (uint32_t)lane * 128u;
+      const uint32_t my_x = (uint32_t)(lane & 7);
+      // coalesced copy pattern: lane -> (row sub-index lane/8, 16-byte chunk lane%8)
+      const int cr = lane >> 3, cc = lane & 7;
+      const int64_t g_off0 = (m_warp + cr) * (int64_t)p.N + n0 + cc * EPC;
+      const uint32_t c_stg = stg + (uint32_t)cr * 128u;
+      for (int c0 = 0; c0 < ncols; c0 += EC) {
+        const int vchunks = min(EC, ncols - c0) / EPC;  // valid 16-byte chunks per row in this pass
+        // (1) residual tile -> staging, coalesced (8 lanes x 16 B = one 128-byte row segment)
+        if (p.res != nullptr) {
+          const T* rp = (const T*)p.res + g_off0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int nn = min(n + j, p.N - 1);
-            float t = fmaf(__uint_as_float(v[j]), sc_s[nn], bi_s[nn]);
-            if (p.act == 1) {
-              if (Cfg::TF32) t = t / (1.f + __expf(-t));
-              else t = 0.5f * t * (1.f + ptx::tanh_approx(0.5f * t));
+          for (int itr = 0; itr < 8; ++itr) {
+            const int rr = itr * 4 + cr;
+            if (rr < rows_valid && cc < vchunks) {
+              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rp + (int64_t)itr * 4 * p.N));
+              ptx::sts128(c_stg + (uint32_t)itr * 512u + (((uint32_t)cc ^ (uint32_t)(rr & 7)) << 4), r4);
             }
-            y[j] = t;
+          }
+          __syncwarp();
+        }
+        // (2) accumulator row -> scale/bias/activation (+ residual) -> staging row
+#pragma unroll
+        for (int h = 0; h < EC / 32; ++h) {
+          uint32_t v[32];
+          ptx::tmem_ld32(taddr + (uint32_t)(c0 + h * 32), v);
+          const float4* sc4 = reinterpret_cast<const float4*>(sc_s + n0 + c0 + h * 32);
+          const float4* bi4 = reinterpret_cast<const float4*>(bi_s + n0 + c0 + h * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {   // 4 columns at a time
+            const float4 s4 = sc4[q], b4 = bi4[q];
+            float y0 = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
+            float y1 = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
+            float y2 = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
+            float y3 = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
+            if (p.act == 1) {
+              if (Cfg::TF32) {
+                y0 = __fdividef(y0, 1.f + __expf(-y0));
+                y1 = __fdividef(y1, 1.f + __expf(-y1));
+                y2 = __fdividef(y2, 1.f + __expf(-y2));
+                y3 = __fdividef(y3, 1.f + __expf(-y3));
+              } else {
+                y0 = fmaf(y0, ptx::tanh_approx(y0), y0);
+                y1 = fmaf(y1, ptx::tanh_approx(y1), y1);
+                y2 = fmaf(y2, ptx::tanh_approx(y2), y2);
+                y3 = fmaf(y3, ptx::tanh_approx(y3), y3);
+              }
+            }
+            v[4 * q + 0] = __float_as_uint(y0);
+            v[4 * q + 1] = __float_as_uint(y1);
+            v[4 * q + 2] = __float_as_uint(y2);
+            v[4 * q + 3] = __float_as_uint(y3);
           }
           if (Cfg::TF32) {
-            float* o = (float*)p.out + m * p.N + n;
-            const float* rs = p.res ? (const float*)p.res + m * p.N + n : nullptr;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (q * 4 < valid) {
-                float4 w4 = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-                if (rs) {
-                  const float4 r4 = *reinterpret_cast<const float4*>(rs + 4 * q);
-                  w4.x += r4.x; w4.y += r4.y; w4.z += r4.z; w4.w += r4.w;
-                }
-                *reinterpret_cast<float4*>(o + 4 * q) = w4;
+            for (int q = 0; q < 8; ++q) {   // 8 chunks of 4 floats
+              const uint32_t sp = my_row + (((uint32_t)q ^ my_x) << 4);
+              uint4 w4 = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              if (p.res != nullptr) {
+                const uint4 r4 = ptx::lds128(sp);
+                w4.x = __float_as_uint(__uint_as_float(w4.x) + __uint_as_float(r4.x));
+                w4.y = __float_as_uint(__uint_as_float(w4.y) + __uint_as_float(r4.y));
+                w4.z = __float_as_uint(__uint_as_float(w4.z) + __uint_as_float(r4.z));
+                w4.w = __float_as_uint(__uint_as_float(w4.w) + __uint_as_float(r4.w));
               }
+              ptx::sts128(sp, w4);
             }
           } else {
-            __nv_bfloat16* o = (__nv_bfloat16*)p.out + m * p.N + n;
-            const __nv_bfloat16* rs = p.res ? (const __nv_bfloat16*)p.res + m * p.N + n : nullptr;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < valid) {
-                if (rs) {
-                  const uint4 r4 = *reinterpret_cast<const uint4*>(rs + 8 * q);
-                  const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&r4);
+            for (int q = 0; q < 4; ++q) {   // 4 chunks of 8 bf16 per 32 columns
+              const uint32_t sp = my_row + (((uint32_t)(h * 4 + q) ^ my_x) << 4);
+              float y[8];
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(rh[e]);
-                    y[8 * q + 2 * e] += f.x;
-                    y[8 * q + 2 * e + 1] += f.y;
-                  }
+              for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[8 * q + e]);
+              if (p.res != nullptr) {
+                const uint4 r4 = ptx::lds128(sp);
+                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(rh[e]);
+                  y[2 * e] += f.x;
+                  y[2 * e + 1] += f.y;
                 }
-                uint4 w4;
-                __nv_bfloat162* wh = reinterpret_cast<__nv_bfloat162*>(&w4);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) wh[e] = __floats2bfloat162_rn(y[8 * q + 2 * e], y[8 * q + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(o + 8 * q) = w4;
               }
+              uint4 w4;
+              __nv_bfloat162* wh = reinterpret_cast<__nv_bfloat162*>(&w4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) wh[e] = __floats2bfloat162_rn(y[2 * e], y[2 * e + 1]);
+              ptx::sts128(sp, w4);
             }
           }
         }
+        __syncwarp();
+        // (3) staging -> global, coalesced
+        {
+          T* op = (T*)p.out + g_off0 + c0;
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int rr = itr * 4 + cr;
+            if (rr < rows_valid && cc < vchunks) {
+              const uint4 w4 = ptx::lds128(c_stg + (uint32_t)itr * 512u + (((uint32_t)cc ^ (uint32_t)(rr & 7)) << 4));
+              *reinterpret_cast<uint4*>(op + (int64_t)itr * 4 * p.N) = w4;
+            }
+          }
+        }
+        __syncwarp();
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty[eg]);
+      ptx::mbar_arrive(&tempty[as]);
     }
   }
   ptx::tc_fence_before();
@@ -580,10 +670,9 @@ inline int pw_tc_build(PwTcPlan** out, const NetCfg& net, const float* params_ho
   plan->layers.resize(33);
   const bool f32 = mode == MC_MODE_FP32;
   if (f32) {
-    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<float>()));
+    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
   } else {
-    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)tc_smem_bytes<__nv_bfloat16>()));
+    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
   }
   auto enabled = [&](int id) { return id < 32 ? ((layer_mask_lo >> id) & 1u) != 0 : ((layer_mask_hi >> (id - 32)) & 1u) != 0; };
   int rc = MC_OK;
@@ -606,7 +695,7 @@ inline int pw_tc_build(PwTcPlan** out, const NetCfg& net, const float* params_ho
   return MC_OK;
 }
 
-inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, const float* gate, const void* res, void* outp, int64_t M, int HW,
+inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, const void* gate, const void* res, void* outp, int64_t M, int HW,
                      cudaStream_t st) {
   PwTcLayer& l = plan->layers[id];
   const bool f32 = plan->mode == MC_MODE_FP32;
@@ -635,13 +724,15 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, const float* gate, c
   a.n_blocks = l.n_blocks;
   a.k_chunks = l.k_chunks;
   a.act = l.act;
+  a.stages = f32 ? tc_num_stages<float>(l.BN) : tc_num_stages<__nv_bfloat16>(l.BN);
+  const size_t smem = TC_FIXED_BYTES + (size_t)a.stages * (f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN));
   a.m_tiles = (M + TC_BM - 1) / TC_BM;
   const int64_t items = a.m_tiles * a.n_blocks;
   const int grid = (int)std::min<int64_t>(items, plan->num_sms);
   if (f32)
-    pw_tc_kernel<float><<<grid, TC_THREADS, tc_smem_bytes<float>(), st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+    pw_tc_kernel<float><<<grid, TC_THREADS, smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
   else
-    pw_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, tc_smem_bytes<__nv_bfloat16>(), st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+    pw_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
   MC_CHECK_LAUNCH();
   return MC_OK;
 }

@@ -94,7 +94,8 @@ def pack_backbone(sd: dict) -> np.ndarray:
         add(s), add(b)
         add(sd[p + "_se_reduce.weight"].float().reshape(cfg["c_se"], cfg["c_mid"]).numpy())
         add(sd[p + "_se_reduce.bias"].float().numpy())
-        add(sd[p + "_se_expand.weight"].float().reshape(cfg["c_mid"], cfg["c_se"]).numpy())
+        # transposed to [c_se][c_mid] so the SE kernel reads it coalesced
+        add(sd[p + "_se_expand.weight"].float().reshape(cfg["c_mid"], cfg["c_se"]).t().contiguous().numpy())
         add(sd[p + "_se_expand.bias"].float().numpy())
         add(sd[p + "_project_conv.weight"].float().reshape(cfg["c_out"], cfg["c_mid"]).numpy())
         s, b = _fold(sd, p + "_bn2")
