@@ -222,8 +222,18 @@ int launch_pw_simt(mc_extractor* h, const T* A, const float* W, const float* sc,
   return MC_OK;
 }
 
+// MC_DEBUG_SYNC=1: synchronise after every layer and name the layer that faulted (bring-up aid).
+int debug_sync(int layer, cudaStream_t st) {
+  static const bool on = getenv("MC_DEBUG_SYNC") != nullptr;
+  if (!on) return MC_OK;
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(MC_ERR_CUDA, "layer " + std::to_string(layer) + ": " + cudaGetErrorString(e));
+  return MC_OK;
+}
+
 template <typename T>
 int tap(mc_extractor* h, int layer, const T* src, int64_t n_elems, cudaStream_t st) {
+  if (int rc = debug_sync(layer, st)) return rc;
   if (h->tap_layer != layer || !h->tap_out) return MC_OK;
   const int64_t n = std::min(n_elems, h->tap_cap);
   to_f32_kernel<T><<<cdiv(n, 256), 256, 0, st>>>(src, h->tap_out, n);

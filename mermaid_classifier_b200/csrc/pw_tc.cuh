@@ -27,6 +27,10 @@
 #include "common.cuh"
 #include "layers.h"
 
+#ifndef MC_BF16_TANH
+#define MC_BF16_TANH 0
+#endif
+
 namespace mc {
 
 // ---------------------------------------------------------------------------------------
@@ -114,14 +118,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"  // same asm statement: the outputs are only defined after the wait
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -172,7 +176,7 @@ struct TcCfg<__nv_bfloat16> {
   static constexpr bool TF32 = false;
   static constexpr int KC = 64;       // elements per 128-byte row
   static constexpr int UK = 16;       // K per MMA
-  static constexpr int BN_MAX = 256;
+  static constexpr int BN_MAX = 128;   // <= 128 so four accumulator stages fit in TMEM (one per epilogue group)
   static constexpr int A_BYTES = TC_BM * 128;
   static constexpr int NA = 1, NW = 1;  // A / W operand copies per stage
   static constexpr int EPI_COLS = 64;   // output columns staged per epilogue pass (128 bytes per row)
@@ -224,9 +228,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* full = bars;                          // [S]   TMA landed
   uint64_t* ready = bars + TC_MAX_STAGES;         // [S]   transform done (when a transform runs)
   uint64_t* empty = bars + 2 * TC_MAX_STAGES;     // [S]   MMAs reading the stage retired
-  uint64_t* tfull = bars + 3 * TC_MAX_STAGES;     // [2]   accumulator complete
-  uint64_t* tempty = tfull + 4;                   // [<=4] accumulator drained
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* tfull = bars + 3 * TC_MAX_STAGES;     // [4]   accumulator complete
+  uint64_t* tempty = tfull + 4;                   // [4]   accumulator drained
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // accumulator stages in TMEM: 4 x 128 columns when the block fits, else 2 x 256
@@ -236,7 +240,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int64_t items = p.m_tiles * p.n_blocks;
 
   // bf16 swish uses x*sigmoid(x) = h + h*tanh(h) with h = x/2: fold the 1/2 into scale and bias
-  const float fold = (!Cfg::TF32 && p.act == 1) ? 0.5f : 1.f;
+  const float fold = (MC_BF16_TANH && !Cfg::TF32 && p.act == 1) ? 0.5f : 1.f;
   for (int i = threadIdx.x; i < p.N; i += TC_THREADS) {
     sc_s[i] = p.scale[i] * fold;
     bi_s[i] = p.bias[i] * fold;
@@ -458,7 +462,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             float y2 = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
             float y3 = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
             if (p.act == 1) {
-              if (Cfg::TF32) {
+              if (Cfg::TF32 || !MC_BF16_TANH) {
                 y0 = __fdividef(y0, 1.f + __expf(-y0));
                 y1 = __fdividef(y1, 1.f + __expf(-y1));
                 y2 = __fdividef(y2, 1.f + __expf(-y2));
