@@ -164,23 +164,48 @@ int64_t mc_head_launches(const mc_head* h); /* kernels launched so far by this h
 
 /* ---- A7: TorchMLPClassifier.partial_fit inner loop
  *      (mermaid_classifier/pyspacer/torch_classifier.py:226-303): per mini-batch
- *      weighted CE + 0.5*alpha/mb*sum(W^2), backward, Adam.  Parameters live on the
- *      device; X/y for one partial_fit chunk are passed already shuffled. ------------- */
+ *      weighted CE + 0.5*alpha/mb*sum(W^2), backward, Adam.  Parameters and Adam state live
+ *      on the device.  weights_host[i] is (dims[i+1] x dims[i]) row-major (the xavier_uniform /
+ *      zero-bias init of torch_classifier.py:62-73 is done by the caller with torch's RNG so it
+ *      is bit-identical to the reference's). ------------------------------------------------- */
 int mc_mlp_create(int32_t n_layers, const int32_t* dims, const float* const* weights_host,
                   const float* const* biases_host, const float* class_weight_host /* K or NULL */,
                   float lr, float alpha, float beta1, float beta2, float eps, int32_t device,
                   mc_mlp** out);
 int mc_mlp_destroy(mc_mlp* h);
-/* Runs ceil(n / batch) Adam steps over x_dev (n x dims[0]) / y_dev (n int32 class indices);
- * *loss_out_host receives the loss_curve_ entry (sample-weighted mean regularised loss).
- * grad_sync: optional callback invoked on the stream after each backward with the flat
- * gradient buffer (device, n_grad floats) -- the data-parallel all-reduce hook. */
+
+/* Data-parallel communicator for the gradient all-reduce (NCCL over NVLink; one process per
+ * GPU).  Rank 0 calls mc_dp_unique_id and hands the 128 bytes to every rank out of band
+ * (torch.distributed broadcast in the Python mirror); every rank then calls mc_dp_create. */
+typedef struct mc_dp mc_dp;
+int mc_dp_unique_id(char* id_out_128);
+int mc_dp_create(const char* id_128, int32_t rank, int32_t world, int32_t device, mc_dp** out);
+int mc_dp_destroy(mc_dp* d);
+int mc_dp_all_reduce_sum(mc_dp* d, float* buf_dev, int64_t n, void* stream);
+
+/* One partial_fit pass = n_steps Adam steps.  Step s trains on THIS RANK's rows
+ * [step_offsets_host[s], step_offsets_host[s+1]) of x_dev (n x dims[0] fp32) / y_dev (n int32
+ * class indices), taken through order_dev (int64 row indices, the shuffled order; NULL =
+ * identity).  A step may have zero local rows (ragged tail under data parallelism).
+ * After each backward the flat gradient buffer -- un-normalised sums followed by the 4
+ * statistics [sum w, sum w*nll, rows, 0], mc_mlp_grad_size() floats -- is all-reduced over `dp`
+ * (NULL = single GPU) and then handed to the optional `grad_sync` hook on the stream; the Adam
+ * kernel normalises by the GLOBAL statistics, so the update equals the reference's for the
+ * global mini-batch.  *loss_out_host receives the loss_curve_ entry (sample-weighted mean of
+ * the regularised mini-batch losses, torch_classifier.py:295-301); passing it synchronises. */
 typedef void (*mc_grad_sync_fn)(float* grad_dev, int64_t n_grad, void* stream, void* user);
-int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, int64_t n, int32_t batch,
-                       int32_t global_batch, mc_grad_sync_fn grad_sync, void* user,
-                       double* loss_out_host, void* stream);
+int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, const int64_t* order_dev,
+                       const int64_t* step_offsets_host, int32_t n_steps, mc_dp* dp,
+                       mc_grad_sync_fn grad_sync, void* user, double* loss_out_host, void* stream);
 int mc_mlp_get_params(mc_mlp* h, float* const* weights_host, float* const* biases_host);
-int64_t mc_mlp_steps(const mc_mlp* h);
+/* Adam first/second moments and step count (pickling: torch_classifier.py:412-444). */
+int mc_mlp_get_adam(mc_mlp* h, float* const* m_w_host, float* const* m_b_host, float* const* v_w_host,
+                    float* const* v_b_host, int64_t* t_out);
+int mc_mlp_set_adam(mc_mlp* h, const float* const* m_w_host, const float* const* m_b_host,
+                    const float* const* v_w_host, const float* const* v_b_host, int64_t t);
+int64_t mc_mlp_steps(const mc_mlp* h);     /* Adam steps taken */
+int64_t mc_mlp_launches(const mc_mlp* h);  /* kernels launched so far by this handle */
+int64_t mc_mlp_grad_size(const mc_mlp* h); /* floats in the flat gradient buffer (incl. 4 statistics) */
 
 #ifdef __cplusplus
 }

@@ -76,9 +76,17 @@ SIGNATURES = {
     "mc_head_launches": (_i64, [_vp]),
     "mc_mlp_create": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i32, _pp]),
     "mc_mlp_destroy": (C.c_int, [_vp]),
-    "mc_mlp_partial_fit": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, GRAD_SYNC_FN, _vp, _vp, _vp]),
+    "mc_dp_unique_id": (C.c_int, [_vp]),
+    "mc_dp_create": (C.c_int, [_vp, _i32, _i32, _i32, _pp]),
+    "mc_dp_destroy": (C.c_int, [_vp]),
+    "mc_dp_all_reduce_sum": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "mc_mlp_partial_fit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mc_mlp_get_params": (C.c_int, [_vp, _vp, _vp]),
+    "mc_mlp_get_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mc_mlp_set_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64]),
     "mc_mlp_steps": (_i64, [_vp]),
+    "mc_mlp_launches": (_i64, [_vp]),
+    "mc_mlp_grad_size": (_i64, [_vp]),
 }
 
 _lib = None

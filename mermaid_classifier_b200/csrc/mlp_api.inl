@@ -1,11 +1,421 @@
-// mc_mlp_* entry points (placeholder: not yet implemented).
-struct mc_mlp { int64_t steps = 0; };
-extern "C" {
-int mc_mlp_create(int32_t, const int32_t*, const float* const*, const float* const*, const float*, float, float, float,
-                  float, float, int32_t, mc_mlp**) { return fail(MC_ERR_UNSUPPORTED, "mc_mlp_create: not implemented yet"); }
-int mc_mlp_destroy(mc_mlp* h) { delete h; return MC_OK; }
-int mc_mlp_partial_fit(mc_mlp*, const float*, const int32_t*, int64_t, int32_t, int32_t, mc_grad_sync_fn, void*, double*,
-                       void*) { return fail(MC_ERR_UNSUPPORTED, "mc_mlp_partial_fit: not implemented yet"); }
-int mc_mlp_get_params(mc_mlp*, float* const*, float* const*) { return fail(MC_ERR_UNSUPPORTED, "not implemented yet"); }
-int64_t mc_mlp_steps(const mc_mlp* h) { return h ? h->steps : 0; }
+// mc_mlp_* / mc_dp_* entry points: the MLP-head training inner loop (A7) and its data-parallel
+// gradient all-reduce (NCCL over NVLink, resolved at run time from the libnccl the process has
+// already loaded -- torch's bundled copy -- so the library itself carries no link dependency).
+#include <dlfcn.h>
+
+#include "mlp_train.cuh"
+
+namespace {
+
+// ---- minimal NCCL surface (nccl.h 2.27: ncclUniqueId is 128 opaque bytes; ncclFloat32 = 7, ncclSum = 0)
+struct NcclId { char internal[128]; };
+typedef int (*nccl_get_unique_id_fn)(NcclId*);
+typedef int (*nccl_comm_init_rank_fn)(void**, int, NcclId, int);
+typedef int (*nccl_comm_destroy_fn)(void*);
+typedef int (*nccl_all_reduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_get_error_string_fn)(int);
+
+struct NcclApi {
+  void* lib = nullptr;
+  nccl_get_unique_id_fn get_unique_id = nullptr;
+  nccl_comm_init_rank_fn comm_init_rank = nullptr;
+  nccl_comm_destroy_fn comm_destroy = nullptr;
+  nccl_all_reduce_fn all_reduce = nullptr;
+  nccl_get_error_string_fn error_string = nullptr;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.lib ? &api : nullptr;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // the copy torch already mapped, if any
+    if (api.lib) break;
+  }
+  if (!api.lib)
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+  if (!api.lib) return nullptr;
+  api.get_unique_id = (nccl_get_unique_id_fn)dlsym(api.lib, "ncclGetUniqueId");
+  api.comm_init_rank = (nccl_comm_init_rank_fn)dlsym(api.lib, "ncclCommInitRank");
+  api.comm_destroy = (nccl_comm_destroy_fn)dlsym(api.lib, "ncclCommDestroy");
+  api.all_reduce = (nccl_all_reduce_fn)dlsym(api.lib, "ncclAllReduce");
+  api.error_string = (nccl_get_error_string_fn)dlsym(api.lib, "ncclGetErrorString");
+  if (!api.get_unique_id || !api.comm_init_rank || !api.comm_destroy || !api.all_reduce) {
+    api.lib = nullptr;
+    return nullptr;
+  }
+  return &api;
 }
+
+int nccl_fail(NcclApi* api, const char* what, int rc) {
+  return fail(MC_ERR_CUDA, std::string(what) + ": NCCL error " + std::to_string(rc) +
+                               (api && api->error_string ? std::string(" (") + api->error_string(rc) + ")" : ""));
+}
+
+}  // namespace
+
+struct mc_dp {
+  void* comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+};
+
+struct mc_mlp {
+  int device = 0, L = 0;
+  std::vector<int> dims, dims_p;
+  MlpSegs segs{};
+  int64_t n_flat = 0;
+  float *d_p = nullptr, *d_m = nullptr, *d_v = nullptr, *d_g = nullptr, *d_cw = nullptr;
+  float* d_ssq[2] = {nullptr, nullptr};
+  int n_blocks = 0, ssq_cur = 0;
+  double* d_loss = nullptr;
+  std::vector<float*> d_act, d_delta;  // [L] each: outputs of layer i / gradient w.r.t. them
+  float* d_part = nullptr;
+  int64_t cap_part = 0;
+  float2* d_rowstat = nullptr;
+  int cap_rows = 0;
+  float* d_xs = nullptr;
+  int64_t cap_xs = 0;
+  int32_t* d_ys = nullptr;
+  int64_t cap_ys = 0;
+  float lr = 1e-3f, alpha = 1e-4f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
+  int64_t t = 0;          // Adam steps taken
+  int64_t launches = 0;   // kernels launched
+};
+
+namespace {
+
+int mlp_ensure_rows(mc_mlp* h, int rows) {
+  if (rows <= h->cap_rows) return MC_OK;
+  const int cap = std::max(rows, 256);
+  for (int i = 0; i < h->L; ++i) {
+    if (h->d_act[i]) cudaFree(h->d_act[i]);
+    if (h->d_delta[i]) cudaFree(h->d_delta[i]);
+    h->d_act[i] = h->d_delta[i] = nullptr;
+    MC_CUDA(cudaMalloc((void**)&h->d_act[i], (size_t)cap * h->dims_p[i + 1] * sizeof(float)));
+    MC_CUDA(cudaMalloc((void**)&h->d_delta[i], (size_t)cap * h->dims_p[i + 1] * sizeof(float)));
+  }
+  if (h->d_rowstat) cudaFree(h->d_rowstat);
+  h->d_rowstat = nullptr;
+  MC_CUDA(cudaMalloc((void**)&h->d_rowstat, (size_t)cap * sizeof(float2)));
+  h->cap_rows = cap;
+  return MC_OK;
+}
+
+// C = A * B with the layout flags of mlp_gemm_kernel; split-K when the tile grid would leave most SMs idle.
+int mlp_gemm(mc_mlp* h, bool a_mc, bool b_nc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M,
+             int N, int K, int epi, const float* bias, const float* mask, int ldmask, float* colsum, cudaStream_t st) {
+  const int tiles = cdiv(M, 64) * cdiv(N, 64);
+  int splits = 1;
+  if (!a_mc && !b_nc && tiles < 64 && K >= 512 && ldc == N) {
+    splits = std::min(cdiv(K, 128), std::max(1, 160 / tiles));
+  }
+  int kps = K;
+  if (splits > 1) {
+    kps = cdiv(cdiv(K, splits), 16) * 16;
+    splits = cdiv(K, kps);
+  }
+  dim3 grid(cdiv(M, 64), cdiv(N, 64), splits);
+  float* out = C;
+  if (splits > 1) {
+    int rc = grow(&h->d_part, &h->cap_part, (int64_t)splits * M * N);
+    if (rc) return rc;
+    out = h->d_part;
+  }
+#define MLP_GEMM_ARGS A, lda, B, ldb, out, splits > 1 ? N : ldc, M, N, K, kps, epi, bias, mask, ldmask, colsum
+  if (!a_mc && !b_nc) mlp_gemm_kernel<false, false><<<grid, 256, 0, st>>>(MLP_GEMM_ARGS);
+  else if (a_mc && b_nc) mlp_gemm_kernel<true, true><<<grid, 256, 0, st>>>(MLP_GEMM_ARGS);
+  else if (!a_mc && b_nc) mlp_gemm_kernel<false, true><<<grid, 256, 0, st>>>(MLP_GEMM_ARGS);
+  else return fail(MC_ERR_UNSUPPORTED, "mlp_gemm: layout combination");
+#undef MLP_GEMM_ARGS
+  MC_CHECK_LAUNCH();
+  h->launches++;
+  if (splits > 1) {
+    mlp_splitk_epilogue_kernel<<<cdiv((int64_t)M * N / 4, 256), 256, 0, st>>>(h->d_part, splits, C, M, N, epi, bias);
+    MC_CHECK_LAUNCH();
+    h->launches++;
+  }
+  return MC_OK;
+}
+
+int mlp_ssq_init(mc_mlp* h, cudaStream_t st) {
+  mlp_ssq_kernel<<<h->n_blocks, MLP_ADAM_THREADS, 0, st>>>(h->d_p, h->segs, h->d_ssq[h->ssq_cur]);
+  MC_CHECK_LAUNCH();
+  h->launches++;
+  return MC_OK;
+}
+
+// pack / unpack between per-layer (out x in) host arrays and the padded flat device layout
+void mlp_pack(const mc_mlp* h, const float* const* w, const float* const* b, std::vector<float>& flat) {
+  flat.assign((size_t)h->n_flat, 0.f);
+  for (int i = 0; i < h->L; ++i) {
+    const int ki = h->dims[i], no = h->dims[i + 1], kp = h->dims_p[i];
+    for (int r = 0; r < no; ++r) memcpy(&flat[h->segs.w_off[i] + (size_t)r * kp], w[i] + (size_t)r * ki, ki * sizeof(float));
+    if (b) memcpy(&flat[h->segs.b_off[i]], b[i], no * sizeof(float));
+  }
+}
+void mlp_unpack(const mc_mlp* h, const std::vector<float>& flat, float* const* w, float* const* b) {
+  for (int i = 0; i < h->L; ++i) {
+    const int ki = h->dims[i], no = h->dims[i + 1], kp = h->dims_p[i];
+    for (int r = 0; r < no; ++r) memcpy(w[i] + (size_t)r * ki, &flat[h->segs.w_off[i] + (size_t)r * kp], ki * sizeof(float));
+    if (b) memcpy(b[i], &flat[h->segs.b_off[i]], no * sizeof(float));
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- data-parallel communicator -----------------------------------------------------------
+int mc_dp_unique_id(char* id_out_128) {
+  if (!id_out_128) return fail(MC_ERR_BAD_ARG, "mc_dp_unique_id: null");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(MC_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+  NcclId id;
+  int rc = api->get_unique_id(&id);
+  if (rc) return nccl_fail(api, "ncclGetUniqueId", rc);
+  memcpy(id_out_128, id.internal, 128);
+  return MC_OK;
+}
+
+int mc_dp_create(const char* id_128, int32_t rank, int32_t world, int32_t device, mc_dp** out) {
+  if (!id_128 || !out || world < 1 || rank < 0 || rank >= world) return fail(MC_ERR_BAD_ARG, "mc_dp_create: bad argument");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(MC_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+  DeviceGuard g(device);
+  NcclId id;
+  memcpy(id.internal, id_128, 128);
+  mc_dp* d = new mc_dp();
+  d->rank = rank;
+  d->world = world;
+  d->device = device;
+  int rc = api->comm_init_rank(&d->comm, world, id, rank);
+  if (rc) {
+    delete d;
+    return nccl_fail(api, "ncclCommInitRank", rc);
+  }
+  *out = d;
+  return MC_OK;
+}
+
+int mc_dp_destroy(mc_dp* d) {
+  if (!d) return MC_OK;
+  NcclApi* api = nccl_api();
+  if (api && d->comm) api->comm_destroy(d->comm);
+  delete d;
+  return MC_OK;
+}
+
+int mc_dp_all_reduce_sum(mc_dp* d, float* buf_dev, int64_t n, void* stream) {
+  if (!d || !buf_dev || n < 0) return fail(MC_ERR_BAD_ARG, "mc_dp_all_reduce_sum: bad argument");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(MC_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+  int rc = api->all_reduce(buf_dev, buf_dev, (size_t)n, 7 /*ncclFloat32*/, 0 /*ncclSum*/, d->comm, (cudaStream_t)stream);
+  if (rc) return nccl_fail(api, "ncclAllReduce", rc);
+  return MC_OK;
+}
+
+// ---- trainer ------------------------------------------------------------------------------------
+int mc_mlp_create(int32_t n_layers, const int32_t* dims, const float* const* weights, const float* const* biases,
+                  const float* class_weight, float lr, float alpha, float beta1, float beta2, float eps, int32_t device,
+                  mc_mlp** out) {
+  if (n_layers < 1 || n_layers > 8 || !dims || !weights || !biases || !out)
+    return fail(MC_ERR_BAD_ARG, "mc_mlp_create: null argument or layer count outside [1, 8]");
+  for (int i = 0; i <= n_layers; ++i)
+    if (dims[i] < 1) return fail(MC_ERR_BAD_ARG, "mc_mlp_create: non-positive layer width");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(MC_ERR_CUDA, "no CUDA device: libmermaid_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(MC_ERR_BAD_ARG, "mc_mlp_create: bad device index");
+  DeviceGuard g(device);
+  mc_mlp* h = new mc_mlp();
+  h->device = device;
+  h->L = n_layers;
+  h->dims.assign(dims, dims + n_layers + 1);
+  for (int d : h->dims) h->dims_p.push_back((d + 3) / 4 * 4);
+  h->lr = lr; h->alpha = alpha; h->beta1 = beta1; h->beta2 = beta2; h->eps = eps;
+  int64_t off = 0;
+  h->segs.n_layers = n_layers;
+  for (int i = 0; i < n_layers; ++i) {
+    h->segs.w_off[i] = off;
+    off += (int64_t)h->dims_p[i + 1] * h->dims_p[i];
+    h->segs.b_off[i] = off;
+    off += h->dims_p[i + 1];
+  }
+  h->segs.end = off;
+  h->n_flat = off;
+  h->n_blocks = cdiv(off, MLP_ADAM_THREADS);
+  h->d_act.assign(n_layers, nullptr);
+  h->d_delta.assign(n_layers, nullptr);
+  std::vector<float> flat;
+  mlp_pack(h, weights, biases, flat);
+  cudaError_t e = cudaMalloc((void**)&h->d_p, off * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_m, off * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_v, off * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_g, (off + 4) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_ssq[0], h->n_blocks * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_ssq[1], h->n_blocks * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_loss, 2 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_p, flat.data(), off * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->d_m, 0, off * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(h->d_v, 0, off * sizeof(float));
+  if (e == cudaSuccess && class_weight) {
+    e = cudaMalloc((void**)&h->d_cw, h->dims.back() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_cw, class_weight, h->dims.back() * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    mc_mlp_destroy(h);
+    return fail(MC_ERR_CUDA, std::string("mc_mlp_create: ") + cudaGetErrorString(e));
+  }
+  int rc = mlp_ssq_init(h, nullptr);
+  if (rc == MC_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(MC_ERR_CUDA, "mc_mlp_create: ssq init failed");
+  if (rc) {
+    mc_mlp_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return MC_OK;
+}
+
+int mc_mlp_destroy(mc_mlp* h) {
+  if (!h) return MC_OK;
+  DeviceGuard g(h->device);
+  for (float* p : h->d_act) if (p) cudaFree(p);
+  for (float* p : h->d_delta) if (p) cudaFree(p);
+  void* ptrs[] = {h->d_p, h->d_m, h->d_v, h->d_g, h->d_cw, h->d_ssq[0], h->d_ssq[1], h->d_loss,
+                  h->d_part, h->d_rowstat, h->d_xs, h->d_ys};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+  return MC_OK;
+}
+
+int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, const int64_t* order_dev,
+                       const int64_t* step_offsets, int32_t n_steps, mc_dp* dp, mc_grad_sync_fn grad_sync, void* user,
+                       double* loss_out_host, void* stream) {
+  if (!h) return fail(MC_ERR_BAD_ARG, "null handle");
+  if (n_steps < 0 || (n_steps > 0 && !step_offsets)) return fail(MC_ERR_BAD_ARG, "mc_mlp_partial_fit: bad steps");
+  const int64_t n = n_steps > 0 ? step_offsets[n_steps] : 0;
+  if (n_steps > 0 && step_offsets[0] != 0) return fail(MC_ERR_BAD_ARG, "mc_mlp_partial_fit: step_offsets[0] must be 0");
+  int max_rows = 0;
+  for (int s = 0; s < n_steps; ++s) {
+    const int64_t r = step_offsets[s + 1] - step_offsets[s];
+    if (r < 0 || r > (1 << 20)) return fail(MC_ERR_BAD_ARG, "mc_mlp_partial_fit: step size outside [0, 2^20]");
+    max_rows = std::max<int>(max_rows, (int)r);
+  }
+  if (n > 0 && (!x_dev || !y_dev)) return fail(MC_ERR_BAD_ARG, "mc_mlp_partial_fit: null data");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  const int L = h->L, D = h->dims[0], Dp = h->dims_p[0], K = h->dims.back(), Kp = h->dims_p.back();
+  if ((rc = mlp_ensure_rows(h, max_rows))) return rc;
+  const float* xs = x_dev;
+  const int32_t* ys = y_dev;
+  if (n > 0 && (order_dev || D != Dp)) {
+    if ((rc = grow(&h->d_xs, &h->cap_xs, n * Dp)) || (rc = grow(&h->d_ys, &h->cap_ys, n))) return rc;
+    mlp_gather_rows_kernel<<<cdiv(n * Dp, 256), 256, 0, st>>>(x_dev, y_dev, order_dev, D, Dp, h->d_xs, h->d_ys, n);
+    MC_CHECK_LAUNCH();
+    h->launches++;
+    xs = h->d_xs;
+    ys = h->d_ys;
+  }
+  MC_CUDA(cudaMemsetAsync(h->d_loss, 0, 2 * sizeof(double), st));
+  for (int s = 0; s < n_steps; ++s) {
+    const int rows = (int)(step_offsets[s + 1] - step_offsets[s]);
+    const float* x = xs + step_offsets[s] * Dp;
+    if (rows > 0) {
+      // forward
+      const float* in = x;
+      for (int i = 0; i < L; ++i) {
+        const int Ki = h->dims_p[i], Ni = h->dims_p[i + 1];
+        if ((rc = mlp_gemm(h, false, false, in, Ki, h->d_p + h->segs.w_off[i], Ki, h->d_act[i], Ni, rows, Ni, Ki,
+                           i < L - 1 ? MLP_EPI_BIAS_RELU : MLP_EPI_BIAS, h->d_p + h->segs.b_off[i], nullptr, 0, nullptr, st)))
+          return rc;
+        in = h->d_act[i];
+      }
+      // loss + un-normalised output delta + statistics
+      mlp_ce_kernel<<<cdiv(rows, 8), 256, 0, st>>>(h->d_act[L - 1], Kp, K, ys + step_offsets[s], h->d_cw, h->d_delta[L - 1],
+                                                  h->d_rowstat, rows);
+      MC_CHECK_LAUNCH();
+      mlp_stats_kernel<<<1, 256, 0, st>>>(h->d_rowstat, rows, h->d_g + h->n_flat);
+      MC_CHECK_LAUNCH();
+      h->launches += 2;
+      // backward
+      for (int i = L - 1; i >= 0; --i) {
+        const int Ki = h->dims_p[i], Ni = h->dims_p[i + 1];
+        const float* lin = i == 0 ? x : h->d_act[i - 1];
+        if ((rc = mlp_gemm(h, true, true, h->d_delta[i], Ni, lin, Ki, h->d_g + h->segs.w_off[i], Ki, Ni, Ki, rows,
+                           MLP_EPI_NONE, nullptr, nullptr, 0, h->d_g + h->segs.b_off[i], st)))
+          return rc;
+        if (i > 0 &&
+            (rc = mlp_gemm(h, false, true, h->d_delta[i], Ni, h->d_p + h->segs.w_off[i], Ki, h->d_delta[i - 1], Ki, rows, Ki,
+                           Ni, MLP_EPI_RELU_MASK, nullptr, h->d_act[i - 1], Ki, nullptr, st)))
+          return rc;
+      }
+    } else {
+      MC_CUDA(cudaMemsetAsync(h->d_g, 0, (h->n_flat + 4) * sizeof(float), st));
+    }
+    if (dp && dp->world > 1 && (rc = mc_dp_all_reduce_sum(dp, h->d_g, h->n_flat + 4, st))) return rc;
+    if (grad_sync) grad_sync(h->d_g, h->n_flat + 4, stream, user);
+    h->t++;
+    const double bc1 = 1.0 - pow((double)h->beta1, (double)h->t);
+    const double bc2 = 1.0 - pow((double)h->beta2, (double)h->t);
+    mlp_adam_kernel<<<h->n_blocks, MLP_ADAM_THREADS, 0, st>>>(h->d_p, h->d_m, h->d_v, h->d_g, h->segs, h->d_g + h->n_flat,
+                                                             h->lr, h->alpha, h->beta1, h->beta2, h->eps, (float)bc1,
+                                                             (float)sqrt(bc2), h->d_ssq[h->ssq_cur], h->n_blocks,
+                                                             h->d_ssq[h->ssq_cur ^ 1], h->d_loss);
+    MC_CHECK_LAUNCH();
+    h->launches++;
+    h->ssq_cur ^= 1;
+  }
+  if (loss_out_host) {
+    double acc[2] = {0.0, 0.0};
+    MC_CUDA(cudaMemcpyAsync(acc, h->d_loss, sizeof(acc), cudaMemcpyDeviceToHost, st));
+    MC_CUDA(cudaStreamSynchronize(st));
+    *loss_out_host = acc[1] > 0.0 ? acc[0] / acc[1] : 0.0;
+  }
+  return MC_OK;
+}
+
+int mc_mlp_get_params(mc_mlp* h, float* const* weights_host, float* const* biases_host) {
+  if (!h || !weights_host || !biases_host) return fail(MC_ERR_BAD_ARG, "mc_mlp_get_params: null");
+  DeviceGuard g(h->device);
+  std::vector<float> flat((size_t)h->n_flat);
+  MC_CUDA(cudaMemcpy(flat.data(), h->d_p, h->n_flat * sizeof(float), cudaMemcpyDeviceToHost));
+  mlp_unpack(h, flat, weights_host, biases_host);
+  return MC_OK;
+}
+
+int mc_mlp_get_adam(mc_mlp* h, float* const* m_w, float* const* m_b, float* const* v_w, float* const* v_b, int64_t* t_out) {
+  if (!h || !m_w || !m_b || !v_w || !v_b || !t_out) return fail(MC_ERR_BAD_ARG, "mc_mlp_get_adam: null");
+  DeviceGuard g(h->device);
+  std::vector<float> flat((size_t)h->n_flat);
+  MC_CUDA(cudaMemcpy(flat.data(), h->d_m, h->n_flat * sizeof(float), cudaMemcpyDeviceToHost));
+  mlp_unpack(h, flat, m_w, m_b);
+  MC_CUDA(cudaMemcpy(flat.data(), h->d_v, h->n_flat * sizeof(float), cudaMemcpyDeviceToHost));
+  mlp_unpack(h, flat, v_w, v_b);
+  *t_out = h->t;
+  return MC_OK;
+}
+
+int mc_mlp_set_adam(mc_mlp* h, const float* const* m_w, const float* const* m_b, const float* const* v_w,
+                    const float* const* v_b, int64_t t) {
+  if (!h || !m_w || !m_b || !v_w || !v_b || t < 0) return fail(MC_ERR_BAD_ARG, "mc_mlp_set_adam: bad argument");
+  DeviceGuard g(h->device);
+  std::vector<float> flat;
+  mlp_pack(h, m_w, m_b, flat);
+  MC_CUDA(cudaMemcpy(h->d_m, flat.data(), h->n_flat * sizeof(float), cudaMemcpyHostToDevice));
+  mlp_pack(h, v_w, v_b, flat);
+  MC_CUDA(cudaMemcpy(h->d_v, flat.data(), h->n_flat * sizeof(float), cudaMemcpyHostToDevice));
+  h->t = t;
+  return MC_OK;
+}
+
+int64_t mc_mlp_steps(const mc_mlp* h) { return h ? h->t : 0; }
+int64_t mc_mlp_launches(const mc_mlp* h) { return h ? h->launches : 0; }
+int64_t mc_mlp_grad_size(const mc_mlp* h) { return h ? h->n_flat + 4 : 0; }
+
+}  // extern "C"

@@ -1,3 +1,294 @@
-// K9: MLP training step kernels (placeholder).
+// K9: MLP-head training step kernels (fp32, CUDA cores).
+//
+// Restates the inner loop of TorchMLPClassifier.partial_fit
+// (mermaid_classifier/pyspacer/torch_classifier.py:270-297): per mini-batch
+//   logits = MLP(x);  loss = CE(logits, y, weight=class_w) + 0.5*alpha/mb * sum(W^2)
+//   backward;  Adam(lr, beta1, beta2, eps)
+// with the data-parallel split made explicit: every rank produces UN-NORMALISED sums
+//   G = sum_rows w_r * d(-log p_r[y_r])/dtheta,  wsum = sum_rows w_r,  lsum = sum_rows w_r * (-log p_r[y_r]),
+//   nrows = rows in this rank's share
+// in one flat buffer, the buffer is summed over ranks (NCCL all-reduce), and the Adam kernel
+// forms  g = G / wsum + alpha / nrows * W  -- exactly F.cross_entropy's weighted-mean reduction
+// (torch_classifier.py:283) and the per-mini-batch L2 term (:288) for the GLOBAL mini-batch.
+//
+// Flat parameter / gradient layout: [W_0 (out0 x in0) | b_0 | W_1 | b_1 | ... ] with every width
+// padded to a multiple of 4 (zero weights; padded classes are excluded from the softmax), then
+// 4 statistics floats [wsum, lsum, nrows, 0] at the end of the gradient buffer only.
 #pragma once
 #include "common.cuh"
+#include "head.cuh"
+
+namespace mc {
+
+enum { MLP_EPI_NONE = 0, MLP_EPI_BIAS_RELU = 1, MLP_EPI_BIAS = 2, MLP_EPI_RELU_MASK = 3 };
+
+// C[m][n] = sum_k A(m,k) * B(k,n)      (64 x 64 x 16 tiles, 256 threads, 4x4 micro-tile)
+//   A_MC == false: A[m * lda + k]   (k contiguous)      A_MC == true: A[k * lda + m]
+//   B_NC == false: B[n * ldb + k]   (k contiguous)      B_NC == true: B[k * ldb + n]
+// Contiguous dimensions must be multiples of 4 (16-byte vector loads); the other one is free.
+// gridDim.z > 1 = split-K: slice z accumulates k in [z*k_per_split, (z+1)*k_per_split) and stores
+// the raw partial to C + z * M * ldc (the epilogue then runs in mlp_splitk_epilogue_kernel).
+// colsum (A_MC only): CTAs with blockIdx.y == 0 also write colsum[m] = sum_k A(m,k)  (bias gradient).
+template <bool A_MC, bool B_NC>
+__global__ void __launch_bounds__(256)
+mlp_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                int M, int N, int K, int k_per_split, int epi, const float* __restrict__ bias,
+                const float* __restrict__ mask, int ldmask, float* __restrict__ colsum) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float csum = 0.f;
+  const bool do_colsum = A_MC && colsum != nullptr && blockIdx.y == 0;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (A_MC) {
+      const int k = k0 + (tid >> 4), m = m0 + (tid & 15) * 4;
+      if (k < kend && m < M) a4 = *reinterpret_cast<const float4*>(A + (int64_t)k * lda + m);
+    } else {
+      const int m = m0 + (tid >> 2), k = k0 + (tid & 3) * 4;
+      if (m < M && k < kend) a4 = *reinterpret_cast<const float4*>(A + (int64_t)m * lda + k);
+    }
+    if (B_NC) {
+      const int k = k0 + (tid >> 4), n = n0 + (tid & 15) * 4;
+      if (k < kend && n < N) b4 = *reinterpret_cast<const float4*>(B + (int64_t)k * ldb + n);
+    } else {
+      const int n = n0 + (tid >> 2), k = k0 + (tid & 3) * 4;
+      if (n < N && k < kend) b4 = *reinterpret_cast<const float4*>(B + (int64_t)n * ldb + k);
+    }
+    __syncthreads();
+    if (A_MC) {
+      *reinterpret_cast<float4*>(&As[tid >> 4][(tid & 15) * 4]) = a4;
+    } else {
+      const int r = tid >> 2, kk = (tid & 3) * 4;
+      As[kk + 0][r] = a4.x; As[kk + 1][r] = a4.y; As[kk + 2][r] = a4.z; As[kk + 3][r] = a4.w;
+    }
+    if (B_NC) {
+      *reinterpret_cast<float4*>(&Bs[tid >> 4][(tid & 15) * 4]) = b4;
+    } else {
+      const int r = tid >> 2, kk = (tid & 3) * 4;
+      Bs[kk + 0][r] = b4.x; Bs[kk + 1][r] = b4.y; Bs[kk + 2][r] = b4.z; Bs[kk + 3][r] = b4.w;
+    }
+    __syncthreads();
+    if (do_colsum && tid < BM) {
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) csum += As[kk][tid];   // rows past kend were stored as zeros
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+  if (do_colsum && tid < BM && m0 + tid < M) colsum[m0 + tid] = csum;
+  const int n = n0 + tx * 4;
+  if (n >= N) return;
+  const bool split = gridDim.z > 1;
+  float* Cz = C + (split ? (int64_t)blockIdx.z * M * ldc : 0);
+  float bi[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!split && (epi == MLP_EPI_BIAS_RELU || epi == MLP_EPI_BIAS)) {
+    const float4 t = *reinterpret_cast<const float4*>(bias + n);
+    bi[0] = t.x; bi[1] = t.y; bi[2] = t.z; bi[3] = t.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j];
+    if (!split) {
+      if (epi == MLP_EPI_BIAS_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j] + bi[j], 0.f);
+      } else if (epi == MLP_EPI_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += bi[j];
+      } else if (epi == MLP_EPI_RELU_MASK) {
+        const float4 mk = *reinterpret_cast<const float4*>(mask + (int64_t)m * ldmask + n);
+        v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
+        v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(Cz + (int64_t)m * ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// Sum the split-K partials in slice order (deterministic) and apply the epilogue.
+__global__ void mlp_splitk_epilogue_kernel(const float* __restrict__ part, int splits, float* __restrict__ C, int M, int N,
+                                           int epi, const float* __restrict__ bias) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)M * N / 4;
+  if (t >= total) return;
+  const int n = (int)((t * 4) % N);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < splits; ++z) {
+    const float4 p = *reinterpret_cast<const float4*>(part + (int64_t)z * M * N + t * 4);
+    s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+  }
+  if (epi == MLP_EPI_BIAS_RELU || epi == MLP_EPI_BIAS) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + n);
+    s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+    if (epi == MLP_EPI_BIAS_RELU) {
+      s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
+    }
+  }
+  *reinterpret_cast<float4*>(C + t * 4) = s;
+}
+
+// One warp per mini-batch row: log-softmax over the K real classes, un-normalised delta
+//   delta[r][k] = w_r * (softmax_k - [k == y_r])     (padded columns K..Kp-1 = 0)
+//   row_stat[r] = (w_r, w_r * -log p[y_r])
+__global__ void mlp_ce_kernel(const float* __restrict__ logits, int Kp, int K, const int32_t* __restrict__ y,
+                              const float* __restrict__ class_w, float* __restrict__ delta,
+                              float2* __restrict__ row_stat, int rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= rows) return;
+  const float* x = logits + (int64_t)r * Kp;
+  float mx = -INFINITY;
+  for (int k = lane; k < K; k += 32) mx = fmaxf(mx, x[k]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int k = lane; k < K; k += 32) sum += expf(x[k] - mx);
+  sum = warp_sum(sum);
+  const float lse = mx + logf(sum);
+  const int yr = y[r];
+  const float w = class_w ? class_w[yr] : 1.f;
+  float* d = delta + (int64_t)r * Kp;
+  for (int k = lane; k < Kp; k += 32) {
+    float v = 0.f;
+    if (k < K) v = w * (expf(x[k] - lse) - (k == yr ? 1.f : 0.f));
+    d[k] = v;
+  }
+  if (lane == 0) row_stat[r] = make_float2(w, w * (lse - x[yr]));
+}
+
+// Fixed-order reduction of the row statistics into the 4 statistics floats of the gradient buffer.
+__global__ void mlp_stats_kernel(const float2* __restrict__ row_stat, int rows, float* __restrict__ stats) {
+  __shared__ float sw[256], sl[256];
+  float w = 0.f, l = 0.f;
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    const float2 s = row_stat[r];
+    w += s.x;
+    l += s.y;
+  }
+  sw[threadIdx.x] = w;
+  sl[threadIdx.x] = l;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sw[threadIdx.x] += sw[threadIdx.x + o];
+      sl[threadIdx.x] += sl[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    stats[0] = sw[0];
+    stats[1] = sl[0];
+    stats[2] = (float)rows;
+    stats[3] = 0.f;
+  }
+}
+
+struct MlpSegs {
+  int n_layers;
+  int64_t w_off[8], b_off[8], end;  // weights of layer i: [w_off[i], b_off[i]); biases: [b_off[i], w_off[i+1] or end)
+};
+
+constexpr int MLP_ADAM_THREADS = 256;
+
+// sum of squares of the weight entries (not biases), one partial per block, fixed order inside a block
+__device__ __forceinline__ void block_ssq_store(float ssq, float* out) {
+  __shared__ float red[MLP_ADAM_THREADS];
+  red[threadIdx.x] = ssq;
+  __syncthreads();
+  for (int o = MLP_ADAM_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
+__device__ __forceinline__ bool mlp_is_weight(const MlpSegs& s, int64_t i) {
+  bool w = false;
+  for (int l = 0; l < s.n_layers; ++l) w = w || (i >= s.w_off[l] && i < s.b_off[l]);
+  return w;
+}
+
+__global__ void __launch_bounds__(MLP_ADAM_THREADS)
+mlp_ssq_kernel(const float* __restrict__ p, MlpSegs segs, float* __restrict__ ssq_part) {
+  const int64_t i = (int64_t)blockIdx.x * MLP_ADAM_THREADS + threadIdx.x;
+  float s = 0.f;
+  if (i < segs.end && mlp_is_weight(segs, i)) s = p[i] * p[i];
+  block_ssq_store(s, ssq_part + blockIdx.x);
+}
+
+// Adam step on the flat parameter vector (torch.optim.Adam semantics: eps added to sqrt(v_hat)).
+//   g = G / wsum + (alpha / nrows) * W   for weights,  G / wsum for biases.
+// Block 0 also books the mini-batch loss:  loss_acc += (lsum / wsum + 0.5 * alpha / nrows * ssq_prev) * nrows,
+// rows_acc += nrows, where ssq_prev = sum(W^2) BEFORE this update (partials written by the previous step).
+__global__ void __launch_bounds__(MLP_ADAM_THREADS)
+mlp_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ G,
+                MlpSegs segs, const float* __restrict__ stats, float lr, float alpha, float beta1, float beta2, float eps,
+                float bc1, float bc2_sqrt, const float* __restrict__ ssq_prev, int n_ssq, float* __restrict__ ssq_next,
+                double* __restrict__ loss_acc) {
+  const float wsum = stats[0], nrows = stats[2];
+  const int64_t i = (int64_t)blockIdx.x * MLP_ADAM_THREADS + threadIdx.x;
+  float s = 0.f;
+  if (i < segs.end && nrows > 0.f) {
+    const bool isw = mlp_is_weight(segs, i);
+    const float pi = p[i];
+    float g = wsum != 0.f ? G[i] / wsum : 0.f;
+    if (isw) g = fmaf(alpha / nrows, pi, g);
+    const float mi = beta1 * m[i] + (1.f - beta1) * g;
+    const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float pn = pi - (lr / bc1) * (mi / denom);
+    p[i] = pn;
+    if (isw) s = pn * pn;
+  } else if (i < segs.end && mlp_is_weight(segs, i)) {
+    s = p[i] * p[i];
+  }
+  block_ssq_store(s, ssq_next + blockIdx.x);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nrows > 0.f) {
+    float ssq = 0.f;
+    for (int b = 0; b < n_ssq; ++b) ssq += ssq_prev[b];
+    const double data = wsum != 0.f ? (double)stats[1] / (double)wsum : 0.0;
+    loss_acc[0] += (data + 0.5 * (double)alpha / (double)nrows * (double)ssq) * (double)nrows;
+    loss_acc[1] += (double)nrows;
+  }
+}
+
+// Rows of X (and their labels) selected by an index vector -- the shuffled order of one partial_fit
+// call (torch_classifier.py:258-264) -- into the zero-padded training layout.  order == nullptr: identity.
+__global__ void mlp_gather_rows_kernel(const float* __restrict__ X, const int32_t* __restrict__ y,
+                                       const int64_t* __restrict__ order, int D, int Dp, float* __restrict__ xs,
+                                       int32_t* __restrict__ ys, int64_t n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * Dp) return;
+  const int64_t r = t / Dp;
+  const int c = (int)(t % Dp);
+  const int64_t src = order ? order[r] : r;
+  xs[t] = c < D ? X[src * D + c] : 0.f;
+  if (c == 0) ys[r] = y[src];
+}
+
+}  // namespace mc

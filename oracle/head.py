@@ -88,6 +88,58 @@ class AdamState:
         self.t = 0
 
 
+def minibatch_sums(weights, biases, xb: torch.Tensor, yb: torch.Tensor, class_weight: torch.Tensor | None = None):
+    """UN-NORMALISED sums over the rows of one (share of a) mini-batch -- what each data-parallel
+    rank contributes to the all-reduce:  ``gW[i] = sum_r w_r * dNLL_r/dW_i``, ``gB[i]`` likewise,
+    ``wsum = sum_r w_r``, ``lsum = sum_r w_r * NLL_r`` with ``w_r = class_weight[y_r]`` (1 when
+    unweighted).  Manual backward so the oracle does not lean on autograd."""
+    L = len(weights)
+    m = xb.shape[0]
+    if m == 0:
+        return [torch.zeros_like(w) for w in weights], [torch.zeros_like(b) for b in biases], 0.0, 0.0
+    acts = [xb]
+    for i in range(L):
+        z = acts[-1] @ weights[i].T + biases[i]
+        acts.append(torch.relu(z) if i < L - 1 else z)
+    logp = F.log_softmax(acts[-1], dim=1)
+    w_r = torch.ones(m) if class_weight is None else class_weight[yb]
+    lsum = float(-(w_r * logp[torch.arange(m), yb]).sum())
+    delta = torch.exp(logp)
+    delta[torch.arange(m), yb] -= 1.0
+    delta = delta * w_r[:, None]
+    gW, gB = [None] * L, [None] * L
+    for i in reversed(range(L)):
+        gW[i] = delta.T @ acts[i]
+        gB[i] = delta.sum(0)
+        if i > 0:
+            delta = (delta @ weights[i]) * (acts[i] > 0).to(delta.dtype)
+    return gW, gB, float(w_r.sum()), lsum
+
+
+def adam_step(weights, biases, adam: AdamState, gW, gB, wsum: float, lsum: float, nrows: int, *, lr, alpha, beta_1,
+              beta_2, epsilon) -> float:
+    """Normalise the (all-reduced) sums like ``F.cross_entropy(weight=...)``'s weighted mean
+    (torch_classifier.py:283), add the per-mini-batch L2 term (``:288``) and apply one
+    ``torch.optim.Adam`` step (eps added to ``sqrt(v_hat)``).  Returns the regularised loss."""
+    loss = lsum / wsum + 0.5 * alpha / nrows * float(sum((w**2).sum() for w in weights))
+    grads = [g / wsum + (alpha / nrows) * w for g, w in zip(gW, weights)] + [g / wsum for g in gB]
+    adam.t += 1
+    bc1 = 1.0 - beta_1**adam.t
+    bc2 = 1.0 - beta_2**adam.t
+    for j, (p, g) in enumerate(zip(list(weights) + list(biases), grads)):
+        adam.m[j].mul_(beta_1).add_(g, alpha=1 - beta_1)
+        adam.v[j].mul_(beta_2).addcmul_(g, g, value=1 - beta_2)
+        denom = (adam.v[j].sqrt() / (bc2**0.5)).add_(epsilon)
+        p.addcdiv_(adam.m[j], denom, value=-lr / bc1)
+    return loss
+
+
+def rank_slice(start: int, end: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous near-equal share of shuffled positions [start, end) owned by ``rank``."""
+    m = end - start
+    return start + (m * rank) // world, start + (m * (rank + 1)) // world
+
+
 def partial_fit(
     weights,
     biases,
@@ -104,9 +156,14 @@ def partial_fit(
     shuffle: bool = True,
     random_state: int | None = 0,
     class_weight: torch.Tensor | None = None,
+    rank: int = 0,
+    world: int = 1,
+    all_reduce=None,
 ) -> float:
     """One ``partial_fit`` call; updates ``weights``/``biases``/``adam`` in place and returns the
-    ``loss_curve_`` entry.  Manual backward so the oracle does not lean on autograd."""
+    ``loss_curve_`` entry.  With ``world > 1`` this is ONE RANK of the data-parallel form: the rank
+    trains on its slice of every global mini-batch and ``all_reduce(flat_tensor)`` must sum the
+    flat buffer over ranks in place (gloo in the CPU tests, NCCL on the GPUs)."""
     X = np.asarray(X, dtype=np.float32)
     n = X.shape[0]
     mb = min(200, n) if batch_size == "auto" else min(int(batch_size), n)
@@ -115,47 +172,23 @@ def partial_fit(
         np.random.default_rng(int(random_state)).shuffle(order)
     Xt = torch.from_numpy(X[order])
     yt = torch.from_numpy(np.asarray(y_idx)[order].astype(np.int64))
-    L = len(weights)
     total, seen = 0.0, 0
     for start in range(0, n, mb):
-        xb, yb = Xt[start : start + mb], yt[start : start + mb]
-        m = xb.shape[0]
-        # forward
-        acts = [xb]
-        for i in range(L):
-            z = acts[-1] @ weights[i].T + biases[i]
-            acts.append(torch.relu(z) if i < L - 1 else z)
-        logits = acts[-1]
-        logp = F.log_softmax(logits, dim=1)
-        if class_weight is None:
-            sw = torch.full((m,), 1.0 / m)
-        else:
-            w_i = class_weight[yb]
-            sw = w_i / w_i.sum()
-        data_loss = -(sw * logp[torch.arange(m), yb]).sum()
-        reg = 0.5 * alpha / m * sum((w**2).sum() for w in weights)
-        loss = float(data_loss + reg)
-        # backward
-        delta = torch.exp(logp)
-        delta[torch.arange(m), yb] -= 1.0
-        delta = delta * sw[:, None]
-        gW, gB = [None] * L, [None] * L
-        for i in reversed(range(L)):
-            gW[i] = delta.T @ acts[i] + (alpha / m) * weights[i]
-            gB[i] = delta.sum(0)
-            if i > 0:
-                delta = (delta @ weights[i]) * (acts[i] > 0).to(delta.dtype)
-        # Adam (torch.optim.Adam semantics: eps added to sqrt(v_hat))
-        adam.t += 1
-        bc1 = 1.0 - beta_1**adam.t
-        bc2 = 1.0 - beta_2**adam.t
-        params = list(weights) + list(biases)
-        grads = gW + gB
-        for j, (p, g) in enumerate(zip(params, grads)):
-            adam.m[j].mul_(beta_1).add_(g, alpha=1 - beta_1)
-            adam.v[j].mul_(beta_2).addcmul_(g, g, value=1 - beta_2)
-            denom = (adam.v[j].sqrt() / (bc2**0.5)).add_(epsilon)
-            p.addcdiv_(adam.m[j], denom, value=-lr / bc1)
-        total += loss * m
-        seen += m
+        end = min(start + mb, n)
+        lo, hi = rank_slice(start, end, rank, world)
+        gW, gB, wsum, lsum = minibatch_sums(weights, biases, Xt[lo:hi], yt[lo:hi], class_weight)
+        nrows = hi - lo
+        if world > 1:
+            flat = torch.cat([g.reshape(-1) for g in gW + gB] + [torch.tensor([wsum, lsum, float(nrows)])])
+            all_reduce(flat)
+            off = 0
+            for lst in (gW, gB):
+                for j, g in enumerate(lst):
+                    lst[j] = flat[off : off + g.numel()].reshape(g.shape)
+                    off += g.numel()
+            wsum, lsum, nrows = float(flat[off]), float(flat[off + 1]), int(round(float(flat[off + 2])))
+        loss = adam_step(weights, biases, adam, gW, gB, wsum, lsum, nrows, lr=lr, alpha=alpha, beta_1=beta_1,
+                         beta_2=beta_2, epsilon=epsilon)
+        total += loss * nrows
+        seen += nrows
     return total / max(seen, 1)

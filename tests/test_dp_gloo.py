@@ -1,0 +1,126 @@
+"""World-size-2 CPU tests (gloo) of the host-side multi-GPU logic:
+
+* image sharding of the extraction path (rank = image_index % world, no collective);
+* the data-parallel training protocol -- what each rank puts in the flat buffer, what is summed,
+  and how the Adam step normalises it -- which the GPU path (mc_mlp_partial_fit + NCCL) follows
+  step for step.  The single-process oracle it is compared with is pinned to the reference
+  (tests/test_oracle_head.py).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mermaid_classifier_b200.sharding import images_for_rank, merge_rank_outputs
+from mermaid_classifier_b200.torch_classifier import split_steps
+from oracle import head as ohead
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cluster(n, d, k, seed):
+    rng = np.random.RandomState(seed)
+    centers = rng.randn(k, d) * 3.0
+    y = rng.randint(0, k, size=n)
+    return (centers[y] + rng.randn(n, d) * 1.3).astype(np.float32), y
+
+
+def _train_rank(rank, world, port, X, y, cw, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    w, b = ohead.init_mlp(X.shape[1], (16, 8), 5, 0)
+    adam = ohead.AdamState(w + b)
+    curve = [ohead.partial_fit(w, b, adam, X, y, lr=1e-3, random_state=0, class_weight=cw, rank=rank, world=world,
+                               all_reduce=lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) for _ in range(2)]
+    # every rank must hold identical parameters after identical all-reduced updates
+    flat = torch.cat([p.reshape(-1) for p in w + b])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    if rank == 0:
+        out.put((curve, [p.numpy() for p in w + b], same, adam.t))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_data_parallel_protocol_matches_single_process(weighted):
+    X, y = _cluster(650, 32, 5, 42)  # 3 full mini-batches + ragged 50 (25 rows per rank in the tail)
+    cw = torch.tensor([0.5 + 0.5 * i for i in range(5)]) if weighted else None
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_rank, args=(r, 2, port, X, y, cw, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    curve, params, same, t = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w, b = ohead.init_mlp(32, (16, 8), 5, 0)
+    adam = ohead.AdamState(w + b)
+    want = [ohead.partial_fit(w, b, adam, X, y, lr=1e-3, random_state=0, class_weight=cw) for _ in range(2)]
+    assert same and t == adam.t == 8
+    np.testing.assert_allclose(curve, want, rtol=1e-5)
+    for got, ref in zip(params, w + b):
+        np.testing.assert_allclose(got, ref.numpy(), atol=1e-5, rtol=1e-4)
+
+
+def test_split_steps_partitions_every_minibatch():
+    for n, mb, world in [(650, 200, 2), (1000, 200, 8), (7, 200, 4), (401, 200, 3), (0, 200, 2)]:
+        seen = []
+        per_step = None
+        for r in range(world):
+            pos, off = split_steps(n, mb, r, world)
+            assert off[0] == 0 and off[-1] == len(pos) and np.all(np.diff(off) >= 0)
+            assert len(off) - 1 == (n + mb - 1) // mb   # every rank takes part in every step (all-reduce!)
+            sizes = np.diff(off)
+            per_step = sizes if per_step is None else per_step + sizes
+            seen.append(pos)
+        allpos = np.sort(np.concatenate(seen)) if seen else np.zeros(0)
+        assert np.array_equal(allpos, np.arange(n))
+        if n:
+            want = [min(mb, n - s) for s in range(0, n, mb)]
+            assert per_step.tolist() == want
+
+
+def _shard_rank(rank, world, port, n_images, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = images_for_rank(n_images, rank, world)
+    # stand-in for the per-image feature rows: row value = image index (no collective on the data path)
+    feats = {i: np.full((3, 4), i, dtype=np.float32) for i in mine}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (mine, feats))   # host-side bookkeeping only (counters / manifest)
+    if rank == 0:
+        out.put(gathered)
+    dist.destroy_process_group()
+
+
+def test_image_sharding_covers_all_images_once():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_rank, args=(r, 2, port, 11, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [m for m, _ in gathered] == [[0, 2, 4, 6, 8, 10], [1, 3, 5, 7, 9]]
+    merged = merge_rank_outputs([f for _, f in gathered], 11)
+    assert [int(a[0, 0]) for a in merged] == list(range(11))
+    for world in (1, 2, 4, 8):
+        cover = sorted(i for r in range(world) for i in images_for_rank(100, r, world))
+        assert cover == list(range(100))
