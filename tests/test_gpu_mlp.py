@@ -140,7 +140,7 @@ def test_errors_and_sklearn_protocol():
         TorchMLPClassifier(solver="sgd")
     clf = TorchMLPClassifier(hidden_layer_sizes=(8,), random_state=0)
     with pytest.raises(RuntimeError):
-        clf.predict(np.zeros((2, 4), np.float32))
+        clf.predict_proba(np.zeros((2, 4), np.float32))  # torch_classifier.py:333-337
     X, y = cluster_data(50, 12, 3, 0)
     clf.partial_fit(X, y, classes=[0, 1, 2])
     with pytest.raises(ValueError):
