@@ -1,0 +1,164 @@
+"""The callers either side of the hot path, restated over the B200 extractor / predictor.
+
+* :func:`prepare_points`           -- ``prepare_source`` grouping, ``scripts/build_feature_bucket.py:658-665``
+* :func:`extract_features`         -- ``spacer.tasks.extract_features(msg)`` as the reference calls it,
+                                      ``scripts/build_feature_bucket.py:775`` (load image, validate, extract, store)
+* :func:`classify_features`        -- pyspacer ``classify_features``-shaped scorer over a ``Predictor``
+                                      (``pyspacer/annotation.py:243-261``: per-point top scores)
+* :func:`build_feature_bucket`     -- the per-source loop of ``process_source``,
+                                      ``scripts/build_feature_bucket.py:691-788``: key layout
+                                      ``s{sid}/features/i{iid}.featurevector``, skip-existing, per-image error
+                                      capture, counters; images are sharded round-robin over ranks
+* :func:`stack_feature_files`      -- ``scripts/extract_reference_features.py:40-61`` (``(N, 1280) float32 .npy``)
+
+Storage is the filesystem / in-memory ``DataLocation`` of :mod:`spacer_compat` (S3 needs pyspacer + network and
+is out of scope); everything numerical runs in libmermaid_b200.
+"""
+
+from __future__ import annotations
+
+import csv
+import time
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Any, Iterable, Mapping, Sequence
+
+import numpy as np
+
+from .sharding import images_for_rank
+from .spacer_compat import (
+    DataLocation,
+    ExtractFeaturesMsg,
+    ExtractFeaturesReturnMsg,
+    ImageFeatures,
+    check_extract_inputs,
+    load_image,
+    storage_factory,
+)
+
+
+def prepare_points(rows: Iterable[int], cols: Iterable[int]) -> list[tuple[int, int]]:
+    """Sorted set of unique ``(row, col)`` int pairs -- defines the output row order."""
+    return sorted({(int(r), int(c)) for r, c in zip(rows, cols)})
+
+
+def feature_key(source_id: str | int, image_id: str | int) -> str:
+    return f"s{source_id}/features/i{image_id}.featurevector"
+
+
+def image_key(source_prefix: str, source_id: str | int, image_id: str | int) -> str:
+    return f"{source_prefix}s{source_id}/images/{image_id}.jpg"
+
+
+def extract_features(msg: ExtractFeaturesMsg) -> ExtractFeaturesReturnMsg:
+    """Load ``msg.image_loc``, validate the points, run ``msg.extractor`` and store ``msg.feature_loc``."""
+    t0 = time.time()
+    img = load_image(msg.image_loc)
+    check_extract_inputs(img, msg.rowcols, getattr(msg.image_loc, "key", ""))
+    features, ret = msg.extractor(img, msg.rowcols)
+    features.store(msg.feature_loc)
+    return ExtractFeaturesReturnMsg(extractor_loaded_remotely=ret.extractor_loaded_remotely, runtime=time.time() - t0)
+
+
+def classify_features(features: Any, predictor: Any, top_k: int | None = None) -> dict[str, Any]:
+    """Score an ``ImageFeatures`` (or an ``(N, D)`` array) with a ``Predictor``.
+
+    Returns ``{"classes": [...], "scores": [(row, col, [p_0..p_K-1]), ...]}``; with ``top_k`` each entry
+    carries instead the ``top_k`` ``(label, score)`` pairs in descending order, ties in class order
+    (``annotation.py:252-261``), selected on the device."""
+    if isinstance(features, ImageFeatures):
+        rowcols = [(pf.row, pf.col) for pf in features.point_features]
+        X = np.asarray([pf.data for pf in features.point_features], dtype=np.float32).reshape(len(rowcols), -1)
+    else:
+        X = np.asarray(features, dtype=np.float32)
+        rowcols = [(None, None)] * X.shape[0]
+    if top_k:
+        labels, scores = predictor.predict_topk(X, top_k)
+        out = [(r, c, list(zip(labels[i].tolist(), scores[i].tolist()))) for i, (r, c) in enumerate(rowcols)]
+    else:
+        proba = predictor.predict_proba(X)
+        out = [(r, c, proba[i].tolist()) for i, (r, c) in enumerate(rowcols)]
+    return {"classes": list(predictor.classes), "scores": out}
+
+
+@dataclass
+class RunCounters:
+    sources_done: int = 0
+    sources_skipped: int = 0
+    images_ok: int = 0
+    images_skipped: int = 0
+    images_failed: int = 0
+    patches: int = 0
+    started: float = field(default_factory=time.monotonic)
+
+
+def build_feature_bucket(
+    sources: Mapping[str, Mapping[str, Sequence[tuple[int, int]]]],
+    extractor: Any,
+    *,
+    source_root: str | Path,
+    target_root: str | Path,
+    source_prefix: str = "",
+    skip_existing: bool = True,
+    rank: int = 0,
+    world: int = 1,
+    error_csv: str | Path | None = None,
+) -> RunCounters:
+    """Extract every image of every source into ``target_root/s{sid}/features/i{iid}.featurevector``.
+
+    ``sources[sid][iid]`` is the image's rowcols (see :func:`prepare_points`).  Images of a source are walked in
+    sorted id order and dealt round-robin to ranks (``index % world == rank``); a failing image is recorded and
+    the run continues (``build_feature_bucket.py:774-786``)."""
+    counters = RunCounters()
+    source_root, target_root = Path(source_root), Path(target_root)
+    err_file = open(error_csv, "a", newline="") if error_csv else None
+    err = csv.writer(err_file) if err_file else None
+    try:
+        for sid in sorted(sources):
+            grouped = sources[sid]
+            if not grouped:
+                counters.sources_skipped += 1
+                continue
+            ids = sorted(grouped)
+            for k in images_for_rank(len(ids), rank, world):
+                iid = ids[k]
+                rowcols = list(grouped[iid])
+                floc = DataLocation("filesystem", str(target_root / feature_key(sid, iid)))
+                if not rowcols:
+                    counters.images_skipped += 1
+                    continue
+                if skip_existing and storage_factory("filesystem").exists(floc.key):
+                    counters.images_skipped += 1
+                    continue
+                msg = ExtractFeaturesMsg(
+                    job_token=f"s{sid}_i{iid}", extractor=extractor, rowcols=rowcols,
+                    image_loc=DataLocation("filesystem", str(source_root / image_key(source_prefix, sid, iid))),
+                    feature_loc=floc)
+                try:
+                    extract_features(msg)
+                    counters.images_ok += 1
+                    counters.patches += len(rowcols)
+                except KeyboardInterrupt:
+                    raise
+                except Exception as exc:  # per-image failure: log and carry on
+                    counters.images_failed += 1
+                    if err:
+                        err.writerow([sid, iid, type(exc).__name__, str(exc)])
+            counters.sources_done += 1
+    finally:
+        if err_file:
+            err_file.close()
+    return counters
+
+
+def stack_feature_files(paths: Sequence[str | Path], out: str | Path) -> np.ndarray:
+    """Concatenate the per-point vectors of ``.featurevector`` files into an ``(N, D) float32 .npy``."""
+    vectors: list[Any] = []
+    for p in paths:
+        feats = ImageFeatures.load(DataLocation("filesystem", str(p)))
+        vectors.extend(pf.data for pf in feats.point_features)
+    X = np.asarray(vectors, dtype=np.float32)
+    if X.ndim != 2:
+        raise SystemExit(f"expected a 2-D feature matrix; got shape {X.shape}")
+    np.save(out, X)
+    return X

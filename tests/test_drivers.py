@@ -1,0 +1,85 @@
+"""Host logic either side of the hot path (no GPU): point grouping, bucket key layout, skip-existing,
+per-image error capture, rank sharding of the bucket driver, .featurevector round trip and stacking."""
+import numpy as np
+from PIL import Image
+
+from mermaid_classifier_b200 import drivers
+from mermaid_classifier_b200.spacer_compat import (
+    DataLocation,
+    ExtractFeaturesReturnMsg,
+    ImageFeatures,
+    image_features_from_array,
+)
+
+
+class FakeExtractor:
+    """Stands in for the GPU extractor: feature = (row, col, mean pixel) so results are checkable."""
+
+    def __init__(self):
+        self.calls = 0
+
+    def __call__(self, im, rowcols):
+        self.calls += 1
+        arr = np.asarray(im)
+        feats = np.array([[r, c, arr.mean()] + [0.0] * 5 for r, c in rowcols], dtype=np.float32)
+        return image_features_from_array(rowcols, feats), ExtractFeaturesReturnMsg(False, 0.0)
+
+
+def test_prepare_points_sorted_unique():
+    assert drivers.prepare_points([5, 1, 5, 1], [2, 9, 2, 3]) == [(1, 3), (1, 9), (5, 2)]
+
+
+def test_image_features_round_trip(tmp_path):
+    feats = np.random.RandomState(0).randn(4, 1280).astype(np.float32)
+    rc = [(3, 4), (10, 2), (10, 7), (99, 0)]
+    f = image_features_from_array(rc, feats)
+    loc = DataLocation("filesystem", str(tmp_path / "s1" / "features" / "i7.featurevector"))
+    f.store(loc)
+    g = ImageFeatures.load(loc)
+    assert g.valid_rowcol and g.npoints == 4 and g.feature_dim == 1280
+    assert np.array_equal(g.get_array((10, 7)), feats[2])  # lossless fp32
+    assert [(p.row, p.col) for p in g.point_features] == rc
+
+
+def test_bucket_driver_layout_skip_errors_and_sharding(tmp_path):
+    src, tgt = tmp_path / "src", tmp_path / "tgt"
+    sources = {"12": {}, "7": {}}
+    for sid, n in (("12", 5), ("7", 2)):
+        (src / f"s{sid}" / "images").mkdir(parents=True)
+        for i in range(n):
+            Image.fromarray(np.full((40, 50, 3), 10 * i, np.uint8)).save(src / f"s{sid}" / "images" / f"{i}.jpg")
+            sources[sid][str(i)] = [(1, 2), (3, 4)]
+    sources["12"]["3"] = [(1, 2), (400, 4)]      # out-of-bounds point -> per-image failure, run continues
+    sources["12"]["4"] = []                       # no rowcols -> skipped
+    ex = FakeExtractor()
+    c0 = drivers.build_feature_bucket(sources, ex, source_root=src, target_root=tgt, rank=0, world=2,
+                                      error_csv=tmp_path / "err.csv")
+    c1 = drivers.build_feature_bucket(sources, ex, source_root=src, target_root=tgt, rank=1, world=2,
+                                      error_csv=tmp_path / "err.csv")
+    assert c0.images_ok + c1.images_ok == 5 and c0.images_failed + c1.images_failed == 1
+    assert c0.images_skipped + c1.images_skipped == 1 and c0.sources_done == 2
+    assert sorted(p.name for p in (tgt / "s12" / "features").iterdir()) == ["i0.featurevector", "i1.featurevector", "i2.featurevector"]
+    assert "RowColumnInvalidError" in (tmp_path / "err.csv").read_text()
+    calls = ex.calls
+    again = drivers.build_feature_bucket(sources, ex, source_root=src, target_root=tgt, skip_existing=True)
+    # only the failing image is retried, and it fails validation again before reaching the extractor
+    assert again.images_ok == 0 and again.images_skipped == 6 and again.images_failed == 1 and ex.calls == calls
+    X = drivers.stack_feature_files(sorted((tgt / "s7" / "features").iterdir()), tmp_path / "ref.npy")
+    assert X.shape == (4, 8) and X.dtype == np.float32 and np.load(tmp_path / "ref.npy").shape == (4, 8)
+
+
+def test_classify_features_shapes():
+    class P:
+        classes = ["a", "b", "c"]
+
+        def predict_proba(self, X):
+            return np.tile(np.array([[0.2, 0.5, 0.3]]), (X.shape[0], 1))
+
+        def predict_topk(self, X, k):
+            return np.array([["b", "c"]] * X.shape[0], dtype=object), np.array([[0.5, 0.3]] * X.shape[0])
+
+    f = image_features_from_array([(1, 2), (3, 4)], np.zeros((2, 8), np.float32))
+    out = drivers.classify_features(f, P())
+    assert out["classes"] == ["a", "b", "c"] and out["scores"][1][:2] == (3, 4) and len(out["scores"][0][2]) == 3
+    top = drivers.classify_features(f, P(), top_k=2)
+    assert top["scores"][0][2] == [("b", 0.5), ("c", 0.3)]
