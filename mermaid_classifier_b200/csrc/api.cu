@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "crop_stem.cuh"
 #include "dwconv_se.cuh"
+#include "dw_tma.cuh"
 #include "head.cuh"
 #include "layers.h"
 #include "mlp_train.cuh"
@@ -107,7 +108,9 @@ struct mc_extractor {
   int64_t cap_feats = 0;
   std::vector<mc_point> h_points;
   PwTcPlan* tc = nullptr;  // tcgen05 GEMM plans (pw_tc.cuh)
+  std::vector<DwLayer> dw;  // TMA-staged depthwise plans (dw_tma.cuh), one per block
   int64_t launches = 0;
+  int64_t l2_budget = 0;  // bytes of per-chunk working set kept L2-resident (0 = no chunking)
   int tap_layer = -1;
   float* tap_out = nullptr;
   int64_t tap_cap = 0;
@@ -171,32 +174,33 @@ int pick_cgt(int cg) {
 }
 
 template <typename T>
-int launch_dw(mc_extractor* h, const BlockCfg& b, const T* in, T* out, int nb, cudaStream_t st) {
+int launch_dw(mc_extractor* h, const BlockCfg& b, int n_off, T* out, int nb, cudaStream_t st) {
   const float* P = h->d_params;
   const int C = b.c_mid;
   const int bidx = (int)(&b - &h->net.blocks[0]);
-  int nparts = 0;
+  DwLayer& l = h->dw[bidx];
+  const int nparts = l.nbands;
   {
     ProfScope ps_dw(h, 2 + 4 * bidx, st);
-    // rolling-accumulator kernel: 4-channel groups, channel-sliced CTAs
-    const int CG = C / 4, cgt = pick_cgt(CG), cz = CG / cgt;
-    const int TW = 2;
-    const int nstrips = cdiv(b.h_out, TW);
-    const int pt_max = std::max(1, std::min(nstrips, 256 / cgt));
-    const int nx = cdiv(nstrips, pt_max);
-    const int pt = cdiv(nstrips, nx);  // balanced strip chunks (no mostly-idle trailing CTA)
-    const int rpb = b.h_out >= 112 ? 16 : (b.h_out >= 56 ? 14 : b.h_out);
-    const int nbands = cdiv(b.h_out, rpb);
-    nparts = nbands * nx;
-    dim3 block(cgt, pt), grid(nparts, nb, cz);
-    const size_t smem = ((size_t)b.k * b.k * cgt * 4 + (size_t)pt * cgt * 4) * sizeof(float);
-#define DW_ARGS in, P + b.w_dw, P + b.s_dw, P + b.b_dw, out, h->d_pool, C, b.h_in, b.h_out, b.pad, rpb, nx
-    if (b.k == 3 && b.stride == 1) dwconv_roll_kernel<T, 3, 1, 2><<<grid, block, smem, st>>>(DW_ARGS);
-    else if (b.k == 5 && b.stride == 1) dwconv_roll_kernel<T, 5, 1, 2><<<grid, block, smem, st>>>(DW_ARGS);
-    else if (b.k == 3 && b.stride == 2) dwconv_roll_kernel<T, 3, 2, 2><<<grid, block, smem, st>>>(DW_ARGS);
-    else if (b.k == 5 && b.stride == 2) dwconv_roll_kernel<T, 5, 2, 2><<<grid, block, smem, st>>>(DW_ARGS);
-    else return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
-#undef DW_ARGS
+    DwArgs a;
+    a.w = P + b.w_dw;
+    a.scale = P + b.s_dw;
+    a.bias = P + b.b_dw;
+    a.out = out;
+    a.pool_partial = h->d_pool;
+    a.C = C;
+    a.Hin = b.h_in;
+    a.Hout = b.h_out;
+    a.pad = b.pad;
+    a.rows_per_band = l.rows_per_band;
+    a.cgt = l.cgt;
+    a.pt = l.pt;
+    a.bwin = l.bwin;
+    a.stages = l.stages;
+    a.row_bytes = l.row_bytes;
+    a.box_bytes = l.box_bytes;
+    a.n_off = n_off;
+    if (int rc = dw_tma_launch<T>(l, l.tm, a, nb, st)) return rc;
   }
   MC_CHECK_LAUNCH();
   h->launches++;
@@ -261,48 +265,65 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
   MC_CHECK_LAUNCH();
   h->launches++;
   if ((rc = tap<T>(h, 0, X, (int64_t)nb * 112 * 112 * 32, st))) return rc;
+  // L2-resident chunked execution: each MBConv block runs expand -> depthwise -> SE -> project over
+  // chunks of patches small enough that the expanded map E and the depthwise output D of a chunk
+  // (which every chunk re-uses at the same addresses) stay in the 126 MB L2 between producer and
+  // consumer; only the block input X and output Y stream through HBM.
+  const bool tapping = h->tap_layer >= 0 && h->tap_out != nullptr;
   for (size_t bi = 0; bi < net.blocks.size(); ++bi) {
     const BlockCfg& b = net.blocks[bi];
-    const int64_t Min = (int64_t)nb * b.h_in * b.h_in, Mout = (int64_t)nb * b.h_out * b.h_out;
-    const T* dw_in = X;
-    if (b.expand != 1) {
-      ProfScope ps(h, 1 + 4 * (int)bi, st);
-      if (h->tc && pw_tc_has(h->tc, (int)bi * 2)) {
-        if ((rc = pw_tc_run(h->tc, (int)bi * 2, X, nullptr, nullptr, E, Min, b.h_in * b.h_in, st))) return rc;
-        h->launches++;
-      } else if ((rc = launch_pw_simt<T, ACT_SILU, false, false>(h, X, P + b.w_exp, P + b.s_exp, P + b.b_exp, nullptr,
-                                                                 nullptr, E, Min, b.c_mid, b.c_in, 1, st)))
-        return rc;
-      dw_in = E;
+    const int HWi = b.h_in * b.h_in, HW = b.h_out * b.h_out;
+    const int64_t per_patch = ((int64_t)HWi * (b.c_in + (b.expand != 1 ? b.c_mid : 0)) + (int64_t)HW * (b.c_mid + b.c_out)) *
+                              (int64_t)sizeof(T);
+    int chunk = nb;
+    if (h->l2_budget > 0 && !tapping) {
+      chunk = (int)std::max<int64_t>(1, std::min<int64_t>(nb, h->l2_budget / per_patch));
+      chunk = cdiv(nb, cdiv(nb, chunk));  // equal-sized chunks
     }
-    if (b.expand != 1 && (rc = tap<T>(h, 1 + 4 * (int)bi, E, Min * b.c_mid, st))) return rc;
-    if ((rc = launch_dw<T>(h, b, dw_in, D, nb, st))) return rc;
-    if ((rc = tap<T>(h, 2 + 4 * (int)bi, D, Mout * b.c_mid, st))) return rc;
-    if ((rc = tap<float>(h, 3 + 4 * (int)bi, h->d_gate, (int64_t)nb * b.c_mid, st))) return rc;
-    const int HW = b.h_out * b.h_out;
-    ProfScope ps_proj(h, 4 + 4 * (int)bi, st);
-    if (h->tc && pw_tc_has(h->tc, (int)bi * 2 + 1)) {
-      const void* gp = h->mode == MC_MODE_BF16 ? (const void*)h->d_gate_h : (const void*)h->d_gate;
-      if ((rc = pw_tc_run(h->tc, (int)bi * 2 + 1, D, gp, b.skip ? X : nullptr, Y, Mout, HW, st))) return rc;
-      h->launches++;
-    } else if (b.skip) {
-      if ((rc = launch_pw_simt<T, ACT_NONE, true, true>(h, D, P + b.w_proj, P + b.s_proj, P + b.b_proj, h->d_gate, X, Y,
-                                                        Mout, b.c_out, b.c_mid, HW, st)))
-        return rc;
-    } else {
-      if ((rc = launch_pw_simt<T, ACT_NONE, true, false>(h, D, P + b.w_proj, P + b.s_proj, P + b.b_proj, h->d_gate,
-                                                         nullptr, Y, Mout, b.c_out, b.c_mid, HW, st)))
-        return rc;
+    for (int c0 = 0; c0 < nb; c0 += chunk) {
+      const int cn = std::min(chunk, nb - c0);
+      const int64_t Min = (int64_t)cn * HWi, Mout = (int64_t)cn * HW;
+      const T* Xc = X + (int64_t)c0 * HWi * b.c_in;
+      T* Yc = Y + (int64_t)c0 * HW * b.c_out;
+      const T* dw_in = Xc;
+      if (b.expand != 1) {
+        ProfScope ps(h, 1 + 4 * (int)bi, st);
+        if (h->tc && pw_tc_has(h->tc, (int)bi * 2)) {
+          if ((rc = pw_tc_run(h->tc, (int)bi * 2, X, (int64_t)c0 * HWi, nullptr, nullptr, E, Min, HWi, st))) return rc;
+          h->launches++;
+        } else if ((rc = launch_pw_simt<T, ACT_SILU, false, false>(h, Xc, P + b.w_exp, P + b.s_exp, P + b.b_exp, nullptr,
+                                                                   nullptr, E, Min, b.c_mid, b.c_in, 1, st)))
+          return rc;
+        dw_in = E;
+      }
+      if (b.expand != 1 && (rc = tap<T>(h, 1 + 4 * (int)bi, E, Min * b.c_mid, st))) return rc;
+      if ((rc = launch_dw<T>(h, b, b.expand != 1 ? 0 : c0, D, cn, st))) return rc;
+      if ((rc = tap<T>(h, 2 + 4 * (int)bi, D, Mout * b.c_mid, st))) return rc;
+      if ((rc = tap<float>(h, 3 + 4 * (int)bi, h->d_gate, (int64_t)cn * b.c_mid, st))) return rc;
+      {
+        ProfScope ps_proj(h, 4 + 4 * (int)bi, st);
+        if (h->tc && pw_tc_has(h->tc, (int)bi * 2 + 1)) {
+          const void* gp = h->mode == MC_MODE_BF16 ? (const void*)h->d_gate_h : (const void*)h->d_gate;
+          if ((rc = pw_tc_run(h->tc, (int)bi * 2 + 1, D, 0, gp, b.skip ? Xc : nullptr, Yc, Mout, HW, st))) return rc;
+          h->launches++;
+        } else if (b.skip) {
+          if ((rc = launch_pw_simt<T, ACT_NONE, true, true>(h, D, P + b.w_proj, P + b.s_proj, P + b.b_proj, h->d_gate, Xc, Yc,
+                                                            Mout, b.c_out, b.c_mid, HW, st)))
+            return rc;
+        } else {
+          if ((rc = launch_pw_simt<T, ACT_NONE, true, false>(h, D, P + b.w_proj, P + b.s_proj, P + b.b_proj, h->d_gate,
+                                                             nullptr, Yc, Mout, b.c_out, b.c_mid, HW, st)))
+            return rc;
+        }
+      }
+      if ((rc = tap<T>(h, 4 + 4 * (int)bi, Yc, Mout * b.c_out, st))) return rc;
     }
-    ps_proj.~ProfScope();
-    ps_proj.on = false;
-    if ((rc = tap<T>(h, 4 + 4 * (int)bi, Y, Mout * b.c_out, st))) return rc;
     std::swap(X, Y);
   }
   const int64_t Mh = (int64_t)nb * 49;
   ProfScope ps_head(h, 65, st);
   if (h->tc && pw_tc_has(h->tc, 32)) {
-    if ((rc = pw_tc_run(h->tc, 32, X, nullptr, nullptr, Hb, Mh, 49, st))) return rc;
+    if ((rc = pw_tc_run(h->tc, 32, X, 0, nullptr, nullptr, Hb, Mh, 49, st))) return rc;
     h->launches++;
   } else if ((rc = launch_pw_simt<T, ACT_SILU, false, false>(h, X, P + net.w_head, P + net.s_head, P + net.b_head,
                                                              nullptr, nullptr, Hb, Mh, 1280, 320, 1, st)))
@@ -457,6 +478,11 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
     mc_extractor_destroy(h);
     return fail(MC_ERR_CUDA, std::string("parameter upload: ") + cudaGetErrorString(e));
   }
+  // MC_L2_MB: working-set budget of the chunked execution in MB.  Default 0 = off: measured on B200, the
+  // per-launch latency chain of ~900 small dependent launches per sub-batch costs more than the HBM
+  // traffic it saves (25 k vs 44 k patches/s at 64 MB); kept as an experiment switch.
+  h->l2_budget = 0;
+  if (const char* env = getenv("MC_L2_MB")) h->l2_budget = (int64_t)atoll(env) << 20;
   // MC_TC_MASK (hex, bit 2b = expand of block b, 2b+1 = project, 32 = head conv) selects which 1x1
   // convs run on the tcgen05 kernel; default: all of them.  Bring-up / bisecting aid only.
   unsigned long long tc_mask = ~0ull;
@@ -465,6 +491,17 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
                         (unsigned)(tc_mask >> 32)))) {
     mc_extractor_destroy(h);
     return rc;
+  }
+  h->dw.resize(h->net.blocks.size());
+  for (size_t bi = 0; bi < h->net.blocks.size(); ++bi) {
+    const BlockCfg& b = h->net.blocks[bi];
+    DwLayer& l = h->dw[bi];
+    l.in_ptr = b.expand != 1 ? h->bufE : h->bufX;  // block 0 (no expand) reads the stem output
+    if ((rc = dw_plan_layer(&l, b, mode == MC_MODE_FP32)) ||
+        (rc = dw_make_map(&l.tm, mode == MC_MODE_FP32, l.in_ptr, b.c_mid, b.h_in, max_batch, l.cgt * 4, l.bwin))) {
+      mc_extractor_destroy(h);
+      return rc;
+    }
   }
   *out = h;
   return MC_OK;

@@ -166,6 +166,7 @@ struct PwTcArgs {
   void* out;          // [M][N]
   int64_t M;
   int N, K, HW, BN, n_blocks, k_chunks, act, stages;
+  int a_row_off;      // first row of this launch inside the activation tensor map (chunked execution)
   int64_t m_tiles;
 };
 
@@ -273,7 +274,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t ph = 0;
       const uint32_t tx = Cfg::A_BYTES + (uint32_t)p.BN * 128u * (Cfg::TF32 ? 2u : 1u);
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-        const int m0 = (int)(it / p.n_blocks) * TC_BM;
+        const int m0 = (int)(it / p.n_blocks) * TC_BM + p.a_row_off;
         const int n0 = (int)(it % p.n_blocks) * p.BN;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -699,8 +700,10 @@ inline int pw_tc_build(PwTcPlan** out, const NetCfg& net, const float* params_ho
   return MC_OK;
 }
 
-inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, const void* gate, const void* res, void* outp, int64_t M, int HW,
-                     cudaStream_t st) {
+// `A` is the BASE of the activation buffer (its tensor map is cached per layer); the launch covers rows
+// [a_row_off, a_row_off + M) of it.  gate / res / outp are already offset to the launch's first row.
+inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, const void* gate, const void* res, void* outp,
+                     int64_t M, int HW, cudaStream_t st) {
   PwTcLayer& l = plan->layers[id];
   const bool f32 = plan->mode == MC_MODE_FP32;
   // tensor map of the activation source (cached: each layer only ever sees the ping-pong buffers)
@@ -721,6 +724,7 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, const void* gate, co
   a.res = res;
   a.out = outp;
   a.M = M;
+  a.a_row_off = (int)a_row_off;
   a.N = l.N;
   a.K = l.K;
   a.HW = HW;
