@@ -179,8 +179,30 @@ int launch_dw(mc_extractor* h, const BlockCfg& b, int n_off, T* out, int nb, cud
   const int C = b.c_mid;
   const int bidx = (int)(&b - &h->net.blocks[0]);
   DwLayer& l = h->dw[bidx];
-  const int nparts = l.nbands;
-  {
+  const int nparts = l.nbands * l.nxc;
+  if (l.lane) {
+    ProfScope ps_dw(h, 2 + 4 * bidx, st);
+    DwRegArgs a;
+    a.w = P + b.w_dw;
+    a.scale = P + b.s_dw;
+    a.bias = P + b.b_dw;
+    a.out = out;
+    a.pool_partial = h->d_pool;
+    a.C = C;
+    a.Hin = b.h_in;
+    a.Hout = b.h_out;
+    a.pad = b.pad;
+    a.rows_per_band = l.rows_per_band;
+    a.cgt = l.cgt;
+    a.ptc = l.ptc;
+    a.nxc = l.nxc;
+    a.stages = l.stages;
+    a.row_bytes = l.row_bytes;
+    a.box_bytes = l.box_bytes;
+    a.n_off = n_off;
+    a.nb = nb;
+    if (int rc = dw_reg_launch<T>(l, l.tm, a, nb, st)) return rc;
+  } else {
     ProfScope ps_dw(h, 2 + 4 * bidx, st);
     DwArgs a;
     a.w = P + b.w_dw;
@@ -498,7 +520,7 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
     DwLayer& l = h->dw[bi];
     l.in_ptr = b.expand != 1 ? h->bufE : h->bufX;  // block 0 (no expand) reads the stem output
     if ((rc = dw_plan_layer(&l, b, mode == MC_MODE_FP32)) ||
-        (rc = dw_make_map(&l.tm, mode == MC_MODE_FP32, l.in_ptr, b.c_mid, b.h_in, max_batch, l.cgt * 4, l.bwin))) {
+        (rc = dw_make_map(&l.tm, mode == MC_MODE_FP32, l.in_ptr, b.c_mid, b.h_in, max_batch, l.lane ? l.cb : l.cgt * 4, l.bwin))) {
       mc_extractor_destroy(h);
       return rc;
     }

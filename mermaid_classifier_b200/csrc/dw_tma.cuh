@@ -221,12 +221,234 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Register-weight variant for every layer past the two 112-wide ones.
+//
+// The kernel above re-reads its k*k weight vectors from shared memory for every input row (one
+// 16-byte load per 4*TW FMAs), which makes the 5x5 and the narrow 3x3 layers shared-memory
+// bandwidth bound (ncu: l1tex 77 %, fma 30 %).  Here a thread owns CH channels and a strip of TW
+// output columns and keeps its k*k*CH weights in REGISTERS for the whole launch, so an input row
+// costs (TW-1)*S + K vector loads against K*K*TW*CH/S FMAs.  A CTA walks several patches
+// (grid-stride over blockIdx.z), so the weights, the barrier set-up and the TMA ring are amortised
+// over them; the ring keeps streaming across patch boundaries.  Channel slices are the FASTEST grid
+// dimension: sibling slices of one patch run together and share the 128-byte lines a slice
+// boundary splits.
+struct DwRegArgs {
+  const float* w;
+  const float* scale;
+  const float* bias;
+  void* out;
+  float* pool_partial;  // [n][gridDim.y][C]
+  int C, Hin, Hout, pad, rows_per_band;
+  int cgt, ptc, nxc;    // channel groups (of CH) per CTA, column strips per CTA, column chunks per row band
+  int stages, row_bytes, box_bytes;
+  int n_off, nb;        // first patch inside the tensor map; patches in this launch
+};
+
+template <typename T, int CH>
+__device__ __forceinline__ void dw_load_ch(uint32_t addr, float (&v)[CH]);
+template <>
+__device__ __forceinline__ void dw_load_ch<float, 2>(uint32_t addr, float (&v)[2]) {
+  const uint2 r = ptx::lds64(addr);
+  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
+}
+template <>
+__device__ __forceinline__ void dw_load_ch<float, 4>(uint32_t addr, float (&v)[4]) {
+  dw_load_vec<float>(addr, v);
+}
+template <>
+__device__ __forceinline__ void dw_load_ch<__nv_bfloat16, 2>(uint32_t addr, float (&v)[2]) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  v[0] = __uint_as_float(r << 16); v[1] = __uint_as_float(r & 0xFFFF0000u);
+}
+template <>
+__device__ __forceinline__ void dw_load_ch<__nv_bfloat16, 4>(uint32_t addr, float (&v)[4]) {
+  dw_load_vec<__nv_bfloat16>(addr, v);
+}
+template <typename T, int CH>
+__device__ __forceinline__ void dw_store_ch(T* p, const float (&y)[CH]);
+template <>
+__device__ __forceinline__ void dw_store_ch<float, 2>(float* p, const float (&y)[2]) {
+  *reinterpret_cast<float2*>(p) = make_float2(y[0], y[1]);
+}
+template <>
+__device__ __forceinline__ void dw_store_ch<float, 4>(float* p, const float (&y)[4]) { store4<float>(p, y); }
+template <>
+__device__ __forceinline__ void dw_store_ch<__nv_bfloat16, 2>(__nv_bfloat16* p, const float (&y)[2]) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(y[0], y[1]);
+}
+template <>
+__device__ __forceinline__ void dw_store_ch<__nv_bfloat16, 4>(__nv_bfloat16* p, const float (&y)[4]) { store4<__nv_bfloat16>(p, y); }
+
+template <typename T, int K, int S, int TW, int CH>
+__global__ void __launch_bounds__(256, 2)
+dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
+  constexpr int NL = (K + S - 1) / S;
+  constexpr int P = S * NL;
+  constexpr int NCOL = (TW - 1) * S + K;
+  constexpr int ES = (int)sizeof(T);
+  extern __shared__ uint8_t dw_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)dw_smem_raw + 127) & ~(uintptr_t)127);
+  const int CGT = a.cgt, PTC = a.ptc, CB = CGT * CH;
+  const int n_cons = CGT * PTC;
+  const int cons_threads = (int)blockDim.x - 32;                    // whole consumer warps
+  uint8_t* ring = smem;                                              // [stages][row_bytes]
+  float* pool_s = (float*)(ring + (size_t)a.stages * a.row_bytes);   // [2][PTC][CB]
+  uint64_t* full = (uint64_t*)(pool_s + 2 * PTC * CB);
+  uint64_t* empty = full + DW_MAX_STAGES;
+
+  const int tid = threadIdx.x;
+  const int band = blockIdx.y / a.nxc, xchunk = blockIdx.y % a.nxc;
+  const int cb0 = blockIdx.x * CB;
+  const int y0 = band * a.rows_per_band, y1 = min(a.Hout, y0 + a.rows_per_band);
+  const int nsteps = (y1 - 1 - y0) * S + K;
+  const int iy0 = y0 * S - a.pad;
+  const int strip0 = xchunk * PTC;
+  const int x_start = strip0 * TW * S - a.pad;
+
+  if (tid == 0) {
+    for (int s = 0; s < DW_MAX_STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], (uint32_t)n_cons);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmIn);
+  }
+  __syncthreads();
+
+  if (tid >= cons_threads) {
+    // ================================ TMA producer ================================
+    if (tid == cons_threads) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
+        for (int t = 0; t < nsteps; ++t) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_expect_tx(&full[s], (uint32_t)a.box_bytes);
+          ptx::tma_load_4d(ring + (size_t)s * a.row_bytes, &tmIn, &full[s], cb0, x_start, iy0 + t, a.n_off + n);
+          if (++s == a.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    return;
+  }
+  // ================================== consumers ===================================
+  const bool active = tid < n_cons;           // the last consumer warp may be partly idle
+  const int cg = active ? tid % CGT : 0, sl = active ? tid / CGT : 0;
+  const int c = cb0 + cg * CH;
+  float w[K * K][CH], sc[CH], bi[CH];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i)
+#pragma unroll
+    for (int e = 0; e < CH; ++e) w[i][e] = a.w[(int64_t)i * a.C + c + e];
+#pragma unroll
+  for (int e = 0; e < CH; ++e) {
+    sc[e] = a.scale[c + e];
+    bi[e] = a.bias[c + e];
+  }
+  const int ox0 = (strip0 + sl) * TW;
+  const uint32_t ring_u32 = ptx::smem_u32(ring) + (uint32_t)((sl * TW * S * CB + cg * CH) * ES);
+  const uint32_t col_pitch = (uint32_t)(CB * ES);
+  int s = 0;
+  uint32_t ph = 0;
+  int pbuf = 0;
+  for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
+    T* out_n = (T*)a.out + ((int64_t)n * a.Hout * a.Hout + ox0) * a.C + c;
+    float acc[NL][TW][CH];
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+#pragma unroll
+      for (int q = 0; q < TW; ++q)
+#pragma unroll
+        for (int e = 0; e < CH; ++e) acc[l][q][e] = 0.f;
+    float psum[CH];
+#pragma unroll
+    for (int e = 0; e < CH; ++e) psum[e] = 0.f;
+    for (int t0 = 0; t0 < nsteps; t0 += P) {
+#pragma unroll
+      for (int r = 0; r < P; ++r) {
+        const int t = t0 + r;
+        if (t < nsteps) {
+          ptx::mbar_wait(&full[s], ph);
+          const uint32_t rowbase = ring_u32 + (uint32_t)s * (uint32_t)a.row_bytes;
+          float v[NCOL][CH];
+#pragma unroll
+          for (int j = 0; j < NCOL; ++j) dw_load_ch<T, CH>(rowbase + (uint32_t)j * col_pitch, v[j]);
+          const int iy = iy0 + t;
+          if (iy >= 0 && iy < a.Hin) {
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+              if ((r - ky + P * 4) % S == 0) {
+                const int slot = (((r - ky + P * 4) / S) % NL);
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                  for (int q = 0; q < TW; ++q)
+#pragma unroll
+                    for (int e = 0; e < CH; ++e) acc[slot][q][e] = fmaf(v[q * S + kx][e], w[ky * K + kx][e], acc[slot][q][e]);
+              }
+            }
+          }
+          if (active) ptx::mbar_arrive(&empty[s]);
+          if (++s == a.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+          if ((r - (K - 1) + P * 4) % S == 0) {
+            const int done = (((r - (K - 1) + P * 4) / S) % NL);
+            const int td = t - (K - 1);
+            const int oy = y0 + td / S;
+            if (td >= 0 && oy < y1 && active) {
+              T* orow = out_n + (int64_t)oy * a.Hout * a.C;
+#pragma unroll
+              for (int q = 0; q < TW; ++q) {
+                if (ox0 + q < a.Hout) {
+                  float y[CH];
+#pragma unroll
+                  for (int e = 0; e < CH; ++e) {
+                    y[e] = silu_f(fmaf(acc[done][q][e], sc[e], bi[e]));
+                    psum[e] += y[e];
+                  }
+                  dw_store_ch<T, CH>(orow + q * a.C, y);
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < TW; ++q)
+#pragma unroll
+              for (int e = 0; e < CH; ++e) acc[done][q][e] = 0.f;
+          }
+        }
+      }
+    }
+    // per-patch pool partial: fixed-order reduction over the CTA's strips
+    float* ps = pool_s + pbuf * PTC * CB;
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < CH; ++e) ps[sl * CB + cg * CH + e] = psum[e];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(cons_threads) : "memory");
+    for (int i = tid; i < CB; i += cons_threads) {
+      float sum = 0.f;
+      for (int pp = 0; pp < PTC; ++pp) sum += ps[pp * CB + i];
+      a.pool_partial[((int64_t)n * gridDim.y + blockIdx.y) * a.C + cb0 + i] = sum;
+    }
+    pbuf ^= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side: per-block launch plans
 // ---------------------------------------------------------------------------------------
 struct DwLayer {
   int K = 0, S = 0, TW = 0, C = 0, Hin = 0, Hout = 0, pad = 0;
   int cgt = 0, pt = 0, cz = 0, bwin = 0, stages = 0, row_bytes = 0, box_bytes = 0, rows_per_band = 0, nbands = 0, threads = 0;
   size_t smem = 0;
+  bool lane = false;  // register-weight kernel (dw_reg_kernel): cb channels, ptc strips per CTA, nxc column chunks
+  int cb = 0, ptc = 0, nxc = 1, ch = 4;
   const void* in_ptr = nullptr;  // the tensor map below describes this buffer
   CUtensorMap tm;
 };
@@ -262,8 +484,55 @@ inline int dw_pick_cgt(int cg_total, int pt, bool f32) {
   return best;
 }
 
+// Register-weight plan: TW/CH per kernel shape, then the channel slice cb (a multiple of CH, 16-byte
+// multiple for the TMA box) and the strips per CTA.
+inline void dw_reg_shape(int K, int S, int* TW, int* CH) {
+  *CH = 2;
+  *TW = (K == 3 && S == 1) ? 8 : 4;
+}
+
+inline int dw_plan_reg(DwLayer* l, const BlockCfg& b, bool f32) {
+  l->lane = true;
+  dw_reg_shape(b.k, b.stride, &l->TW, &l->ch);
+  l->pt = (b.h_out + l->TW - 1) / l->TW;
+  const int es = f32 ? 4 : 2;
+  double best = -1.0;
+  for (int cb = 8; cb <= 256 && cb <= b.c_mid; cb += 8) {
+    if (b.c_mid % cb) continue;
+    const int cgt = cb / l->ch;
+    int ptc = std::min(l->pt, 224 / cgt);
+    if (ptc < 1) continue;
+    const int nxc = (l->pt + ptc - 1) / ptc;
+    ptc = (l->pt + nxc - 1) / nxc;
+    // prefer full CTAs, one column chunk, and slices that are whole 128-byte lines of a pixel
+    const double score = (double)cgt * ptc * (nxc == 1 ? 1.0 : 0.93) * ((cb * es) % 128 == 0 ? 1.0 : 0.9) *
+                         (cb * es >= 128 ? 1.0 : 0.6);
+    if (score > best) {
+      best = score;
+      l->cb = cb; l->ptc = ptc; l->nxc = nxc;
+    }
+  }
+  if (best < 0) return fail(MC_ERR_UNSUPPORTED, "depthwise: no channel-slice size for the register-weight kernel");
+  l->cgt = l->cb / l->ch;
+  l->cz = b.c_mid / l->cb;
+  l->bwin = (l->ptc * l->TW - 1) * b.stride + b.k;
+  l->box_bytes = l->bwin * l->cb * es;
+  l->row_bytes = (l->box_bytes + 127) / 128 * 128;
+  l->rows_per_band = b.h_out >= 56 ? 14 : b.h_out;
+  l->nbands = (b.h_out + l->rows_per_band - 1) / l->rows_per_band;
+  l->threads = (l->cgt * l->ptc + 31) / 32 * 32 + 32;
+  const size_t fixed = 128 + (size_t)2 * l->ptc * l->cb * sizeof(float) + 2 * DW_MAX_STAGES * sizeof(uint64_t);
+  int stages = (int)((64 * 1024 - fixed) / l->row_bytes);
+  l->stages = stages < 2 ? 2 : (stages > DW_MAX_STAGES ? DW_MAX_STAGES : stages);
+  l->smem = fixed + (size_t)l->stages * l->row_bytes;
+  if (l->bwin > 256 || l->cb > 256) return fail(MC_ERR_UNSUPPORTED, "depthwise tile exceeds the TMA box limits");
+  return MC_OK;
+}
+
 inline int dw_plan_layer(DwLayer* l, const BlockCfg& b, bool f32) {
   l->K = b.k; l->S = b.stride; l->C = b.c_mid; l->Hin = b.h_in; l->Hout = b.h_out; l->pad = b.pad;
+  static const bool vec_env = getenv("MC_DW_VEC") != nullptr;   // experiment switch: 4-channel-vector kernel everywhere
+  if (!vec_env && b.h_in < 112) return dw_plan_reg(l, b, f32);   // the two 112-wide layers keep the 4-channel-vector kernel
   l->TW = dw_pick_tw(b.k, b.stride, b.h_out);
   l->pt = (b.h_out + l->TW - 1) / l->TW;
   l->cgt = dw_pick_cgt(b.c_mid / 4, l->pt, f32);
@@ -304,6 +573,30 @@ inline int dw_tma_launch(DwLayer& l, const CUtensorMap& tm, const DwArgs& a, int
   DW_CASE(5, 1, 2)
   DW_CASE(3, 2, 2)
   DW_CASE(5, 2, 2)
+#undef DW_CASE
+  return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
+}
+
+template <typename T>
+inline int dw_reg_launch(DwLayer& l, const CUtensorMap& tm, const DwRegArgs& a, int nb, cudaStream_t st) {
+  const int per_patch = l.nbands * l.nxc * l.cz;
+  const int gz = std::max(1, std::min(nb, 3000 / per_patch));   // CTAs walk patches grid-stride
+  dim3 grid(l.cz, l.nbands * l.nxc, gz), block(l.threads);
+#define DW_CASE(KK, SS, TT, CC)                                                                                       \
+  if (l.K == KK && l.S == SS && l.TW == TT && l.ch == CC) {                                                           \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      MC_CUDA(cudaFuncSetAttribute(dw_reg_kernel<T, KK, SS, TT, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    dw_reg_kernel<T, KK, SS, TT, CC><<<grid, block, l.smem, st>>>(tm, a);                                             \
+    MC_CHECK_LAUNCH();                                                                                                \
+    return MC_OK;                                                                                                     \
+  }
+  DW_CASE(3, 1, 8, 2)
+  DW_CASE(5, 1, 4, 2)
+  DW_CASE(3, 2, 4, 2)
+  DW_CASE(5, 2, 4, 2)
 #undef DW_CASE
   return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
 }
