@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "layers.h"
+#include "pw_simt.cuh"
 
 #ifndef MC_BF16_TANH
 #define MC_BF16_TANH 0
@@ -127,6 +128,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bits, repeated 4 times (32 fp32 columns): the mma-style fragment layout.  For
+// repetition i (columns 8i .. 8i+7) thread t holds  v[4i+0..1] = (lane t/4,     columns 8i + 2(t%4) + {0,1})
+//                                                   v[4i+2..3] = (lane t/4 + 8, same columns).
+// No wait inside: issue several, then tmem_ld_wait() once.
+__device__ __forceinline__ void tmem_ld16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -166,6 +181,7 @@ struct PwTcArgs {
   void* out;          // [M][N]
   int64_t M;
   int N, K, HW, BN, n_blocks, k_chunks, act, stages;
+  int exp_flags;      // MC_TC_EXP timing experiments: 1 = no activation, 2 = no global stores, 4 = no operand transform
   int a_row_off;      // first row of this launch inside the activation tensor map (chunked execution)
   int64_t m_tiles;
 };
@@ -197,7 +213,7 @@ struct TcCfg<float> {
 
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_BUDGET = 227 * 1024;
-constexpr int TC_EPI_BYTES = 4 * TC_EPI_GROUPS * 32 * 128;                      // one 32-row x 128-byte staging tile per epilogue warp
+constexpr int TC_EPI_BYTES = 0;                                                  // the epilogue stores straight from registers
 constexpr int TC_FIXED_BYTES = 1024 /*align slack*/ + TC_EPI_BYTES + 2 * 1280 * 4 + 512;
 
 // bytes of one pipeline stage for a layer with BN output columns per block (1024-aligned)
@@ -364,7 +380,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {  // eight 16-byte chunks per 128-byte row
-            if (j < nch) {
+            if (j < nch && !(p.exp_flags & 4)) {
               const uint32_t phys = a_hi + (((uint32_t)j ^ xr) << 4);
               uint4 raw = ptx::lds128(phys);
               if (Cfg::TF32) {
@@ -382,7 +398,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   hp[e] = hbits;
                   lp[e] = __float_as_uint(v[e] - __uint_as_float(hbits));      // exact remainder
                 }
-                ptx::sts128(phys, hi);
+                // ungated tiles keep the raw fp32 value as the hi operand: kind::tf32 reads only the upper 19 bits
+                if (gated || !(p.exp_flags & 8)) ptx::sts128(phys, hi);
                 ptx::sts128(phys + Cfg::A_BYTES, lo);
               } else if (gated) {
                 __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
@@ -423,116 +440,65 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
       const int ncols = min(p.BN, p.N - n0);
       const int64_t m_warp = (it / p.n_blocks) * TC_BM + quarter * 32;   // first row of this warp
-      const int rows_valid = (p.M - m_warp) < 32 ? (int)(p.M - m_warp) : 32;        // <= 0 when the warp is past M
-      constexpr int EC = Cfg::EPI_COLS;                                   // columns per pass (128 B per row)
-      constexpr int EPC = 16 / (int)sizeof(T);                            // elements per 16-byte chunk
-      const uint32_t stg = ptx::smem_u32(epi_base) + (uint32_t)(warp - 6) * 4096u;  // 32 rows x 128 B, chunk-swizzled
-      const uint32_t my_row = stg + (uint32_t)lane * 128u;
-      const uint32_t my_x = (uint32_t)(lane & 7);
-      // coalesced copy pattern: lane -> (row sub-index lane/8, 16-byte chunk lane%8)
-      const int cr = lane >> 3, cc = lane & 7;
-      const int64_t g_off0 = (m_warp + cr) * (int64_t)p.N + n0 + cc * EPC;
-      const uint32_t c_stg = stg + (uint32_t)cr * 128u;
-      for (int c0 = 0; c0 < ncols; c0 += EC) {
-        const int vchunks = min(EC, ncols - c0) / EPC;  // valid 16-byte chunks per row in this pass
-        // (1) residual tile -> staging, coalesced (8 lanes x 16 B = one 128-byte row segment)
-        if (p.res != nullptr) {
-          const T* rp = (const T*)p.res + g_off0 + c0;
+      // Accumulator -> registers in the mma fragment layout (tcgen05.ld 16x256b), one exchange with the
+      // neighbouring lane so every thread owns FOUR consecutive columns of a row, then BN-fold, swish,
+      // residual and a 16-byte (fp32) / 8-byte (bf16) store straight from registers: a quad writes 64
+      // (32) contiguous bytes of a row, whole 32-byte sectors, and nothing is staged through shared
+      // memory (the smem pipe is the scarce resource of this kernel: TMA fills, UMMA operand reads and
+      // the transform warps already share its 128 B/clk).
+      const int lr = lane >> 2, q = lane & 3;
+      const bool odd = (q & 1) != 0;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[2][16];
+        ptx::tmem_ld16x256b_x4(taddr + (uint32_t)c0, v[0]);                      // lanes  0..15 of this warp's quarter
+        ptx::tmem_ld16x256b_x4(taddr + (16u << 16) + (uint32_t)c0, v[1]);        // lanes 16..31
+        ptx::tmem_ld_wait();
 #pragma unroll
-          for (int itr = 0; itr < 8; ++itr) {
-            const int rr = itr * 4 + cr;
-            if (rr < rows_valid && cc < vchunks) {
-              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rp + (int64_t)itr * 4 * p.N));
-              ptx::sts128(c_stg + (uint32_t)itr * 512u + (((uint32_t)cc ^ (uint32_t)(rr & 7)) << 4), r4);
-            }
-          }
-          __syncwarp();
-        }
-        // (2) accumulator row -> scale/bias/activation (+ residual) -> staging row
+        for (int h2 = 0; h2 < 2; ++h2) {
 #pragma unroll
-        for (int h = 0; h < EC / 32; ++h) {
-          uint32_t v[32];
-          ptx::tmem_ld32(taddr + (uint32_t)(c0 + h * 32), v);
-          const float4* sc4 = reinterpret_cast<const float4*>(sc_s + n0 + c0 + h * 32);
-          const float4* bi4 = reinterpret_cast<const float4*>(bi_s + n0 + c0 + h * 32);
+          for (int pr = 0; pr < 2; ++pr) {        // column-block pair (8-column blocks 2pr, 2pr+1)
+            // this thread ends up with columns cb .. cb+3 of the 32-column group
+            const int cb = odd ? 16 * pr + 8 + 2 * (q - 1) : 16 * pr + 2 * q;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {   // 4 columns at a time
-            const float4 s4 = sc4[q], b4 = bi4[q];
-            float y0 = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
-            float y1 = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
-            float y2 = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
-            float y3 = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
-            if (p.act == 1) {
-              if (Cfg::TF32 || !MC_BF16_TANH) {
-                y0 = __fdividef(y0, 1.f + __expf(-y0));
-                y1 = __fdividef(y1, 1.f + __expf(-y1));
-                y2 = __fdividef(y2, 1.f + __expf(-y2));
-                y3 = __fdividef(y3, 1.f + __expf(-y3));
-              } else {
-                y0 = fmaf(y0, ptx::tanh_approx(y0), y0);
-                y1 = fmaf(y1, ptx::tanh_approx(y1), y1);
-                y2 = fmaf(y2, ptx::tanh_approx(y2), y2);
-                y3 = fmaf(y3, ptx::tanh_approx(y3), y3);
-              }
-            }
-            v[4 * q + 0] = __float_as_uint(y0);
-            v[4 * q + 1] = __float_as_uint(y1);
-            v[4 * q + 2] = __float_as_uint(y2);
-            v[4 * q + 3] = __float_as_uint(y3);
-          }
-          if (Cfg::TF32) {
+            for (int rh = 0; rh < 2; ++rh) {       // rows lr and lr + 8 of the 16-lane half
+              const uint32_t a0 = v[h2][8 * pr + 2 * rh], a1 = v[h2][8 * pr + 2 * rh + 1];          // block 2pr
+              const uint32_t b0 = v[h2][8 * pr + 4 + 2 * rh], b1 = v[h2][8 * pr + 4 + 2 * rh + 1];  // block 2pr+1
+              const uint32_t s0 = odd ? a0 : b0, s1 = odd ? a1 : b1;
+              const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+              float y[4];
+              y[0] = __uint_as_float(odd ? r0 : a0);
+              y[1] = __uint_as_float(odd ? r1 : a1);
+              y[2] = __uint_as_float(odd ? b0 : r0);
+              y[3] = __uint_as_float(odd ? b1 : r1);
+              const int64_t row = m_warp + 16 * h2 + 8 * rh + lr;
+              if (row < p.M && c0 + cb < ncols) {
+                const float4 s4 = *reinterpret_cast<const float4*>(sc_s + n0 + c0 + cb);
+                const float4 b4 = *reinterpret_cast<const float4*>(bi_s + n0 + c0 + cb);
+                y[0] = fmaf(y[0], s4.x, b4.x);
+                y[1] = fmaf(y[1], s4.y, b4.y);
+                y[2] = fmaf(y[2], s4.z, b4.z);
+                y[3] = fmaf(y[3], s4.w, b4.w);
+                if (p.act == 1 && !(p.exp_flags & 1)) {
+                  if (Cfg::TF32 || !MC_BF16_TANH) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {   // 8 chunks of 4 floats
-              const uint32_t sp = my_row + (((uint32_t)q ^ my_x) << 4);
-              uint4 w4 = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-              if (p.res != nullptr) {
-                const uint4 r4 = ptx::lds128(sp);
-                w4.x = __float_as_uint(__uint_as_float(w4.x) + __uint_as_float(r4.x));
-                w4.y = __float_as_uint(__uint_as_float(w4.y) + __uint_as_float(r4.y));
-                w4.z = __float_as_uint(__uint_as_float(w4.z) + __uint_as_float(r4.z));
-                w4.w = __float_as_uint(__uint_as_float(w4.w) + __uint_as_float(r4.w));
-              }
-              ptx::sts128(sp, w4);
-            }
-          } else {
+                    for (int e = 0; e < 4; ++e) y[e] = __fdividef(y[e], 1.f + __expf(-y[e]));
+                  } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {   // 4 chunks of 8 bf16 per 32 columns
-              const uint32_t sp = my_row + (((uint32_t)(h * 4 + q) ^ my_x) << 4);
-              float y[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[8 * q + e]);
-              if (p.res != nullptr) {
-                const uint4 r4 = ptx::lds128(sp);
-                const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&r4);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(rh[e]);
-                  y[2 * e] += f.x;
-                  y[2 * e + 1] += f.y;
+                    for (int e = 0; e < 4; ++e) y[e] = fmaf(y[e], ptx::tanh_approx(y[e]), y[e]);
+                  }
                 }
+                const int64_t off = row * (int64_t)p.N + n0 + c0 + cb;
+                if (p.res != nullptr) {
+                  float r[4];
+                  load4<T>((const T*)p.res + off, r);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) y[e] += r[e];
+                }
+                if (!(p.exp_flags & 2)) store4<T>((T*)p.out + off, y);
               }
-              uint4 w4;
-              __nv_bfloat162* wh = reinterpret_cast<__nv_bfloat162*>(&w4);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) wh[e] = __floats2bfloat162_rn(y[2 * e], y[2 * e + 1]);
-              ptx::sts128(sp, w4);
             }
           }
         }
-        __syncwarp();
-        // (3) staging -> global, coalesced
-        {
-          T* op = (T*)p.out + g_off0 + c0;
-#pragma unroll
-          for (int itr = 0; itr < 8; ++itr) {
-            const int rr = itr * 4 + cr;
-            if (rr < rows_valid && cc < vchunks) {
-              const uint4 w4 = ptx::lds128(c_stg + (uint32_t)itr * 512u + (((uint32_t)cc ^ (uint32_t)(rr & 7)) << 4));
-              *reinterpret_cast<uint4*>(op + (int64_t)itr * 4 * p.N) = w4;
-            }
-          }
-        }
-        __syncwarp();
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[as]);
@@ -725,6 +691,8 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   a.out = outp;
   a.M = M;
   a.a_row_off = (int)a_row_off;
+  static const int exp_flags = getenv("MC_TC_EXP") ? atoi(getenv("MC_TC_EXP")) : 0;
+  a.exp_flags = exp_flags;
   a.N = l.N;
   a.K = l.K;
   a.HW = HW;
