@@ -28,6 +28,9 @@
 #include "layers.h"
 #include "pw_simt.cuh"
 
+#ifndef MC_TC_TIMING
+#define MC_TC_TIMING 0   // 1: per-role wait/total cycle counters (MC_TC_DBG=<layer>); costs registers, off in production
+#endif
 #ifndef MC_BF16_TANH
 #define MC_BF16_TANH 0
 #endif
@@ -70,6 +73,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 8000000000ll) __trap();
   }
+}
+
+// wait + cycles spent waiting (role-level pipeline diagnosis, MC_TC_DBG)
+__device__ __forceinline__ long long mbar_wait_timed(uint64_t* bar, uint32_t parity) {
+#if MC_TC_TIMING
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  return clock64() - t0;
+#else
+  mbar_wait(bar, parity);
+  return 0;
+#endif
+}
+__device__ __forceinline__ long long tc_clock() {
+#if MC_TC_TIMING
+  return clock64();
+#else
+  return 0;
+#endif
 }
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -169,7 +191,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // kernel
 // ---------------------------------------------------------------------------------------
 constexpr int TC_EPI_GROUPS = 4;                       // epilogue warp groups (4 warps each)
-constexpr int TC_THREADS = (6 + 4 * TC_EPI_GROUPS) * 32;
+// warps per CTA: TMA + MMA + transform + epilogue groups of four.  Ungated layers (expand, head conv): 4 transform
+// warps + 4 epilogue groups = 22 warps (80 registers); gated layers (project): 8 transform warps + 2 epilogue groups =
+// 18 warps, which leaves 112 registers per thread for the gate double-buffer.
+template <bool GATED>
+__host__ __device__ constexpr int tc_threads() { return GATED ? (2 + 8 + 4 * 2) * 32 : (2 + 4 + 4 * 4) * 32; }
 constexpr int TC_BM = 128;
 constexpr int TC_ACC_COLS = 256;  // TMEM columns per accumulator stage (2 stages = 512)
 
@@ -181,6 +207,7 @@ struct PwTcArgs {
   void* out;          // [M][N]
   int64_t M;
   int N, K, HW, BN, n_blocks, k_chunks, act, stages;
+  long long* dbg;     // MC_TC_DBG: per-role wait/total cycle counters of CTA 0 (null = off)
   int exp_flags;      // MC_TC_EXP timing experiments: 1 = no activation, 2 = no global stores, 4 = no operand transform
   int a_row_off;      // first row of this launch inside the activation tensor map (chunked execution)
   int64_t m_tiles;
@@ -227,8 +254,8 @@ inline int tc_num_stages(int BN) {
   return s > TC_MAX_STAGES ? TC_MAX_STAGES : s;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <typename T, bool GATED>
+__global__ void __launch_bounds__(tc_threads<GATED>(), 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmWlo, const PwTcArgs p) {
   using Cfg = TcCfg<T>;
@@ -251,9 +278,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // accumulator stages in TMEM: 4 x 128 columns when the block fits, else 2 x 256
-  const int NAS = p.BN <= 128 ? 4 : 2;
+  // warp roles: 0 TMA, 1 MMA, [2, 2+ntw) transform, the rest epilogue groups of four warps
+  constexpr bool gated_layer = GATED;
+  constexpr int TC_THREADS = tc_threads<GATED>();
+  constexpr int ntw = GATED ? 8 : 4;
+  constexpr int n_groups = (TC_THREADS / 32 - 2 - ntw) / 4;   // 4 ungated, 2 gated
+  const int NAS = p.BN <= 128 ? n_groups : 2;
   const int acc_cols = p.BN <= 128 ? 128 : 256;
-  const bool transform = Cfg::TF32 || p.gate != nullptr;
+  constexpr bool transform = Cfg::TF32 || GATED;
   const int64_t items = p.m_tiles * p.n_blocks;
 
   // bf16 swish uses x*sigmoid(x) = h + h*tanh(h) with h = x/2: fold the 1/2 into scale and bias
@@ -265,7 +297,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_MAX_STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&ready[s], 128);
+      ptx::mbar_init(&ready[s], (uint32_t)(ntw * 32));
       ptx::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 4; ++s) {
@@ -289,11 +321,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tx = Cfg::A_BYTES + (uint32_t)p.BN * 128u * (Cfg::TF32 ? 2u : 1u);
+      long long w_empty = 0;
+      const long long t_begin = ptx::tc_clock();
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
         const int m0 = (int)(it / p.n_blocks) * TC_BM + p.a_row_off;
         const int n0 = (int)(it % p.n_blocks) * p.BN;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+          w_empty += ptx::mbar_wait_timed(&empty[s], ph ^ 1);
           uint8_t* st = stage_base + (size_t)s * STAGE_BYTES;
           ptx::mbar_expect_tx(&full[s], tx);
           ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, m0);
@@ -309,6 +343,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      if (MC_TC_TIMING && p.dbg && blockIdx.x == 0) {
+        p.dbg[0] = w_empty;
+        p.dbg[1] = ptx::tc_clock() - t_begin;
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
@@ -318,14 +356,16 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       int64_t li = 0;
+      long long w_tempty = 0, w_full = 0;
+      const long long t_begin = ptx::tc_clock();
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++li) {
         const int as = (int)(li % NAS);
         const uint32_t use = (uint32_t)(li / NAS);
-        ptx::mbar_wait(&tempty[as], (use & 1) ^ 1);
+        w_tempty += ptx::mbar_wait_timed(&tempty[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_cols);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          ptx::mbar_wait(transform ? &ready[s] : &full[s], ph);
+          w_full += ptx::mbar_wait_timed(transform ? &ready[s] : &full[s], ph);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES);
           const int krem = p.K - kc * Cfg::KC;
@@ -354,66 +394,139 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         ptx::mma_commit(&tfull[as]);
       }
+      if (MC_TC_TIMING && p.dbg && blockIdx.x == 0) {
+        p.dbg[2] = w_tempty;
+        p.dbg[3] = w_full;
+        p.dbg[4] = ptx::tc_clock() - t_begin;
+        p.dbg[5] = li;
+      }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + ntw) {
     // ============================ operand transform ================================
-    if (transform) {
-      const int r = threadIdx.x - 64;  // tile row owned by this thread
+    // Gated (project) layers: 8 warps, two threads per tile row, four 16-byte chunks each, and the gate
+    // chunks of the NEXT k-chunk are fetched (L2, one round trip) while the current one is processed.
+    // Ungated fp32 layers: 4 warps, one thread per row, only the TF32 lo operand is produced.
+    if constexpr (GATED) {
+      const int r2 = threadIdx.x - 64;
+      const int r = r2 & 127;              // tile row
+      const int j0 = (r2 >> 7) * 4;        // first of this thread's four 16-byte chunks
+      const uint32_t row_off = (uint32_t)r * 128u;
+      const uint32_t xr = (uint32_t)(r & 7);
+      constexpr int EPCH = 16 / (int)sizeof(T);    // elements per 16-byte chunk
+      int s = 0;
+      uint32_t ph = 0;
+      // (tile, k-chunk) walked incrementally; `gp` / `gp_n` = gate row of this / the next step's tile row
+      const int n_items = (int)items;
+      int it = blockIdx.x, kc = 0;
+      auto gate_row = [&](int item) -> const T* {
+        const int m = (item / p.n_blocks) * TC_BM + r;
+        return (item < n_items && m < (int)p.M) ? (const T*)p.gate + (int64_t)(m / p.HW) * p.K : nullptr;
+      };
+      const T* gp = gate_row(it);
+      uint4 gn0 = make_uint4(0u, 0u, 0u, 0u), gn1 = gn0, gn2 = gn0, gn3 = gn0;   // gate chunks of the next step
+#define MC_GATE_FETCH(ROW, KCHUNK)                                                                        \
+  do {                                                                                                    \
+    const int k0_ = (KCHUNK) * Cfg::KC;                                                                   \
+    const int nch_ = min(8, (p.K - k0_) / EPCH);                                                          \
+    const uint4* src_ = reinterpret_cast<const uint4*>((ROW) + k0_ + j0 * EPCH);                          \
+    if ((ROW) != nullptr) {                                                                               \
+      if (j0 + 0 < nch_) gn0 = __ldg(src_ + 0);                                                           \
+      if (j0 + 1 < nch_) gn1 = __ldg(src_ + 1);                                                           \
+      if (j0 + 2 < nch_) gn2 = __ldg(src_ + 2);                                                           \
+      if (j0 + 3 < nch_) gn3 = __ldg(src_ + 3);                                                           \
+    }                                                                                                     \
+  } while (0)
+      MC_GATE_FETCH(gp, 0);
+      while (it < n_items) {
+        const bool gated = gp != nullptr;
+        const int k0 = kc * Cfg::KC;
+        const int nch = min(8, (p.K - k0) / EPCH);  // chunks that hold real data (the rest is TMA zero fill)
+        const uint4 gq[4] = {gn0, gn1, gn2, gn3};
+        // advance to the next step and start fetching its gate chunks before waiting for this step's data
+        int it_n = it, kc_n = kc + 1;
+        const T* gp_n = gp;
+        if (kc_n == p.k_chunks) {
+          kc_n = 0;
+          it_n = it + (int)gridDim.x;
+          gp_n = gate_row(it_n);
+        }
+        MC_GATE_FETCH(gp_n, kc_n);
+        ptx::mbar_wait(&full[s], ph);
+        const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = j0 + jj;
+          if (j < nch && !(p.exp_flags & 4)) {
+            const uint32_t phys = a_hi + (((uint32_t)j ^ xr) << 4);
+            uint4 raw = ptx::lds128(phys);
+            const uint4 gj = gq[jj];
+            if (Cfg::TF32) {
+              float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+              if (gated) {
+                v[0] *= __uint_as_float(gj.x); v[1] *= __uint_as_float(gj.y);
+                v[2] *= __uint_as_float(gj.z); v[3] *= __uint_as_float(gj.w);
+              }
+              uint4 hi, lo;
+              uint32_t* hp = &hi.x;
+              uint32_t* lp = &lo.x;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t hbits = __float_as_uint(v[e]) & 0xFFFFE000u;  // exact TF32 value
+                hp[e] = hbits;
+                lp[e] = __float_as_uint(v[e] - __uint_as_float(hbits));      // exact remainder
+              }
+              if (gated) ptx::sts128(phys, hi);
+              ptx::sts128(phys + Cfg::A_BYTES, lo);
+            } else if (gated) {
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+              const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gj);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], gh[e]);
+              ptx::sts128(phys, raw);
+            }
+          } else if (Cfg::TF32 && j >= nch) {
+            // zero-filled K tail: the lo copy must be zero too
+            ptx::sts128(a_hi + Cfg::A_BYTES + (((uint32_t)j ^ xr) << 4), make_uint4(0u, 0u, 0u, 0u));
+          }
+        }
+        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+        ptx::mbar_arrive(&ready[s]);
+        if (++s == S) {
+          s = 0;
+          ph ^= 1;
+        }
+        it = it_n;
+        kc = kc_n;
+        gp = gp_n;
+      }
+#undef MC_GATE_FETCH
+    } else if constexpr (Cfg::TF32) {
+      // ungated fp32: one thread per tile row; the raw fp32 tile stays in place as the hi operand
+      // (kind::tf32 reads only the upper 19 bits), only the lo operand a - tf32(a) is written.
+      const int r = threadIdx.x - 64;
       const uint32_t row_off = (uint32_t)r * 128u;
       const uint32_t xr = (uint32_t)(r & 7);
       int s = 0;
       uint32_t ph = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-        const int64_t m = (it / p.n_blocks) * TC_BM + r;
-        const bool gated = p.gate != nullptr && m < p.M;
-        const T* grow = gated ? (const T*)p.gate + (m / p.HW) * p.K : nullptr;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          const int k0 = kc * Cfg::KC;
-          constexpr int EPCH = 16 / (int)sizeof(T);   // elements per 16-byte chunk
-          const int nch = min(8, (p.K - k0) / EPCH);  // chunks that hold real data (the rest is TMA zero fill)
-          // the gate row (L2-resident, one round trip) is fetched BEFORE waiting for the TMA data
-          uint4 g[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (gated && j < nch) g[j] = __ldg(reinterpret_cast<const uint4*>(grow + k0 + j * EPCH));
+          const int nch = min(8, (p.K - kc * Cfg::KC) / 4);
           ptx::mbar_wait(&full[s], ph);
           const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {  // eight 16-byte chunks per 128-byte row
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t phys = a_hi + (((uint32_t)j ^ xr) << 4);
+            uint4 lo = make_uint4(0u, 0u, 0u, 0u);   // zero-filled K tail: the lo copy must be zero too
             if (j < nch && !(p.exp_flags & 4)) {
-              const uint32_t phys = a_hi + (((uint32_t)j ^ xr) << 4);
-              uint4 raw = ptx::lds128(phys);
-              if (Cfg::TF32) {
-                float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-                if (gated) {
-                  v[0] *= __uint_as_float(g[j].x); v[1] *= __uint_as_float(g[j].y);
-                  v[2] *= __uint_as_float(g[j].z); v[3] *= __uint_as_float(g[j].w);
-                }
-                uint4 hi, lo;
-                uint32_t* hp = &hi.x;
-                uint32_t* lp = &lo.x;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const uint32_t hbits = __float_as_uint(v[e]) & 0xFFFFE000u;  // exact TF32 value
-                  hp[e] = hbits;
-                  lp[e] = __float_as_uint(v[e] - __uint_as_float(hbits));      // exact remainder
-                }
-                // ungated tiles keep the raw fp32 value as the hi operand: kind::tf32 reads only the upper 19 bits
-                if (gated || !(p.exp_flags & 8)) ptx::sts128(phys, hi);
-                ptx::sts128(phys + Cfg::A_BYTES, lo);
-              } else if (gated) {
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-                const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g[j]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], gh[e]);
-                ptx::sts128(phys, raw);
-              }
-            } else if (Cfg::TF32) {
-              // zero-filled K tail: the lo copy must be zero too
-              ptx::sts128(a_hi + Cfg::A_BYTES + (((uint32_t)j ^ xr) << 4), make_uint4(0u, 0u, 0u, 0u));
+              const uint4 raw = ptx::lds128(phys);
+              lo.x = __float_as_uint(__uint_as_float(raw.x) - __uint_as_float(raw.x & 0xFFFFE000u));
+              lo.y = __float_as_uint(__uint_as_float(raw.y) - __uint_as_float(raw.y & 0xFFFFE000u));
+              lo.z = __float_as_uint(__uint_as_float(raw.z) - __uint_as_float(raw.z & 0xFFFFE000u));
+              lo.w = __float_as_uint(__uint_as_float(raw.w) - __uint_as_float(raw.w & 0xFFFFE000u));
             }
+            ptx::sts128(phys + Cfg::A_BYTES, lo);
           }
-          ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+          ptx::fence_proxy_async();
           ptx::mbar_arrive(&ready[s]);
           if (++s == S) {
             s = 0;
@@ -424,9 +537,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ================================== epilogue ====================================
-    const int eg = (warp - 6) >> 2;   // epilogue group: handles work items li with li % TC_EPI_GROUPS == eg
+    const int eg = (warp - 2 - ntw) >> 2;   // epilogue group: handles work items li with li % n_groups == eg
     const int quarter = warp & 3;     // TMEM lanes 32*quarter .. +31 are visible to this warp
     int64_t li = 0;
+    long long w_tfull = 0, t_work = 0;
+    const long long t_begin = ptx::tc_clock();
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x, ++li) {
       // A group follows EVERY phase of the accumulator stage it serves (a parity wait is only
       // meaningful for the current or the immediately preceding phase) but drains only its own items.
@@ -434,8 +549,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (as != eg % NAS) continue;
       const uint32_t use = (uint32_t)(li / NAS);
       const int n0 = (int)(it % p.n_blocks) * p.BN;
-      ptx::mbar_wait(&tfull[as], use & 1);
-      if ((int)(li % TC_EPI_GROUPS) != eg) continue;
+      w_tfull += ptx::mbar_wait_timed(&tfull[as], use & 1);
+      if ((int)(li % n_groups) != eg) continue;
+      const long long t_item = ptx::tc_clock();
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
       const int ncols = min(p.BN, p.N - n0);
@@ -448,7 +564,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // the transform warps already share its 128 B/clk).
       const int lr = lane >> 2, q = lane & 3;
       const bool odd = (q & 1) != 0;
+      const int rows_valid = (p.M - m_warp) < 32 ? (int)(p.M - m_warp) : 32;   // <= 0 when the warp is past M
+      // 64-bit tile bases once, 32-bit offsets inside the tile
+      T* out_t = (T*)p.out + m_warp * (int64_t)p.N + n0;
+      const T* res_t = p.res != nullptr ? (const T*)p.res + m_warp * (int64_t)p.N + n0 : nullptr;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
+        // both 16-lane halves in flight before the single wait: the tcgen05.ld round trip is the longest
+        // latency of the epilogue (serialising the halves cost 40 % on the expand layers)
         uint32_t v[2][16];
         ptx::tmem_ld16x256b_x4(taddr + (uint32_t)c0, v[0]);                      // lanes  0..15 of this warp's quarter
         ptx::tmem_ld16x256b_x4(taddr + (16u << 16) + (uint32_t)c0, v[1]);        // lanes 16..31
@@ -470,8 +592,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               y[1] = __uint_as_float(odd ? r1 : a1);
               y[2] = __uint_as_float(odd ? b0 : r0);
               y[3] = __uint_as_float(odd ? b1 : r1);
-              const int64_t row = m_warp + 16 * h2 + 8 * rh + lr;
-              if (row < p.M && c0 + cb < ncols) {
+              const int row = 16 * h2 + 8 * rh + lr;      // row inside this warp's 32
+              if (row < rows_valid && c0 + cb < ncols) {
                 const float4 s4 = *reinterpret_cast<const float4*>(sc_s + n0 + c0 + cb);
                 const float4 b4 = *reinterpret_cast<const float4*>(bi_s + n0 + c0 + cb);
                 y[0] = fmaf(y[0], s4.x, b4.x);
@@ -487,14 +609,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     for (int e = 0; e < 4; ++e) y[e] = fmaf(y[e], ptx::tanh_approx(y[e]), y[e]);
                   }
                 }
-                const int64_t off = row * (int64_t)p.N + n0 + c0 + cb;
-                if (p.res != nullptr) {
+                const int off = row * p.N + c0 + cb;
+                if (res_t != nullptr) {
                   float r[4];
-                  load4<T>((const T*)p.res + off, r);
+                  load4<T>(res_t + off, r);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) y[e] += r[e];
                 }
-                if (!(p.exp_flags & 2)) store4<T>((T*)p.out + off, y);
+                if (!(p.exp_flags & 2)) store4<T>(out_t + off, y);
               }
             }
           }
@@ -502,6 +624,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[as]);
+      t_work += ptx::tc_clock() - t_item;
+    }
+    if (MC_TC_TIMING && p.dbg && blockIdx.x == 0 && lane == 0 && (warp & 3) == 2) {
+      p.dbg[8 + 3 * eg] = w_tfull;
+      p.dbg[9 + 3 * eg] = t_work;
+      p.dbg[10 + 3 * eg] = ptx::tc_clock() - t_begin;
     }
   }
   ptx::tc_fence_before();
@@ -641,9 +769,11 @@ inline int pw_tc_build(PwTcPlan** out, const NetCfg& net, const float* params_ho
   plan->layers.resize(33);
   const bool f32 = mode == MC_MODE_FP32;
   if (f32) {
-    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
   } else {
-    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
   }
   auto enabled = [&](int id) { return id < 32 ? ((layer_mask_lo >> id) & 1u) != 0 : ((layer_mask_hi >> (id - 32)) & 1u) != 0; };
   int rc = MC_OK;
@@ -693,6 +823,15 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   a.a_row_off = (int)a_row_off;
   static const int exp_flags = getenv("MC_TC_EXP") ? atoi(getenv("MC_TC_EXP")) : 0;
   a.exp_flags = exp_flags;
+  // MC_TC_DBG=<layer id>: after that layer's launch, print CTA 0's per-role wait/total cycles (synchronises)
+  static const int dbg_layer = getenv("MC_TC_DBG") ? atoi(getenv("MC_TC_DBG")) : -1;
+  static long long* dbg_buf = nullptr;
+  a.dbg = nullptr;
+  if (dbg_layer == id) {
+    if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 32 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 32 * sizeof(long long), st);
+    a.dbg = dbg_buf;
+  }
   a.N = l.N;
   a.K = l.K;
   a.HW = HW;
@@ -705,11 +844,31 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   a.m_tiles = (M + TC_BM - 1) / TC_BM;
   const int64_t items = a.m_tiles * a.n_blocks;
   const int grid = (int)std::min<int64_t>(items, plan->num_sms);
-  if (f32)
-    pw_tc_kernel<float><<<grid, TC_THREADS, smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+  const bool gated = a.gate != nullptr;
+  if (f32 && gated)
+    pw_tc_kernel<float, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+  else if (f32)
+    pw_tc_kernel<float, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+  else if (gated)
+    pw_tc_kernel<__nv_bfloat16, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
   else
-    pw_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+    pw_tc_kernel<__nv_bfloat16, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
   MC_CHECK_LAUNCH();
+  if (a.dbg) {
+    long long d[32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(d, dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
+    static int printed = 0;
+    if (printed++ < 3) {
+      const double it = (double)std::max<long long>(d[5], 1);
+      fprintf(stderr, "[MC_TC_DBG layer %d] M=%lld N=%d K=%d BN=%d stages=%d items/CTA=%lld | per item (cycles): producer wait_empty %.0f total %.0f | "
+                      "mma wait_tempty %.0f wait_full %.0f total %.0f | transform wait_full %.0f total %.0f |",
+              id, (long long)M, l.N, l.K, l.BN, a.stages, d[5], d[0] / it, d[1] / it, d[2] / it, d[3] / it, d[4] / it, d[6] / it, d[7] / it);
+      for (int g = 0; g < (gated ? 2 : 4); ++g)
+        fprintf(stderr, " epi%d wait_tfull %.0f work %.0f total %.0f |", g, d[8 + 3 * g] / it, d[9 + 3 * g] / it, d[10 + 3 * g] / it);
+      fprintf(stderr, "\n");
+    }
+  }
   return MC_OK;
 }
 
