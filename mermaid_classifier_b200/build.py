@@ -30,13 +30,18 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_defs() -> list[str]:
+    """Extra -D flags for diagnosis builds, e.g. MC_NVCC_DEFS="-DMC_TC_TIMING=1"."""
+    return os.environ.get("MC_NVCC_DEFS", "").split()
+
+
 def _sources_digest() -> str:
     h = hashlib.sha256()
     files = sorted(list(CSRC.glob("*")) + list(INCLUDE.glob("*.h")))
     for f in files:
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_defs()).encode())
     return h.hexdigest()
 
 
@@ -55,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     digest = _sources_digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", str(INCLUDE), "-o", str(LIB), str(CSRC / "api.cu"), "-lcuda"]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *_extra_defs(), "-I", str(INCLUDE), "-o", str(LIB), str(CSRC / "api.cu"), "-lcuda"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)
