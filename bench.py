@@ -121,6 +121,22 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+NCU_CAPTURE_OF_LAYER = {0: "stem", 6: "dw_b1", 18: "dw_b4", 5: "exp_b1", 12: "proj_b2", 65: "head_conv"}
+
+
+def ncu_traffic(layer_id: int, mode: str, patches_per_launch: float):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of the
+    same kernel (profiles/r01_summary_<mode>.json, 500 patches per launch), scaled to this run's launch
+    size.  None when that layer has no committed capture."""
+    f = ROOT / "profiles" / f"r01_summary_{mode}.json"
+    name = NCU_CAPTURE_OF_LAYER.get(layer_id)
+    if name is None or not f.exists():
+        return None
+    d = json.loads(f.read_text())
+    mb = d.get("traffic_MB_per_launch", {}).get(name)
+    return None if mb is None else mb * 1e6 * patches_per_launch / d["patches_per_launch"]
+
+
 def measured_peaks() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -325,7 +341,8 @@ def run_b200(args, rank: int, world: int, local: int):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(dominant, args.mode, patches_per_launch),
+                     "algorithmic_bytes_per_launch": dom_bytes * patches_per_launch, "peak_source": peak_src,
                      "algorithmic_bytes_per_patch": dom_bytes, "avg_launch_ms": dom_ms,
                      "patches_per_launch": patches_per_launch, "share_of_step": share,
                      "top_kernels_ms_per_step": [[n, round(m, 3)] for m, n in table[:8]]},

@@ -1,0 +1,48 @@
+"""Condense gpurun_out/ ncu captures into the tracked summaries under profiles/ (round tag as argv[1])."""
+import csv, io, json, subprocess, sys, collections
+from pathlib import Path
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+mode = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+out = Path("profiles"); out.mkdir(exist_ok=True)
+g = Path("gpurun_out")
+
+# 1. launch list -> per-launch rows of the first full sub-batch + per-family shares
+rows = [r for r in csv.reader(open(g / f"launches_{mode}.csv")) if len(r) > 10 and r[0].isdigit()]
+launches = [(int(r[0]), r[4].split("(")[0].replace("void ", ""), r[7], r[8], float(r[14]) / 1e3) for r in rows]
+def family(name):
+    for k in ("synth_image", "stem", "dw_tma", "dw_reg", "se_kernel", "pw_tc_kernel<float, (bool)0>", "pw_tc_kernel<float, (bool)1>",
+              "pw_tc_kernel<__nv_bfloat16, (bool)0>", "pw_tc_kernel<__nv_bfloat16, (bool)1>", "pw_tc", "avgpool", "pw_simt", "head_rows"):
+        if k in name: return k
+    return "other(torch)"
+# one sub-batch = from the first stem launch to the launch before the second stem (or head_rows)
+stems = [i for i, l in enumerate(launches) if "stem" in l[1]]
+lo = stems[0]; hi = stems[1] if len(stems) > 1 else len(launches)
+sub = launches[lo:hi]
+with open(out / f"{tag}_launches_{mode}.csv", "w") as f:
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none : one 500-patch sub-batch of `python bench.py --images 5 --batch 500 --steps 1 --mode %s` (cold-cache, serialised: compare shares)\n" % mode)
+    f.write("launch,kernel,block,grid,us\n")
+    for i, n, b, gr, us in sub: f.write(f"{i},{n},\"{b}\",\"{gr}\",{us:.1f}\n")
+fam = collections.OrderedDict()
+for _, n, _, _, us in sub: fam[family(n)] = fam.get(family(n), 0.0) + us
+tot = sum(fam.values())
+shares = {k: round(v / tot, 4) for k, v in fam.items()}
+
+# 2. per-kernel full-set summaries
+summ = []
+for name in ("stem", "dw_b1", "dw_b4", "exp_b1", "proj_b2", "head_conv", "head_rows"):
+    rep = g / f"prof_{name}_{mode}.ncu-rep"
+    if not rep.exists(): continue
+    t = subprocess.run([sys.executable, "tools/ncu_table.py", str(rep)], capture_output=True, text=True).stdout.strip().splitlines()
+    hdr, row = t[0].split(","), t[-1].split(",")
+    d = dict(zip(hdr, row)); d["capture"] = name
+    summ.append(d)
+if summ:
+    cols = ["capture"] + [c for c in summ[0] if c not in ("capture", "idx")]
+    with open(out / f"{tag}_kernels_{mode}.csv", "w") as f:
+        f.write("# ncu --set full --clock-control none, one launch each (500 patches); dram_*_MB = dram__bytes_{read,write}.sum per launch\n")
+        f.write(",".join(cols) + "\n")
+        for d in summ: f.write(",".join(d.get(c, "") for c in cols) + "\n")
+json.dump({"mode": mode, "patches_per_launch": 500, "family_time_shares_ncu": shares, "sub_batch_us_ncu": round(tot, 1),
+           "traffic_MB_per_launch": {d["capture"]: round(float(d["dram_rd_MB"]) + float(d["dram_wr_MB"]), 1) for d in summ}},
+          open(out / f"{tag}_summary_{mode}.json", "w"), indent=1)
+print(json.dumps(shares, indent=1)); print(tot)
