@@ -108,6 +108,7 @@ struct mc_extractor {
   int64_t cap_feats = 0;
   std::vector<mc_point> h_points;
   PwTcPlan* tc = nullptr;  // tcgen05 GEMM plans (pw_tc.cuh)
+  StemParams stem;          // stem weights + folded BN, passed by value (kernel parameter / constant bank)
   std::vector<DwLayer> dw;  // TMA-staged depthwise plans (dw_tma.cuh), one per block
   int64_t launches = 0;
   int64_t l2_budget = 0;  // bytes of per-chunk working set kept L2-resident (0 = no chunking)
@@ -281,8 +282,7 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
   int rc;
   {
     ProfScope ps(h, 0, st);
-    stem_kernel<T><<<dim3(49, nb), 256, 0, st>>>(h->d_images, h->d_points, P + net.w_stem, P + net.s_stem,
-                                                 P + net.b_stem, h->d_lut, X);
+    stem_kernel<T><<<dim3(49, nb), 256, 0, st>>>(h->d_images, h->d_points, h->stem, h->d_lut, X);
   }
   MC_CHECK_LAUNCH();
   h->launches++;
@@ -514,6 +514,9 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
     mc_extractor_destroy(h);
     return rc;
   }
+  memcpy(h->stem.w, params + h->net.w_stem, sizeof(h->stem.w));
+  memcpy(h->stem.scale, params + h->net.s_stem, sizeof(h->stem.scale));
+  memcpy(h->stem.bias, params + h->net.b_stem, sizeof(h->stem.bias));
   h->dw.resize(h->net.blocks.size());
   for (size_t bi = 0; bi < h->net.blocks.size(); ++bi) {
     const BlockCfg& b = h->net.blocks[bi];

@@ -69,22 +69,34 @@ __global__ void normalize_kernel(const uint8_t* __restrict__ patches, const floa
 
 // ---- fused K1+K2: gather + normalise + stem conv3x3/s2 + BN + swish --------------------
 // One CTA = one 16x16 tile of the 112x112 stem output of one patch (grid 49 x n).
-// The 33x33x3 input window is gathered straight from the source image (reflect),
-// normalised through the LUT into shared memory, and each thread produces the 32 output
-// channels of one output pixel; the tile is then written out NHWC, fully coalesced.
+// The 33x33x3 input window is gathered straight from the source image (reflect), normalised
+// through the LUT into shared memory, and each thread produces the 32 output channels of one
+// output pixel; the tile is then written out NHWC, fully coalesced.
+// The 27x32 weights and the folded BN live in the kernel's PARAMETER space (constant bank): every
+// FFMA takes its weight as a constant operand, so the math loop issues no weight loads at all
+// (the shared-memory version spent 216 LDS.128 per thread on them and was smem-bandwidth bound).
+struct StemParams {
+  float w[27 * 32];   // [ky][kx][ci][co]
+  float scale[32];
+  float bias[32];
+};
+
+// np.pad(mode='reflect') index with a fast path for the usual single reflection
+__device__ __forceinline__ int reflect_fast(int t, int n) {
+  if (t < 0) t = -t;
+  if (t >= n) t = 2 * (n - 1) - t;
+  return (t >= 0 && t < n) ? t : reflect_idx(t, n);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) stem_kernel(const mc_image* __restrict__ images,
                                                    const mc_point* __restrict__ points,
-                                                   const float* __restrict__ w,      // [27][32]
-                                                   const float* __restrict__ scale,  // [32]
-                                                   const float* __restrict__ bias,   // [32]
+                                                   const __grid_constant__ StemParams P,
                                                    const float* __restrict__ lut,    // [3][256]
                                                    T* __restrict__ out) {            // [n][112][112][32]
   constexpr int TS = 16, IN = 2 * TS + 1;  // 33
   __shared__ float in_s[IN][IN * 3 + 1];
-  __shared__ __align__(16) float w_s[27 * 32];
   __shared__ float lut_s[768];
-  __shared__ float sc_s[32], bi_s[32];
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
   const int oy0 = (tile / 7) * TS, ox0 = (tile % 7) * TS;
@@ -92,29 +104,37 @@ __global__ void __launch_bounds__(256) stem_kernel(const mc_image* __restrict__ 
   const mc_point pt = points[k];
   const mc_image im = images[pt.image];
 
-  for (int t = tid; t < 27 * 32; t += 256) w_s[t] = w[t];
-  for (int t = tid; t < 768; t += 256) lut_s[t] = lut[t];
-  if (tid < 32) {
-    sc_s[tid] = scale[tid];
-    bi_s[tid] = bias[tid];
-  }
-  __syncthreads();
-  // gather: IN rows x IN pixels x 3 bytes
-  for (int t = tid; t < IN * IN; t += 256) {
-    const int r = t / IN, cpx = t % IN;
+  // gather: IN rows x IN pixels x 3 bytes.  All of a thread's byte loads are issued before the LUT pass.
+  constexpr int NIT = (IN * IN + 255) / 256;   // 5
+  uint8_t px[NIT][3];
+  bool ok[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int t = tid + it * 256;
+    const int r = t / IN, cpx = t - r * IN;
     const int pi = 2 * oy0 + r, pj = 2 * ox0 + cpx;  // patch coordinates; 224 == the SAME zero pad
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (pi < 224 && pj < 224) {
-      const int y = reflect_idx(pt.row - 112 + pi, im.height);
-      const int x = reflect_idx(pt.col - 112 + pj, im.width);
+    ok[it] = t < IN * IN && pi < 224 && pj < 224;
+    px[it][0] = px[it][1] = px[it][2] = 0;
+    if (ok[it]) {
+      const int y = reflect_fast(pt.row - 112 + pi, im.height);
+      const int x = reflect_fast(pt.col - 112 + pj, im.width);
       const uint8_t* s = im.data + (int64_t)y * im.row_pitch + (int64_t)x * 3;
-      v0 = lut_s[s[0]];
-      v1 = lut_s[256 + s[1]];
-      v2 = lut_s[512 + s[2]];
+      px[it][0] = s[0];
+      px[it][1] = s[1];
+      px[it][2] = s[2];
     }
-    in_s[r][cpx * 3 + 0] = v0;
-    in_s[r][cpx * 3 + 1] = v1;
-    in_s[r][cpx * 3 + 2] = v2;
+  }
+  for (int t = tid; t < 768; t += 256) lut_s[t] = lut[t];
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int t = tid + it * 256;
+    if (t < IN * IN) {
+      const int r = t / IN, cpx = t - r * IN;
+      in_s[r][cpx * 3 + 0] = ok[it] ? lut_s[px[it][0]] : 0.f;
+      in_s[r][cpx * 3 + 1] = ok[it] ? lut_s[256 + px[it][1]] : 0.f;
+      in_s[r][cpx * 3 + 2] = ok[it] ? lut_s[512 + px[it][2]] : 0.f;
+    }
   }
   __syncthreads();
 
@@ -129,15 +149,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const mc_image* __restrict__ 
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float v = in_s[2 * ty + ky][(2 * tx + kx) * 3 + ci];
-        const float4* wr = reinterpret_cast<const float4*>(&w_s[((ky * 3 + kx) * 3 + ci) * 32]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 wv = wr[q];
-          acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
-        }
+        for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, P.w[((ky * 3 + kx) * 3 + ci) * 32 + c], acc[c]);
       }
     }
   }
@@ -149,7 +162,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const mc_image* __restrict__ 
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       const int c = q * VN + e;
-      v.v[e] = silu_f(fmaf(acc[c], sc_s[c], bi_s[c]));
+      v.v[e] = silu_f(fmaf(acc[c], P.scale[c], P.bias[c]));
     }
     v.store(o + q * VN);
   }
