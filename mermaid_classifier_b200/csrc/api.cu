@@ -189,17 +189,6 @@ int launch_dw(mc_extractor* h, const BlockCfg& b, int n_off, T* out, int nb, cud
     a.bias = P + b.b_dw;
     a.out = out;
     a.pool_partial = h->d_pool;
-    a.C = C;
-    a.Hin = b.h_in;
-    a.Hout = b.h_out;
-    a.pad = b.pad;
-    a.rows_per_band = l.rows_per_band;
-    a.cgt = l.cgt;
-    a.ptc = l.ptc;
-    a.nxc = l.nxc;
-    a.stages = l.stages;
-    a.row_bytes = l.row_bytes;
-    a.box_bytes = l.box_bytes;
     a.n_off = n_off;
     a.nb = nb;
     if (int rc = dw_reg_launch<T>(l, l.tm, a, nb, st)) return rc;

@@ -221,6 +221,73 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Compile-time layer shapes of the register-weight kernel: the ten distinct depthwise layers of
+// EfficientNet-B0 past the two 112-wide ones.  Everything the kernel indexes with (channel count, map
+// size, slice width, ring geometry) is a constant, so shared-memory and global offsets fold into
+// immediates instead of per-row integer arithmetic (the run-time-shaped version spent ~145 address
+// instructions per input row against 200 FMAs).
+struct DwShape {
+  int K, S, C, Hin;                 // kernel, stride, channels, input map size
+  int Hout, pad, TW, CH;            // output map size, leading SAME pad, columns / channels per thread
+  int cb, ptc, nxc, cgt, cz;        // channels per CTA, strips per CTA, column chunks, channel groups per CTA, slices
+  int bwin, box_bytes, row_bytes;   // staged input columns, bytes per TMA box, ring pitch
+  int rows_per_band, nbands, threads, stages, smem;
+};
+
+constexpr int DW_N_SHAPES = 10;
+constexpr int DW_SHAPE_KSCH[DW_N_SHAPES][4] = {{3, 1, 144, 56},  {5, 2, 144, 56},  {5, 1, 240, 28}, {3, 2, 240, 28},
+                                               {3, 1, 480, 14},  {5, 1, 480, 14},  {5, 1, 672, 14}, {5, 2, 672, 14},
+                                               {5, 1, 1152, 7},  {3, 1, 1152, 7}};
+
+constexpr int dw_shape_index(int K, int S, int C, int Hin) {
+  for (int i = 0; i < DW_N_SHAPES; ++i)
+    if (DW_SHAPE_KSCH[i][0] == K && DW_SHAPE_KSCH[i][1] == S && DW_SHAPE_KSCH[i][2] == C && DW_SHAPE_KSCH[i][3] == Hin) return i;
+  return -1;
+}
+
+// Slice / strip selection (same rule at compile time for the kernel and at run time for the host plan).
+__host__ __device__ constexpr DwShape dw_make_shape(int K, int S, int C, int Hin, int es) {
+  DwShape d{};
+  d.K = K; d.S = S; d.C = C; d.Hin = Hin;
+  d.Hout = (Hin + S - 1) / S;
+  int total = (d.Hout - 1) * S + K - Hin;
+  if (total < 0) total = 0;
+  d.pad = total / 2;
+  d.CH = 2;
+  d.TW = (K == 3 && S == 1) ? 8 : 4;
+  const int pt = (d.Hout + d.TW - 1) / d.TW;
+  double best = -1.0;
+  for (int cb = 8; cb <= 256 && cb <= C; cb += 8) {
+    if (C % cb) continue;
+    const int cgt = cb / d.CH;
+    int ptc = pt < 224 / cgt ? pt : 224 / cgt;
+    if (ptc < 1) continue;
+    const int nxc = (pt + ptc - 1) / ptc;
+    ptc = (pt + nxc - 1) / nxc;
+    // prefer full CTAs, one column chunk, and slices that are whole 128-byte lines of a pixel
+    const double score = (double)cgt * ptc * (nxc == 1 ? 1.0 : 0.93) * ((cb * es) % 128 == 0 ? 1.0 : 0.9) *
+                         (cb * es >= 128 ? 1.0 : 0.6);
+    if (score > best) {
+      best = score;
+      d.cb = cb; d.ptc = ptc; d.nxc = nxc;
+    }
+  }
+  d.cgt = d.cb / d.CH;
+  d.cz = C / d.cb;
+  d.bwin = (d.ptc * d.TW - 1) * S + K;
+  d.box_bytes = d.bwin * d.cb * es;
+  d.row_bytes = (d.box_bytes + 127) / 128 * 128;
+  d.rows_per_band = d.Hout >= 56 ? 14 : d.Hout;
+  d.nbands = (d.Hout + d.rows_per_band - 1) / d.rows_per_band;
+  d.threads = (d.cgt * d.ptc + 31) / 32 * 32 + 32;
+  const int fixed = 128 + 2 * d.ptc * d.cb * 4 + 2 * 8 * 8;
+  int stages = (64 * 1024 - fixed) / d.row_bytes;
+  d.stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
+  d.smem = fixed + d.stages * d.row_bytes;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------
 // Register-weight variant for every layer past the two 112-wide ones.
 //
 // The kernel above re-reads its k*k weight vectors from shared memory for every input row (one
@@ -238,9 +305,6 @@ struct DwRegArgs {
   const float* bias;
   void* out;
   float* pool_partial;  // [n][gridDim.y][C]
-  int C, Hin, Hout, pad, rows_per_band;
-  int cgt, ptc, nxc;    // channel groups (of CH) per CTA, column strips per CTA, column chunks per row band
-  int stages, row_bytes, box_bytes;
   int n_off, nb;        // first patch inside the tensor map; patches in this launch
 };
 
@@ -280,31 +344,35 @@ __device__ __forceinline__ void dw_store_ch<__nv_bfloat16, 2>(__nv_bfloat16* p, 
 template <>
 __device__ __forceinline__ void dw_store_ch<__nv_bfloat16, 4>(__nv_bfloat16* p, const float (&y)[4]) { store4<__nv_bfloat16>(p, y); }
 
-template <typename T, int K, int S, int TW, int CH>
+template <typename T, int SHAPE>
 __global__ void __launch_bounds__(256, 2)
 dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
+  constexpr DwShape SH = dw_make_shape(DW_SHAPE_KSCH[SHAPE][0], DW_SHAPE_KSCH[SHAPE][1], DW_SHAPE_KSCH[SHAPE][2],
+                                       DW_SHAPE_KSCH[SHAPE][3], (int)sizeof(T));
+  constexpr int K = SH.K, S = SH.S, TW = SH.TW, CH = SH.CH;
   constexpr int NL = (K + S - 1) / S;
   constexpr int P = S * NL;
   constexpr int NCOL = (TW - 1) * S + K;
   constexpr int ES = (int)sizeof(T);
   extern __shared__ uint8_t dw_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)dw_smem_raw + 127) & ~(uintptr_t)127);
-  const int CGT = a.cgt, PTC = a.ptc, CB = CGT * CH;
-  const int n_cons = CGT * PTC;
+  constexpr int CGT = SH.cgt, PTC = SH.ptc, CB = SH.cb, NXC = SH.nxc, C = SH.C, HIN = SH.Hin, HOUT = SH.Hout, PAD = SH.pad;
+  constexpr int RPB = SH.rows_per_band, STAGES = SH.stages, ROW_BYTES = SH.row_bytes, BOX_BYTES = SH.box_bytes;
+  constexpr int n_cons = CGT * PTC;
   const int cons_threads = (int)blockDim.x - 32;                    // whole consumer warps
   uint8_t* ring = smem;                                              // [stages][row_bytes]
-  float* pool_s = (float*)(ring + (size_t)a.stages * a.row_bytes);   // [2][PTC][CB]
+  float* pool_s = (float*)(ring + (size_t)STAGES * ROW_BYTES);   // [2][PTC][CB]
   uint64_t* full = (uint64_t*)(pool_s + 2 * PTC * CB);
   uint64_t* empty = full + DW_MAX_STAGES;
 
   const int tid = threadIdx.x;
-  const int band = blockIdx.y / a.nxc, xchunk = blockIdx.y % a.nxc;
+  const int band = blockIdx.y / NXC, xchunk = blockIdx.y % NXC;
   const int cb0 = blockIdx.x * CB;
-  const int y0 = band * a.rows_per_band, y1 = min(a.Hout, y0 + a.rows_per_band);
+  const int y0 = band * RPB, y1 = min(HOUT, y0 + RPB);
   const int nsteps = (y1 - 1 - y0) * S + K;
-  const int iy0 = y0 * S - a.pad;
+  const int iy0 = y0 * S - PAD;
   const int strip0 = xchunk * PTC;
-  const int x_start = strip0 * TW * S - a.pad;
+  const int x_start = strip0 * TW * S - PAD;
 
   if (tid == 0) {
     for (int s = 0; s < DW_MAX_STAGES; ++s) {
@@ -324,9 +392,9 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
       for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
         for (int t = 0; t < nsteps; ++t) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
-          ptx::mbar_expect_tx(&full[s], (uint32_t)a.box_bytes);
-          ptx::tma_load_4d(ring + (size_t)s * a.row_bytes, &tmIn, &full[s], cb0, x_start, iy0 + t, a.n_off + n);
-          if (++s == a.stages) {
+          ptx::mbar_expect_tx(&full[s], (uint32_t)BOX_BYTES);
+          ptx::tma_load_4d(ring + (size_t)s * ROW_BYTES, &tmIn, &full[s], cb0, x_start, iy0 + t, a.n_off + n);
+          if (++s == STAGES) {
             s = 0;
             ph ^= 1;
           }
@@ -343,7 +411,7 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
 #pragma unroll
   for (int i = 0; i < K * K; ++i)
 #pragma unroll
-    for (int e = 0; e < CH; ++e) w[i][e] = a.w[(int64_t)i * a.C + c + e];
+    for (int e = 0; e < CH; ++e) w[i][e] = a.w[(int64_t)i * C + c + e];
 #pragma unroll
   for (int e = 0; e < CH; ++e) {
     sc[e] = a.scale[c + e];
@@ -356,7 +424,7 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
   uint32_t ph = 0;
   int pbuf = 0;
   for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
-    T* out_n = (T*)a.out + ((int64_t)n * a.Hout * a.Hout + ox0) * a.C + c;
+    T* out_n = (T*)a.out + ((int64_t)n * HOUT * HOUT + ox0) * C + c;
     float acc[NL][TW][CH];
 #pragma unroll
     for (int l = 0; l < NL; ++l)
@@ -367,18 +435,18 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
     float psum[CH];
 #pragma unroll
     for (int e = 0; e < CH; ++e) psum[e] = 0.f;
-    for (int t0 = 0; t0 < nsteps; t0 += P) {
+    auto row_block = [&](const int t0) {
 #pragma unroll
       for (int r = 0; r < P; ++r) {
         const int t = t0 + r;
         if (t < nsteps) {
           ptx::mbar_wait(&full[s], ph);
-          const uint32_t rowbase = ring_u32 + (uint32_t)s * (uint32_t)a.row_bytes;
+          const uint32_t rowbase = ring_u32 + (uint32_t)s * (uint32_t)ROW_BYTES;
           float v[NCOL][CH];
 #pragma unroll
           for (int j = 0; j < NCOL; ++j) dw_load_ch<T, CH>(rowbase + (uint32_t)j * col_pitch, v[j]);
           const int iy = iy0 + t;
-          if (iy >= 0 && iy < a.Hin) {
+          if (iy >= 0 && iy < HIN) {
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
               if ((r - ky + P * 4) % S == 0) {
@@ -393,7 +461,7 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
             }
           }
           if (active) ptx::mbar_arrive(&empty[s]);
-          if (++s == a.stages) {
+          if (++s == STAGES) {
             s = 0;
             ph ^= 1;
           }
@@ -402,17 +470,17 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
             const int td = t - (K - 1);
             const int oy = y0 + td / S;
             if (td >= 0 && oy < y1 && active) {
-              T* orow = out_n + (int64_t)oy * a.Hout * a.C;
+              T* orow = out_n + (int64_t)oy * HOUT * C;
 #pragma unroll
               for (int q = 0; q < TW; ++q) {
-                if (ox0 + q < a.Hout) {
+                if (ox0 + q < HOUT) {
                   float y[CH];
 #pragma unroll
                   for (int e = 0; e < CH; ++e) {
                     y[e] = silu_f(fmaf(acc[done][q][e], sc[e], bi[e]));
                     psum[e] += y[e];
                   }
-                  dw_store_ch<T, CH>(orow + q * a.C, y);
+                  dw_store_ch<T, CH>(orow + q * C, y);
                 }
               }
             }
@@ -423,6 +491,16 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
           }
         }
       }
+    };
+    // Short bands (the 14x14 and 7x7 maps, <= 22 input rows) are unrolled completely; longer ones keep the row loop
+    // rolled at its P-step period -- fully unrolled, the 28x28 layer is ~150 KB of code and thrashes the instruction cache.
+    constexpr int NSTEPS_MAX = (RPB - 1) * S + K;
+    if constexpr (SH.nbands == 1 && NSTEPS_MAX <= 22) {
+#pragma unroll
+      for (int t0 = 0; t0 < NSTEPS_MAX; t0 += P) row_block(t0);
+    } else {
+#pragma unroll 1
+      for (int t0 = 0; t0 < nsteps; t0 += P) row_block(t0);
     }
     // per-patch pool partial: fixed-order reduction over the CTA's strips
     float* ps = pool_s + pbuf * PTC * CB;
@@ -434,7 +512,7 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
     for (int i = tid; i < CB; i += cons_threads) {
       float sum = 0.f;
       for (int pp = 0; pp < PTC; ++pp) sum += ps[pp * CB + i];
-      a.pool_partial[((int64_t)n * gridDim.y + blockIdx.y) * a.C + cb0 + i] = sum;
+      a.pool_partial[((int64_t)n * gridDim.y + blockIdx.y) * C + cb0 + i] = sum;
     }
     pbuf ^= 1;
   }
@@ -448,7 +526,7 @@ struct DwLayer {
   int cgt = 0, pt = 0, cz = 0, bwin = 0, stages = 0, row_bytes = 0, box_bytes = 0, rows_per_band = 0, nbands = 0, threads = 0;
   size_t smem = 0;
   bool lane = false;  // register-weight kernel (dw_reg_kernel): cb channels, ptc strips per CTA, nxc column chunks
-  int cb = 0, ptc = 0, nxc = 1, ch = 4;
+  int cb = 0, ptc = 0, nxc = 1, ch = 4, shape = -1;
   const void* in_ptr = nullptr;  // the tensor map below describes this buffer
   CUtensorMap tm;
 };
@@ -484,47 +562,19 @@ inline int dw_pick_cgt(int cg_total, int pt, bool f32) {
   return best;
 }
 
-// Register-weight plan: TW/CH per kernel shape, then the channel slice cb (a multiple of CH, 16-byte
-// multiple for the TMA box) and the strips per CTA.
-inline void dw_reg_shape(int K, int S, int* TW, int* CH) {
-  *CH = 2;
-  *TW = (K == 3 && S == 1) ? 8 : 4;
-}
-
+// Register-weight plan: copy the compile-time shape (dw_make_shape) of this layer into the run-time plan.
 inline int dw_plan_reg(DwLayer* l, const BlockCfg& b, bool f32) {
+  const int idx = dw_shape_index(b.k, b.stride, b.c_mid, b.h_in);
+  if (idx < 0) return fail(MC_ERR_UNSUPPORTED, "depthwise layer shape is not in the compiled EfficientNet-B0 table");
+  const DwShape d = dw_make_shape(b.k, b.stride, b.c_mid, b.h_in, f32 ? 4 : 2);
+  if (d.Hout != b.h_out || d.pad != b.pad) return fail(MC_ERR_UNSUPPORTED, "depthwise shape table disagrees with the layer table");
   l->lane = true;
-  dw_reg_shape(b.k, b.stride, &l->TW, &l->ch);
-  l->pt = (b.h_out + l->TW - 1) / l->TW;
-  const int es = f32 ? 4 : 2;
-  double best = -1.0;
-  for (int cb = 8; cb <= 256 && cb <= b.c_mid; cb += 8) {
-    if (b.c_mid % cb) continue;
-    const int cgt = cb / l->ch;
-    int ptc = std::min(l->pt, 224 / cgt);
-    if (ptc < 1) continue;
-    const int nxc = (l->pt + ptc - 1) / ptc;
-    ptc = (l->pt + nxc - 1) / nxc;
-    // prefer full CTAs, one column chunk, and slices that are whole 128-byte lines of a pixel
-    const double score = (double)cgt * ptc * (nxc == 1 ? 1.0 : 0.93) * ((cb * es) % 128 == 0 ? 1.0 : 0.9) *
-                         (cb * es >= 128 ? 1.0 : 0.6);
-    if (score > best) {
-      best = score;
-      l->cb = cb; l->ptc = ptc; l->nxc = nxc;
-    }
-  }
-  if (best < 0) return fail(MC_ERR_UNSUPPORTED, "depthwise: no channel-slice size for the register-weight kernel");
-  l->cgt = l->cb / l->ch;
-  l->cz = b.c_mid / l->cb;
-  l->bwin = (l->ptc * l->TW - 1) * b.stride + b.k;
-  l->box_bytes = l->bwin * l->cb * es;
-  l->row_bytes = (l->box_bytes + 127) / 128 * 128;
-  l->rows_per_band = b.h_out >= 56 ? 14 : b.h_out;
-  l->nbands = (b.h_out + l->rows_per_band - 1) / l->rows_per_band;
-  l->threads = (l->cgt * l->ptc + 31) / 32 * 32 + 32;
-  const size_t fixed = 128 + (size_t)2 * l->ptc * l->cb * sizeof(float) + 2 * DW_MAX_STAGES * sizeof(uint64_t);
-  int stages = (int)((64 * 1024 - fixed) / l->row_bytes);
-  l->stages = stages < 2 ? 2 : (stages > DW_MAX_STAGES ? DW_MAX_STAGES : stages);
-  l->smem = fixed + (size_t)l->stages * l->row_bytes;
+  l->shape = idx;
+  l->TW = d.TW; l->ch = d.CH; l->cb = d.cb; l->ptc = d.ptc; l->nxc = d.nxc; l->cgt = d.cgt; l->cz = d.cz;
+  l->pt = (d.Hout + d.TW - 1) / d.TW;
+  l->bwin = d.bwin; l->box_bytes = d.box_bytes; l->row_bytes = d.row_bytes;
+  l->rows_per_band = d.rows_per_band; l->nbands = d.nbands; l->threads = d.threads; l->stages = d.stages;
+  l->smem = (size_t)d.smem;
   if (l->bwin > 256 || l->cb > 256) return fail(MC_ERR_UNSUPPORTED, "depthwise tile exceeds the TMA box limits");
   return MC_OK;
 }
@@ -577,28 +627,36 @@ inline int dw_tma_launch(DwLayer& l, const CUtensorMap& tm, const DwArgs& a, int
   return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
 }
 
+template <typename T, int SHAPE>
+inline int dw_reg_launch_shape(DwLayer& l, const CUtensorMap& tm, const DwRegArgs& a, dim3 grid, dim3 block, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(cudaFuncSetAttribute(dw_reg_kernel<T, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    attr_set = true;
+  }
+  dw_reg_kernel<T, SHAPE><<<grid, block, l.smem, st>>>(tm, a);
+  MC_CHECK_LAUNCH();
+  return MC_OK;
+}
+
 template <typename T>
 inline int dw_reg_launch(DwLayer& l, const CUtensorMap& tm, const DwRegArgs& a, int nb, cudaStream_t st) {
   const int per_patch = l.nbands * l.nxc * l.cz;
   const int gz = std::max(1, std::min(nb, 3000 / per_patch));   // CTAs walk patches grid-stride
   dim3 grid(l.cz, l.nbands * l.nxc, gz), block(l.threads);
-#define DW_CASE(KK, SS, TT, CC)                                                                                       \
-  if (l.K == KK && l.S == SS && l.TW == TT && l.ch == CC) {                                                           \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
-      MC_CUDA(cudaFuncSetAttribute(dw_reg_kernel<T, KK, SS, TT, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
-      attr_set = true;                                                                                                \
-    }                                                                                                                 \
-    dw_reg_kernel<T, KK, SS, TT, CC><<<grid, block, l.smem, st>>>(tm, a);                                             \
-    MC_CHECK_LAUNCH();                                                                                                \
-    return MC_OK;                                                                                                     \
+  switch (l.shape) {
+    case 0: return dw_reg_launch_shape<T, 0>(l, tm, a, grid, block, st);
+    case 1: return dw_reg_launch_shape<T, 1>(l, tm, a, grid, block, st);
+    case 2: return dw_reg_launch_shape<T, 2>(l, tm, a, grid, block, st);
+    case 3: return dw_reg_launch_shape<T, 3>(l, tm, a, grid, block, st);
+    case 4: return dw_reg_launch_shape<T, 4>(l, tm, a, grid, block, st);
+    case 5: return dw_reg_launch_shape<T, 5>(l, tm, a, grid, block, st);
+    case 6: return dw_reg_launch_shape<T, 6>(l, tm, a, grid, block, st);
+    case 7: return dw_reg_launch_shape<T, 7>(l, tm, a, grid, block, st);
+    case 8: return dw_reg_launch_shape<T, 8>(l, tm, a, grid, block, st);
+    case 9: return dw_reg_launch_shape<T, 9>(l, tm, a, grid, block, st);
   }
-  DW_CASE(3, 1, 8, 2)
-  DW_CASE(5, 1, 4, 2)
-  DW_CASE(3, 2, 4, 2)
-  DW_CASE(5, 2, 4, 2)
-#undef DW_CASE
-  return fail(MC_ERR_UNSUPPORTED, "depthwise kernel/stride combination");
+  return fail(MC_ERR_UNSUPPORTED, "depthwise layer shape");
 }
 
 }  // namespace mc
