@@ -421,7 +421,7 @@ def main():
     ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--images", type=int, default=1000)
     ap.add_argument("--points", type=int, default=100)
-    ap.add_argument("--batch", type=int, default=500, help="patches per sub-batch")
+    ap.add_argument("--batch", type=int, default=1000, help="patches per sub-batch")
     ap.add_argument("--group", type=int, default=5, help="images per extract call on the e2e path")
     ap.add_argument("--host-pool", type=int, default=64, help="distinct pinned host images cycled by the e2e path")
     ap.add_argument("--cpu-images", type=int, default=3, help="images timed by the cpu_baseline leg")

@@ -74,6 +74,29 @@ struct Vec<__nv_bfloat16> {
   }
 };
 
+// Four channels as loaded from memory (kept packed while in flight).
+template <typename T>
+struct RawVec4;
+template <>
+struct RawVec4<float> {
+  typedef float4 type;
+  __device__ __forceinline__ static float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ static float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ static void unpack(const float4& r, float (&v)[4]) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+};
+template <>
+struct RawVec4<__nv_bfloat16> {
+  typedef uint2 type;
+  __device__ __forceinline__ static uint2 load(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ static uint2 zero() { return make_uint2(0u, 0u); }
+  __device__ __forceinline__ static void unpack(const uint2& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x << 16);
+    v[1] = __uint_as_float(r.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(r.y << 16);
+    v[3] = __uint_as_float(r.y & 0xFFFF0000u);
+  }
+};
+
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
 template <typename T>

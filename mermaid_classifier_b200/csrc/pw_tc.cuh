@@ -573,8 +573,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool odd = (q & 1) != 0;
       const int rows_valid = (p.M - m_warp) < 32 ? (int)(p.M - m_warp) : 32;   // <= 0 when the warp is past M
       // 64-bit tile bases once, 32-bit offsets inside the tile
-      T* out_t = (T*)p.out + m_warp * (int64_t)p.N + n0;
-      const T* res_t = p.res != nullptr ? (const T*)p.res + m_warp * (int64_t)p.N + n0 : nullptr;
+      // restrict: the residual (block input) never aliases the output, so its loads may be hoisted above earlier stores
+      T* __restrict__ out_t = (T*)p.out + m_warp * (int64_t)p.N + n0;
+      const T* __restrict__ res_t = p.res != nullptr ? (const T*)p.res + m_warp * (int64_t)p.N + n0 : nullptr;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         // both 16-lane halves in flight before the single wait: the tcgen05.ld round trip is the longest
         // latency of the epilogue (serialising the halves cost 40 % on the expand layers)
