@@ -31,6 +31,23 @@ inline int fail(int code, const std::string& msg) {
 // ---- math -----------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// swish of bn = acc * scale + bias in the activation mode of T.
+//   fp32 mode: exact form, 2 MUFU ops (ex2, rcp).
+//   bf16 mode: x * sigmoid(x) = h + h * tanh(h) with h = x / 2 and ONE MUFU op (tanh.approx, rel. error 2^-11,
+//   below the bf16 rounding of the stored result); the 1/2 is folded into the BN FMA.
+template <typename T>
+__device__ __forceinline__ float bn_silu(float acc, float scale, float bias);
+template <>
+__device__ __forceinline__ float bn_silu<float>(float acc, float scale, float bias) {
+  return silu_f(fmaf(acc, scale, bias));
+}
+template <>
+__device__ __forceinline__ float bn_silu<__nv_bfloat16>(float acc, float scale, float bias) {
+  const float h = fmaf(acc, 0.5f * scale, 0.5f * bias);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // ---- 16-byte activation vectors ---------------------------------------------------
 template <typename T>

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const mc_image* __restrict__ 
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       const int c = q * VN + e;
-      v.v[e] = silu_f(fmaf(acc[c], P.scale[c], P.bias[c]));
+      v.v[e] = bn_silu<T>(acc[c], P.scale[c], P.bias[c]);
     }
     v.store(o + q * VN);
   }

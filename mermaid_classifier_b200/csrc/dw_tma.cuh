@@ -192,7 +192,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
                   float y[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    y[e] = silu_f(fmaf(acc[done][q][e], sc[e], bi[e]));
+                    y[e] = bn_silu<T>(acc[done][q][e], sc[e], bi[e]);
                     psum[e] += y[e];
                   }
                   store4<T>(out_n + ((int64_t)oy * a.Hout + ox) * a.C, y);
@@ -477,7 +477,7 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
                   float y[CH];
 #pragma unroll
                   for (int e = 0; e < CH; ++e) {
-                    y[e] = silu_f(fmaf(acc[done][q][e], sc[e], bi[e]));
+                    y[e] = bn_silu<T>(acc[done][q][e], sc[e], bi[e]);
                     psum[e] += y[e];
                   }
                   dw_store_ch<T, CH>(orow + q * C, y);

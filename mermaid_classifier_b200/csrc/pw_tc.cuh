@@ -32,7 +32,7 @@
 #define MC_TC_TIMING 0   // 1: per-role wait/total cycle counters (MC_TC_DBG=<layer>); costs registers, off in production
 #endif
 #ifndef MC_BF16_TANH
-#define MC_BF16_TANH 0
+#define MC_BF16_TANH 1   // bf16 mode: swish with one MUFU op (tanh.approx) instead of two (ex2 + rcp)
 #endif
 
 namespace mc {
