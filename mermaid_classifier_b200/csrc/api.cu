@@ -408,7 +408,7 @@ int mc_crop_patches(const mc_image* images, int32_t n_images, const mc_point* po
   MC_CUDA(cudaMemcpyAsync(d_pt, points, n * sizeof(mc_point), cudaMemcpyHostToDevice, st));
   for (int64_t s = 0; s < n; s += 32768) {
     const int nb = (int)std::min<int64_t>(32768, n - s);
-    crop_kernel<<<dim3(224, nb), 224, 0, st>>>(d_im, d_pt + s, patches_dev + s * 224 * 224 * 3);
+    crop_kernel<<<dim3(8, nb), 192, 0, st>>>(d_im, d_pt + s, patches_dev + s * 224 * 224 * 3);
     MC_CHECK_LAUNCH();
   }
   MC_CUDA(cudaFreeAsync(d_im, st));

@@ -30,28 +30,52 @@ __global__ void synth_image_kernel(uint8_t* img, int H, int W, int64_t pitch, ui
 }
 
 // ---- K1 stand-alone: bit-exact crop (parity gate + pre-cropped patch producer) ---------
-// grid (224 patch rows, n points), 224 threads: thread j copies pixel (i, j).
-__global__ void crop_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__ points,
-                            uint8_t* __restrict__ out) {
-  const int i = blockIdx.x;
+// grid (8 row bands, n points), 192 threads: a CTA copies 28 patch rows of 672 bytes.
+// Interior rows (no column reflection) are contiguous in the source image: thread t produces output word t
+// from two aligned 4-byte loads and a funnel shift (vectorised, coalesced; the source alignment is arbitrary
+// because a pixel is 3 bytes).  Rows that reflect in x fall back to per-pixel byte gathers through shared memory.
+// Row reflection in y only selects the source row.
+__global__ void __launch_bounds__(192) crop_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__ points,
+                                                   uint8_t* __restrict__ out) {
+  constexpr int ROWS = 28;
   const int64_t k = blockIdx.y;
   const mc_point pt = points[k];
   const mc_image im = images[pt.image];
-  const int y = reflect_idx(pt.row - 112 + i, im.height);
-  const uint8_t* src_row = im.data + (int64_t)y * im.row_pitch;
+  const int x0 = pt.col - 112;
+  // one pixel of slack on the right: the last aligned word of a misaligned segment reaches up to 3 bytes past it
+  const bool interior = x0 >= 0 && x0 + 225 <= im.width;
+  const int tid = threadIdx.x;
   __shared__ uint8_t row_s[224 * 3];
-  for (int j = threadIdx.x; j < 224; j += blockDim.x) {
-    const int x = reflect_idx(pt.col - 112 + j, im.width);
-    const uint8_t* s = src_row + (int64_t)x * 3;
-    row_s[j * 3 + 0] = s[0];
-    row_s[j * 3 + 1] = s[1];
-    row_s[j * 3 + 2] = s[2];
+#pragma unroll 7
+  for (int r = 0; r < ROWS; ++r) {
+    const int i = blockIdx.x * ROWS + r;
+    const int y = reflect_idx(pt.row - 112 + i, im.height);
+    const uint8_t* src_row = im.data + (int64_t)y * im.row_pitch;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (k * 224 + i) * 672);
+    if (interior) {
+      if (tid < 168) {
+        const uint8_t* s = src_row + (int64_t)x0 * 3 + tid * 4;        // first source byte of output word `tid`
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3) * 8u;
+        const uint32_t w0 = __ldg(w);
+        // the second word is only dereferenced when the segment is misaligned (never reads past the last needed byte's word)
+        const uint32_t w1 = sh ? __ldg(w + 1) : 0u;
+        dst[tid] = __funnelshift_r(w0, w1, sh);
+      }
+    } else {
+      for (int j = tid; j < 224; j += 192) {
+        const int x = reflect_idx(x0 + j, im.width);
+        const uint8_t* s = src_row + (int64_t)x * 3;
+        row_s[j * 3 + 0] = s[0];
+        row_s[j * 3 + 1] = s[1];
+        row_s[j * 3 + 2] = s[2];
+      }
+      __syncthreads();
+      if (tid < 168) dst[tid] = reinterpret_cast<const uint32_t*>(row_s)[tid];
+      __syncthreads();
+    }
   }
-  __syncthreads();
-  // coalesced 4-byte stores of the 672-byte output row
-  uint32_t* dst = reinterpret_cast<uint32_t*>(out + (k * 224 + i) * 672);
-  const uint32_t* srs = reinterpret_cast<const uint32_t*>(row_s);
-  for (int t = threadIdx.x; t < 168; t += blockDim.x) dst[t] = srs[t];
 }
 
 // ---- A3 stand-alone: ToTensor + Normalize (parity gate only) ---------------------------
