@@ -27,21 +27,18 @@ for _, n, _, _, us in sub: fam[family(n)] = fam.get(family(n), 0.0) + us
 tot = sum(fam.values())
 shares = {k: round(v / tot, 4) for k, v in fam.items()}
 
-# 2. per-kernel full-set summaries
+# 2. per-kernel full-set summaries (already condensed on the GPU box by tools/ncu_capture.sh)
 summ = []
-for name in ("stem", "dw_b1", "dw_b4", "exp_b1", "proj_b2", "head_conv", "head_rows"):
-    rep = g / f"prof_{name}_{mode}.ncu-rep"
-    if not rep.exists(): continue
-    t = subprocess.run([sys.executable, "tools/ncu_table.py", str(rep)], capture_output=True, text=True).stdout.strip().splitlines()
-    hdr, row = t[0].split(","), t[-1].split(",")
-    d = dict(zip(hdr, row)); d["capture"] = name
-    summ.append(d)
-if summ:
-    cols = ["capture"] + [c for c in summ[0] if c not in ("capture", "idx")]
+kf = g / f"kernels_{mode}.csv"
+if kf.exists():
+    lines = [l for l in kf.read_text().splitlines() if l.strip()]
+    hdr = lines[0].split(",")
+    for l in lines[1:]:
+        if l.startswith("capture,"): continue
+        summ.append(dict(zip(hdr, l.split(","))))
     with open(out / f"{tag}_kernels_{mode}.csv", "w") as f:
         f.write("# ncu --set full --clock-control none, one launch each (500 patches); dram_*_MB = dram__bytes_{read,write}.sum per launch\n")
-        f.write(",".join(cols) + "\n")
-        for d in summ: f.write(",".join(d.get(c, "") for c in cols) + "\n")
+        f.write("\n".join(lines) + "\n")
 json.dump({"mode": mode, "patches_per_launch": 500, "family_time_shares_ncu": shares, "sub_batch_us_ncu": round(tot, 1),
            "traffic_MB_per_launch": {d["capture"]: round(float(d["dram_rd_MB"]) + float(d["dram_wr_MB"]), 1) for d in summ}},
           open(out / f"{tag}_summary_{mode}.json", "w"), indent=1)

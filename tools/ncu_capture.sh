@@ -1,19 +1,21 @@
 #!/bin/bash
-# Round-1 ncu evidence (run under gpurun): launch list of one 500-patch sub-batch + full-set captures of one
-# kernel per family.  Outputs under gpurun_out/; tools/ncu_table.py / ncu_src.py summarise them into profiles/.
-MODE=${1:-fp32}
+# ncu evidence (run under gpurun): launch list of one 500-patch sub-batch + `--set full` captures of one kernel
+# per family.  Reports are summarised ON the GPU box (tools/ncu_table.py) and deleted: gpurun_out/ is capped at 64 MiB.
+MODE=${1:-fp32}; shift
+CAPS=${@:-"stem:stem_kernel:0 dw_b1:dw_tma_kernel:1 dw_b4:dw_reg_kernel:2 dw_b9:dw_reg_kernel:7 exp_b1:pw_tc_kernel:1 proj_b2:pw_tc_kernel:4 proj_b15:pw_tc_kernel:30 head_conv:pw_tc_kernel:31"}
 CMD="python bench.py --images 5 --batch 500 --steps 1 --no-cpu-baseline --mode $MODE"
 timeout 120 $CMD > gpurun_out/plain_$MODE.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$MODE.log; exit 1; }
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$MODE.csv $CMD > gpurun_out/ncu_l.log 2>&1
-cap() {  # name regex skip
-  timeout 200 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o gpurun_out/prof_${1}_$MODE -f $CMD > gpurun_out/ncu_$1.log 2>&1
-  tail -1 gpurun_out/ncu_$1.log
-}
-cap stem stem_kernel 0
-cap dw_b1 dw_tma_kernel 1
-cap dw_b4 dw_reg_kernel 2
-cap exp_b1 "pw_tc_kernel.*Lb0" 0
-cap proj_b2 "pw_tc_kernel.*Lb1" 2
-cap head_conv "pw_tc_kernel.*Lb0" 15
-cap head_rows head_rows_kernel 0
-ls -la gpurun_out/*.ncu-rep
+# pw_tc launches of a sub-batch in order: b0.project(0) b1.expand(1) b1.project(2) ... b15.project(30) head conv(31)
+OUT=gpurun_out/kernels_$MODE.csv; : > $OUT
+for spec in $CAPS; do
+  IFS=: read name regex skip <<< "$spec"
+  timeout 200 ncu --set full --clock-control none -k regex:$regex -s $skip -c 1 -o /tmp/prof_$name -f $CMD > gpurun_out/ncu_$name.log 2>&1
+  if [ -f /tmp/prof_$name.ncu-rep ]; then
+    python tools/ncu_table.py /tmp/prof_$name.ncu-rep | awk -v n=$name 'NR==1 && !h {print "capture," $0} NR>1 {print n "," $0}' h=$( [ -s $OUT ] && echo 1 ) >> $OUT
+    rm -f /tmp/prof_$name.ncu-rep
+  else
+    echo "capture $name failed"; tail -2 gpurun_out/ncu_$name.log
+  fi
+done
+cat $OUT | cut -c1-160
