@@ -150,6 +150,9 @@ int mc_head_create(int32_t n_layers, const int32_t* dims /* n_layers + 1 */,
                    const float* platt_a_host, const float* platt_b_host, int32_t device,
                    mc_head** out);
 int mc_head_destroy(mc_head* h);
+/* The Linear/ReLU chain runs on the tensor cores (tcgen05, 3xTF32 split, fp32-class) by default; exact != 0 selects the
+ * exact-fp32 CUDA-core GEMM (used by predict_proba, whose contract is the reference's 1e-6 export gate). */
+int mc_head_set_exact(mc_head* h, int32_t exact);
 
 /* features_dev: n x dims[0] fp32.  Any of the outputs may be NULL.
  *   proba_dev  : n x K float64 (predict_proba)

@@ -71,6 +71,7 @@ SIGNATURES = {
     "mc_extractor_profile_read": (C.c_int, [_vp, _vp, _vp, _i32]),
     "mc_head_create": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _pp]),
     "mc_head_destroy": (C.c_int, [_vp]),
+    "mc_head_set_exact": (C.c_int, [_vp, _i32]),
     "mc_head_scores": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "mc_head_scores_host": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "mc_head_launches": (_i64, [_vp]),

@@ -645,6 +645,10 @@ struct mc_head {
   int32_t* d_labels = nullptr;
   int64_t cap_feats = 0, cap_proba = 0, cap_labels = 0;
   int64_t launches = 0;
+  // tensor-core Linear chain (tcgen05, 3xTF32): used by the device scoring path unless `exact` is requested
+  PwTcPlan* tc = nullptr;
+  float* d_ones = nullptr;
+  bool exact = false;   // MC_HEAD_EXACT / mc_head_set_exact: run the Linear chain on the exact-fp32 CUDA-core GEMM
 };
 
 extern "C" {
@@ -701,7 +705,42 @@ int mc_head_create(int32_t n_layers, const int32_t* dims, const float* const* we
     mc_head_destroy(h);
     return fail(MC_ERR_CUDA, std::string("mc_head_create: ") + cudaGetErrorString(e));
   }
+  // tcgen05 plan of the Linear chain: layer i = (dims_p[i+1] x dims_p[i]) padded weights, scale 1, bias, ReLU between layers
+  {
+    int max_w = 0;
+    for (int d : h->dims_p) max_w = std::max(max_w, d);
+    cudaDeviceProp prop;
+    bool ok = cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.major == 10 && max_w <= 1280 && getenv("MC_HEAD_EXACT") == nullptr;
+    if (ok) {
+      std::vector<float> ones((size_t)max_w, 1.f);
+      ok = cudaMalloc((void**)&h->d_ones, ones.size() * sizeof(float)) == cudaSuccess &&
+           cudaMemcpy(h->d_ones, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (ok) {
+      PwTcPlan* plan = new PwTcPlan();
+      plan->mode = MC_MODE_FP32;
+      plan->device = device;
+      plan->num_sms = prop.multiProcessorCount;
+      plan->max_batch = (int)h->chunk;
+      plan->layers.resize(n_layers);
+      ok = cudaFuncSetAttribute(pw_tc_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET) == cudaSuccess;
+      for (int i = 0; i < n_layers && ok; ++i) {
+        const int ki = h->dims[i], no = h->dims[i + 1], kp = h->dims_p[i], np_ = h->dims_p[i + 1];
+        std::vector<float> wp((size_t)np_ * kp, 0.f);
+        for (int r = 0; r < no; ++r) memcpy(&wp[(size_t)r * kp], weights[i] + (size_t)r * ki, ki * sizeof(float));
+        ok = pw_tc_add(plan, i, wp.data(), h->d_ones, h->d_b[i], np_, kp, i < n_layers - 1 ? 2 : 0, false) == MC_OK;
+      }
+      if (ok) h->tc = plan;
+      else pw_tc_free(plan);
+    }
+  }
   *out = h;
+  return MC_OK;
+}
+
+int mc_head_set_exact(mc_head* h, int32_t exact) {
+  if (!h) return fail(MC_ERR_BAD_ARG, "null handle");
+  h->exact = exact != 0;
   return MC_OK;
 }
 
@@ -711,8 +750,9 @@ int mc_head_destroy(mc_head* h) {
   for (float* p : h->d_w) if (p) cudaFree(p);
   for (float* p : h->d_b) if (p) cudaFree(p);
   for (float* p : h->d_act) if (p) cudaFree(p);
-  void* ptrs[] = {h->d_a, h->d_pb, h->d_in_pad, h->d_feats, h->d_proba, h->d_labels};
+  void* ptrs[] = {h->d_a, h->d_pb, h->d_in_pad, h->d_feats, h->d_proba, h->d_labels, h->d_ones};
   for (void* p : ptrs) if (p) cudaFree(p);
+  pw_tc_free(h->tc);
   delete h;
   return MC_OK;
 }
@@ -736,8 +776,19 @@ int mc_head_scores(mc_head* h, const float* features_dev, int64_t n, double* pro
       h->launches++;
       x = h->d_in_pad;
     }
+    const bool use_tc = h->tc != nullptr && !h->exact;
+    const bool x_is_callers = x == features_dev + s * h->dims[0];
     for (int i = 0; i < L; ++i) {
       const int N = h->dims_p[i + 1], Kd = h->dims_p[i];
+      if (use_tc) {
+        // layer 0 reads the caller's feature rows [s, s + m): the map covers exactly those rows
+        const int64_t map_rows = (i == 0 && x_is_callers) ? m : -1;
+        int rc = pw_tc_run(h->tc, i, x, 0, nullptr, nullptr, h->d_act[i], m, 1, st, map_rows);
+        if (rc) return rc;
+        h->launches++;
+        x = h->d_act[i];
+        continue;
+      }
       dim3 grid(cdiv(m, 64), cdiv(N, 64));
       if (i < L - 1)
         pw_simt_kernel<float, float, ACT_RELU, false, false><<<grid, 256, 0, st>>>(x, h->d_w[i], nullptr, h->d_b[i], nullptr,

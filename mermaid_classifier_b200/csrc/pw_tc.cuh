@@ -622,6 +622,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     for (int e = 0; e < 4; ++e) y[e] = fmaf(y[e], ptx::tanh_approx(y[e]), y[e]);
                   }
                 }
+                if (p.act == 2) {   // ReLU (MLP head Linear layers)
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+                }
                 const int off = row * p.N + c0 + cb;
                 if (res_t != nullptr) {
                   float r[4];
@@ -698,6 +702,7 @@ struct PwTcLayer {
   CUtensorMap tmW, tmWlo;
   // activation maps are cached per source pointer (the ping-pong buffers alternate)
   const void* a_ptr[2] = {nullptr, nullptr};
+  int64_t a_rows[2] = {0, 0};
   CUtensorMap tmA[2];
 };
 
@@ -811,20 +816,23 @@ inline int pw_tc_build(PwTcPlan** out, const NetCfg& net, const float* params_ho
 
 // `A` is the BASE of the activation buffer (its tensor map is cached per layer); the launch covers rows
 // [a_row_off, a_row_off + M) of it.  gate / res / outp are already offset to the launch's first row.
+// map_rows >= 0: the activation buffer is caller-owned and holds exactly that many rows (the map must not reach past it).
 inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, const void* gate, const void* res, void* outp,
-                     int64_t M, int HW, cudaStream_t st) {
+                     int64_t M, int HW, cudaStream_t st, int64_t map_rows = -1) {
   PwTcLayer& l = plan->layers[id];
   const bool f32 = plan->mode == MC_MODE_FP32;
   // tensor map of the activation source (cached: each layer only ever sees the ping-pong buffers)
+  const int64_t rows = map_rows >= 0 ? map_rows : (int64_t)plan->max_batch * HW;
   int slot = -1;
   for (int i = 0; i < 2; ++i)
-    if (l.a_ptr[i] == A) slot = i;
+    if (l.a_ptr[i] == A && l.a_rows[i] == rows) slot = i;
   if (slot < 0) {
     slot = l.a_ptr[0] == nullptr ? 0 : 1;
     // rows = the buffer's capacity for this layer: rows past it are zero-filled by TMA, never read
-    int rc = make_map(&l.tmA[slot], f32, A, (int64_t)plan->max_batch * HW, l.K, TC_BM);
+    int rc = make_map(&l.tmA[slot], f32, A, rows, l.K, TC_BM);
     if (rc) return rc;
     l.a_ptr[slot] = A;
+    l.a_rows[slot] = rows;
   }
   PwTcArgs a;
   a.scale = l.scale;

@@ -128,7 +128,14 @@ class DeviceHead:
         except Exception:
             pass
 
-    def scores_host(self, arr: np.ndarray, want_proba=True, want_labels=True):
+    def _set_exact(self, exact: bool) -> None:
+        _lib.check(_lib.load().mc_head_set_exact(self._h, 1 if exact else 0))
+
+    def scores_host(self, arr: np.ndarray, want_proba=True, want_labels=True, exact: bool | None = None):
+        """``exact`` (default: whenever probabilities are returned) runs the Linear chain on the exact-fp32
+        CUDA-core GEMM -- ``predict_proba`` keeps the reference's 1e-6 export tolerance -- otherwise on the
+        tensor cores (tcgen05, 3xTF32 split, error ~2^-21)."""
+        self._set_exact(want_proba if exact is None else exact)
         n = arr.shape[0]
         proba = np.empty((n, self.n_classes), dtype=np.float64) if want_proba else None
         labels = np.empty((n,), dtype=np.int32) if want_labels else None
@@ -138,8 +145,10 @@ class DeviceHead:
                 labels.ctypes.data if want_labels else None, _lib.stream_ptr()))
         return proba, labels
 
-    def scores_device(self, feats: torch.Tensor, want_proba=False, topk: int = 0):
-        """CUDA fp32 ``(n, input_dim)`` -> dict of CUDA tensors (labels / proba / topk)."""
+    def scores_device(self, feats: torch.Tensor, want_proba=False, topk: int = 0, exact: bool | None = None):
+        """CUDA fp32 ``(n, input_dim)`` -> dict of CUDA tensors (labels / proba / topk).  Same rule as
+        :meth:`scores_host`: exact chain when probabilities are returned (unless overridden), tensor cores otherwise."""
+        self._set_exact(want_proba if exact is None else exact)
         if feats.dtype != torch.float32 or feats.dim() != 2 or feats.shape[1] != self.dims[0] or not feats.is_contiguous():
             raise ValueError(f"features must be contiguous CUDA float32 (N, {self.dims[0]}); got {tuple(feats.shape)}")
         n = feats.shape[0]

@@ -77,3 +77,21 @@ def test_unpadded_dims():
     want = ohead.calibrated_proba(X, w, bb, a, b)
     assert np.max(np.abs(proba - want)) <= 1e-6
     assert np.array_equal(labels, want.argmax(1))
+
+
+@pytest.mark.parametrize("hidden", [(200, 100), (500, 300, 100)])
+def test_tensor_core_chain_matches_exact_chain(hidden):
+    """Device scoring runs the Linear chain on tcgen05 (3xTF32); it must agree with the exact-fp32 chain and the oracle:
+    proba within 1e-5, >= 99.9 % identical labels; ragged row counts exercise the TMA row bound."""
+    w, bb, a, b, _ = synth.synth_head(1280, hidden, 500, seed=0)
+    head = DeviceHead([x.numpy() for x in w], [x.numpy() for x in bb], a.numpy(), b.numpy())
+    for n in (1, 127, 129, 5000):
+        X = synth.synth_features(n, 1280, seed=21 + n)
+        xd = X.cuda()
+        fast = head.scores_device(xd, want_proba=True, topk=3, exact=False)
+        exact = head.scores_device(xd, want_proba=True, topk=3, exact=True)
+        want = ohead.calibrated_proba(X.numpy(), w, bb, a, b)
+        assert torch.max(torch.abs(fast["proba"] - exact["proba"])).item() <= 1e-5
+        assert np.max(np.abs(fast["proba"].cpu().numpy() - want)) <= 1e-5
+        assert (fast["labels"].cpu().numpy() == want.argmax(1)).mean() >= 0.999
+        assert (fast["labels"] == exact["labels"]).float().mean().item() >= 0.999
