@@ -252,11 +252,14 @@ def run_b200(args, rank: int, world: int, local: int):
     torch.cuda.synchronize()
 
     lib = _lib.load()
+    _shift = torch.empty(int(float(os.environ.get('MC_SHIFT_MB', '0')) * (1 << 20)) + 1, dtype=torch.uint8, device=dev)  # address-shift experiment
     h = ext._ensure_handle()
+
+    _hx = os.environ.get('MC_BENCH_HEAD_EXACT') is not None   # experiment: exact head chain at run time
 
     def step_resident():
         ext.extract_device(images, points, out=feats)
-        return head.scores_device(feats)["labels"]
+        return head.scores_device(feats, exact=_hx)["labels"]
 
     # ---- warm-up, with one fully profiled pass to find the dominant kernel ------------------
     lbytes = layer_bytes(4 if args.mode == "fp32" else 2)

@@ -19,6 +19,17 @@
 
 using namespace mc;
 
+#ifdef MC_PAD
+// placement experiment: a dummy kernel of MC_PAD FMAs shifts the code addresses of the kernels linked after it
+__global__ void mc_pad_kernel(float* p) {
+  float x = p[0];
+#pragma unroll
+  for (int i = 0; i < MC_PAD; ++i) x = fmaf(x, 1.0001f, 0.5f + (float)i);
+  p[0] = x;
+}
+void* mc_pad_ref = (void*)mc_pad_kernel;
+#endif
+
 
 
 namespace {
@@ -719,11 +730,11 @@ int mc_head_create(int32_t n_layers, const int32_t* dims, const float* const* we
     if (ok) {
       PwTcPlan* plan = new PwTcPlan();
       plan->mode = MC_MODE_FP32;
+      plan->relu_variant = true;
       plan->device = device;
       plan->num_sms = prop.multiProcessorCount;
       plan->max_batch = (int)h->chunk;
       plan->layers.resize(n_layers);
-      ok = cudaFuncSetAttribute(pw_tc_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET) == cudaSuccess;
       for (int i = 0; i < n_layers && ok; ++i) {
         const int ki = h->dims[i], no = h->dims[i + 1], kp = h->dims_p[i], np_ = h->dims_p[i + 1];
         std::vector<float> wp((size_t)np_ * kp, 0.f);

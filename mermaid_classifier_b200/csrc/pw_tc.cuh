@@ -209,6 +209,7 @@ struct PwTcArgs {
   int N, K, HW, BN, n_blocks, k_chunks, act, stages;
   long long* dbg;     // MC_TC_DBG: per-role wait/total cycle counters of CTA 0 (null = off)
   int exp_flags;      // MC_TC_EXP timing experiments: 1 no activation, 2 no global stores, 4 no operand transform, 16 no MMA, 32 no tcgen05.ld
+  int w_res;          // 1: the layer's whole weight (all n-blocks x k-chunks, hi+lo) stays resident in smem
   int a_row_off;      // first row of this launch inside the activation tensor map (chunked execution)
   int64_t m_tiles;
 };
@@ -253,19 +254,39 @@ inline int tc_num_stages(int BN) {
   int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES) / tc_stage_bytes<T>(BN);
   return s > TC_MAX_STAGES ? TC_MAX_STAGES : s;
 }
+// resident-weight layout: W region of n_blocks * k_chunks * NW tiles, stages carry the A operands only
+constexpr int TC_W_RES_MAX = 96 * 1024;
+template <typename T>
+inline int tc_w_res_bytes(int BN, int n_blocks, int k_chunks) {
+  return n_blocks * k_chunks * TcCfg<T>::NW * ((BN * 128 + 1023) / 1024 * 1024);
+}
+template <typename T>
+inline int tc_num_stages_res(int w_bytes) {
+  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES - w_bytes) / (TcCfg<T>::NA * TcCfg<T>::A_BYTES);
+  return s > TC_MAX_STAGES ? TC_MAX_STAGES : s;
+}
 
-template <typename T, bool GATED>
+// RELU: a separate instantiation for the MLP-head Linear layers.  The conv instantiations must not even carry the
+// (never taken) ReLU branch: b1.expand sits on a scheduling knife-edge between 4.7 and 3.1 TB/s, and that branch alone
+// tipped it (measured, round 1).
+template <typename T, bool GATED, bool RELU = false>
 __global__ void __launch_bounds__(tc_threads<GATED>(), 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmWlo, const PwTcArgs p) {
   using Cfg = TcCfg<T>;
   const int S = p.stages;
   const int W_BYTES = (p.BN * 128 + 1023) / 1024 * 1024;       // one W operand tile (1024-aligned)
-  const int STAGE_BYTES = Cfg::NA * Cfg::A_BYTES + Cfg::NW * W_BYTES;
+  // Weight residency: when the whole layer weight fits, it is loaded ONCE per CTA and the ring carries activations only.
+  // Re-fetching the same W tile for every work item made 148 CTAs hammer a handful of L2 lines: throughput of the
+  // front layers then depended on which L2 slices the weight allocation happened to hash to (4.8 vs 3.2 TB/s on b1.expand).
+  const bool w_res = p.w_res != 0;
+  const int W_RES_BYTES = w_res ? p.n_blocks * p.k_chunks * Cfg::NW * W_BYTES : 0;
+  const int STAGE_BYTES = Cfg::NA * Cfg::A_BYTES + (w_res ? 0 : Cfg::NW * W_BYTES);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* stage_base = smem;
-  uint8_t* epi_base = smem + (size_t)S * STAGE_BYTES;          // 8 x 4 KB, 1024-aligned
+  uint8_t* w_base = smem;                                      // resident weights (1024-aligned tiles), may be empty
+  uint8_t* stage_base = smem + W_RES_BYTES;
+  uint8_t* epi_base = stage_base + (size_t)S * STAGE_BYTES;
   float* sc_s = (float*)(epi_base + TC_EPI_BYTES);
   float* bi_s = sc_s + 1280;
   uint64_t* bars = (uint64_t*)(bi_s + 1280);
@@ -274,7 +295,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty = bars + 2 * TC_MAX_STAGES;     // [S]   MMAs reading the stage retired
   uint64_t* tfull = bars + 3 * TC_MAX_STAGES;     // [4]   accumulator complete
   uint64_t* tempty = tfull + 4;                   // [4]   accumulator drained
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 4);
+  uint64_t* wbar = tempty + 4;                    // resident weights landed
+  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // accumulator stages in TMEM: 4 x 128 columns when the block fits, else 2 x 256
@@ -306,6 +328,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::mbar_init(&ready[s], (uint32_t)(ntw * 32));
       ptx::mbar_init(&empty[s], 1);
     }
+    ptx::mbar_init(wbar, 1);
     for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&tfull[s], 1);
       ptx::mbar_init(&tempty[s], 128);
@@ -326,7 +349,17 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = Cfg::A_BYTES + (uint32_t)p.BN * 128u * (Cfg::TF32 ? 2u : 1u);
+      const uint32_t w_tile_tx = (uint32_t)p.BN * 128u;   // bytes one W box delivers
+      const uint32_t tx = Cfg::A_BYTES + (w_res ? 0u : w_tile_tx * (Cfg::TF32 ? 2u : 1u));
+      if (w_res) {
+        ptx::mbar_expect_tx(wbar, w_tile_tx * (uint32_t)(p.n_blocks * p.k_chunks * Cfg::NW));
+        for (int nb_ = 0; nb_ < p.n_blocks; ++nb_)
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            uint8_t* wt = w_base + (size_t)((nb_ * p.k_chunks + kc) * Cfg::NW) * W_BYTES;
+            ptx::tma_load_2d(wt, &tmW, wbar, kc * Cfg::KC, nb_ * p.BN);
+            if (Cfg::TF32) ptx::tma_load_2d(wt + W_BYTES, &tmWlo, wbar, kc * Cfg::KC, nb_ * p.BN);
+          }
+      }
       long long w_empty = 0;
       const long long t_begin = ptx::tc_clock();
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -338,11 +371,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint8_t* st = stage_base + (size_t)s * STAGE_BYTES;
           ptx::mbar_expect_tx(&full[s], tx);
           ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, m0);
-          if (Cfg::TF32) {
-            ptx::tma_load_2d(st + 2 * Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
-            ptx::tma_load_2d(st + 2 * Cfg::A_BYTES + W_BYTES, &tmWlo, &full[s], kc * Cfg::KC, n0);
-          } else {
-            ptx::tma_load_2d(st + Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
+          if (!w_res) {
+            if (Cfg::TF32) {
+              ptx::tma_load_2d(st + 2 * Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
+              ptx::tma_load_2d(st + 2 * Cfg::A_BYTES + W_BYTES, &tmWlo, &full[s], kc * Cfg::KC, n0);
+            } else {
+              ptx::tma_load_2d(st + Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
+            }
           }
           if (++s == S) {
             s = 0;
@@ -365,9 +400,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int li = 0;
       long long w_tempty = 0, w_full = 0;
       const long long t_begin = ptx::tc_clock();
+      if (w_res) {
+        ptx::mbar_wait(wbar, 0);
+        ptx::tc_fence_after();
+      }
       for (int it = blockIdx.x; it < items; it += gridDim.x, ++li) {
         const int as = li % NAS;
         const uint32_t use = (uint32_t)(li / NAS);
+        const int nb_i = (int)((uint32_t)it - ((uint32_t)it / nblk) * nblk);   // n-block of this item
         w_tempty += ptx::mbar_wait_timed(&tempty[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_cols);
@@ -375,6 +415,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           w_full += ptx::mbar_wait_timed(transform ? &ready[s] : &full[s], ph);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+          // W tile of (n-block, k-chunk): resident region, or behind the A operands of this stage
+          const uint32_t w_addr = w_res ? ptx::smem_u32(w_base + (size_t)((nb_i * p.k_chunks + kc) * Cfg::NW) * W_BYTES)
+                                        : a_addr + Cfg::NA * Cfg::A_BYTES;
           const int krem = p.K - kc * Cfg::KC;
           const int ksteps = (min(krem, Cfg::KC) + Cfg::UK - 1) / Cfg::UK;
           for (int ks = 0; ks < ((p.exp_flags & 16) ? 0 : ksteps); ++ks) {
@@ -383,14 +426,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (Cfg::TF32) {
               const uint64_t ahi = umma_desc_sw128(a_addr + koff);
               const uint64_t alo = umma_desc_sw128(a_addr + Cfg::A_BYTES + koff);
-              const uint64_t whi = umma_desc_sw128(a_addr + 2 * Cfg::A_BYTES + koff);
-              const uint64_t wlo = umma_desc_sw128(a_addr + 2 * Cfg::A_BYTES + W_BYTES + koff);
+              const uint64_t whi = umma_desc_sw128(w_addr + koff);
+              const uint64_t wlo = umma_desc_sw128(w_addr + W_BYTES + koff);
               ptx::mma_ss<true>(d_tmem, alo, whi, idesc, acc);
               ptx::mma_ss<true>(d_tmem, ahi, wlo, idesc, 1u);
               ptx::mma_ss<true>(d_tmem, ahi, whi, idesc, 1u);
             } else {
-              ptx::mma_ss<false>(d_tmem, umma_desc_sw128(a_addr + koff), umma_desc_sw128(a_addr + Cfg::A_BYTES + koff),
-                                 idesc, acc);
+              ptx::mma_ss<false>(d_tmem, umma_desc_sw128(a_addr + koff), umma_desc_sw128(w_addr + koff), idesc, acc);
             }
           }
           ptx::mma_commit(&empty[s]);
@@ -622,9 +664,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     for (int e = 0; e < 4; ++e) y[e] = fmaf(y[e], ptx::tanh_approx(y[e]), y[e]);
                   }
                 }
-                if (p.act == 2) {   // ReLU (MLP head Linear layers)
+                if (RELU) {   // MLP head Linear layers (hidden layers; the last layer runs with act 0 but shares the instantiation)
+                  if (p.act == 2) {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+                    for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+                  }
                 }
                 const int off = row * p.N + c0 + cb;
                 if (res_t != nullptr) {
@@ -708,6 +752,7 @@ struct PwTcLayer {
 
 struct PwTcPlan {
   int mode = 0, device = 0, num_sms = 148, max_batch = 0;
+  bool relu_variant = false;   // launch the RELU instantiation (MLP head)
   std::vector<PwTcLayer> layers;  // 2*b = expand of block b, 2*b+1 = project, 32 = head conv
 };
 
@@ -860,13 +905,29 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   a.n_blocks = l.n_blocks;
   a.k_chunks = l.k_chunks;
   a.act = l.act;
-  a.stages = f32 ? tc_num_stages<float>(l.BN) : tc_num_stages<__nv_bfloat16>(l.BN);
-  const size_t smem = TC_FIXED_BYTES + (size_t)a.stages * (f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN));
+  const int w_bytes = f32 ? tc_w_res_bytes<float>(l.BN, l.n_blocks, l.k_chunks) : tc_w_res_bytes<__nv_bfloat16>(l.BN, l.n_blocks, l.k_chunks);
+  static const bool no_w_res = getenv("MC_TC_NO_WRES") != nullptr;   // experiment switch
+  a.w_res = (!no_w_res && w_bytes <= TC_W_RES_MAX) ? 1 : 0;
+  size_t smem;
+  if (a.w_res) {
+    a.stages = f32 ? tc_num_stages_res<float>(w_bytes) : tc_num_stages_res<__nv_bfloat16>(w_bytes);
+    smem = TC_FIXED_BYTES + (size_t)w_bytes + (size_t)a.stages * (f32 ? 2 : 1) * TC_BM * 128;
+  } else {
+    a.stages = f32 ? tc_num_stages<float>(l.BN) : tc_num_stages<__nv_bfloat16>(l.BN);
+    smem = TC_FIXED_BYTES + (size_t)a.stages * (f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN));
+  }
   a.m_tiles = (M + TC_BM - 1) / TC_BM;
   const int64_t items = a.m_tiles * a.n_blocks;
   const int grid = (int)std::min<int64_t>(items, plan->num_sms);
   const bool gated = a.gate != nullptr;
-  if (f32 && gated)
+  if (plan->relu_variant) {   // MLP head (fp32, ungated)
+    static bool attr_set = false;
+    if (!attr_set) {
+      MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+      attr_set = true;
+    }
+    pw_tc_kernel<float, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+  } else if (f32 && gated)
     pw_tc_kernel<float, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
   else if (f32)
     pw_tc_kernel<float, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
