@@ -282,7 +282,7 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
   int rc;
   {
     ProfScope ps(h, 0, st);
-    stem_kernel<T><<<dim3(49, nb), 256, 0, st>>>(h->d_images, h->d_points, h->stem, h->d_lut, X);
+    stem_kernel<T><<<dim3(7, nb), 256, 0, st>>>(h->d_images, h->d_points, h->stem, h->d_lut, X);
   }
   MC_CHECK_LAUNCH();
   h->launches++;

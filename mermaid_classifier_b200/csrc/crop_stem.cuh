@@ -113,82 +113,88 @@ __device__ __forceinline__ int reflect_fast(int t, int n) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) stem_kernel(const mc_image* __restrict__ images,
+__global__ void __launch_bounds__(256, 3) stem_kernel(const mc_image* __restrict__ images,
                                                    const mc_point* __restrict__ points,
                                                    const __grid_constant__ StemParams P,
                                                    const float* __restrict__ lut,    // [3][256]
                                                    T* __restrict__ out) {            // [n][112][112][32]
+  // One CTA = one ROW of seven 16x16 output tiles of one patch (grid 7 x n).  The source bytes of tile t+1 are
+  // gathered into registers while tile t is convolved, so the gather's DRAM latency hides behind the FMAs.
   constexpr int TS = 16, IN = 2 * TS + 1;  // 33
+  constexpr int NT = 7;                    // tiles per row
   __shared__ float in_s[IN][IN * 3 + 1];
   __shared__ float lut_s[768];
   const int tid = threadIdx.x;
-  const int tile = blockIdx.x;
-  const int oy0 = (tile / 7) * TS, ox0 = (tile % 7) * TS;
+  const int oy0 = blockIdx.x * TS;
   const int64_t k = blockIdx.y;
   const mc_point pt = points[k];
   const mc_image im = images[pt.image];
-
-  // gather: IN rows x IN pixels x 3 bytes.  All of a thread's byte loads are issued before the LUT pass.
-  constexpr int NIT = (IN * IN + 255) / 256;   // 5
+  constexpr int NIT = (IN * IN + 255) / 256;   // 5 window pixels per thread
   uint8_t px[NIT][3];
   bool ok[NIT];
+  auto gather = [&](const int ox0) {
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int t = tid + it * 256;
-    const int r = t / IN, cpx = t - r * IN;
-    const int pi = 2 * oy0 + r, pj = 2 * ox0 + cpx;  // patch coordinates; 224 == the SAME zero pad
-    ok[it] = t < IN * IN && pi < 224 && pj < 224;
-    px[it][0] = px[it][1] = px[it][2] = 0;
-    if (ok[it]) {
-      const int y = reflect_fast(pt.row - 112 + pi, im.height);
-      const int x = reflect_fast(pt.col - 112 + pj, im.width);
-      const uint8_t* s = im.data + (int64_t)y * im.row_pitch + (int64_t)x * 3;
-      px[it][0] = s[0];
-      px[it][1] = s[1];
-      px[it][2] = s[2];
-    }
-  }
-  for (int t = tid; t < 768; t += 256) lut_s[t] = lut[t];
-  __syncthreads();
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int t = tid + it * 256;
-    if (t < IN * IN) {
+    for (int it = 0; it < NIT; ++it) {
+      const int t = tid + it * 256;
       const int r = t / IN, cpx = t - r * IN;
-      in_s[r][cpx * 3 + 0] = ok[it] ? lut_s[px[it][0]] : 0.f;
-      in_s[r][cpx * 3 + 1] = ok[it] ? lut_s[256 + px[it][1]] : 0.f;
-      in_s[r][cpx * 3 + 2] = ok[it] ? lut_s[512 + px[it][2]] : 0.f;
-    }
-  }
-  __syncthreads();
-
-  const int ty = tid / TS, tx = tid % TS;
-  float acc[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float v = in_s[2 * ty + ky][(2 * tx + kx) * 3 + ci];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, P.w[((ky * 3 + kx) * 3 + ci) * 32 + c], acc[c]);
+      const int pi = 2 * oy0 + r, pj = 2 * ox0 + cpx;   // patch coordinates; 224 == the SAME zero pad
+      ok[it] = t < IN * IN && pi < 224 && pj < 224;
+      px[it][0] = px[it][1] = px[it][2] = 0;
+      if (ok[it]) {
+        const uint8_t* s = im.data + (int64_t)reflect_fast(pt.row - 112 + pi, im.height) * im.row_pitch +
+                           (int64_t)reflect_fast(pt.col - 112 + pj, im.width) * 3;
+        px[it][0] = s[0];
+        px[it][1] = s[1];
+        px[it][2] = s[2];
       }
     }
-  }
-  T* o = out + (((k * 112 + (oy0 + ty)) * 112) + (ox0 + tx)) * 32;
-  constexpr int VN = Vec<T>::N;
+  };
+  gather(0);
+  for (int t = tid; t < 768; t += 256) lut_s[t] = lut[t];
+  __syncthreads();
+  const int ty = tid / TS, tx = tid % TS;
+  for (int tile = 0; tile < NT; ++tile) {
+    const int ox0 = tile * TS;
 #pragma unroll
-  for (int q = 0; q < 32 / VN; ++q) {
-    Vec<T> v;
-#pragma unroll
-    for (int e = 0; e < VN; ++e) {
-      const int c = q * VN + e;
-      v.v[e] = bn_silu<T>(acc[c], P.scale[c], P.bias[c]);
+    for (int it = 0; it < NIT; ++it) {
+      const int t = tid + it * 256;
+      if (t < IN * IN) {
+        const int r = t / IN, cpx = t - r * IN;
+        in_s[r][cpx * 3 + 0] = ok[it] ? lut_s[px[it][0]] : 0.f;
+        in_s[r][cpx * 3 + 1] = ok[it] ? lut_s[256 + px[it][1]] : 0.f;
+        in_s[r][cpx * 3 + 2] = ok[it] ? lut_s[512 + px[it][2]] : 0.f;
+      }
     }
-    v.store(o + q * VN);
+    __syncthreads();
+    if (tile + 1 < NT) gather(ox0 + TS);   // in flight during the convolution below
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float v = in_s[2 * ty + ky][(2 * tx + kx) * 3 + ci];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, P.w[((ky * 3 + kx) * 3 + ci) * 32 + c], acc[c]);
+        }
+      }
+    }
+    T* o = out + (((k * 112 + (oy0 + ty)) * 112) + (ox0 + tx)) * 32;
+    constexpr int VN = Vec<T>::N;
+#pragma unroll
+    for (int q = 0; q < 32 / VN; ++q) {
+      Vec<T> v;
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        const int c = q * VN + e;
+        v.v[e] = bn_silu<T>(acc[c], P.scale[c], P.bias[c]);
+      }
+      v.store(o + q * VN);
+    }
+    __syncthreads();   // everyone is done reading in_s before the next tile overwrites it
   }
 }
 
