@@ -234,10 +234,13 @@ struct DwShape {
   int rows_per_band, nbands, threads, stages, smem;
 };
 
-constexpr int DW_N_SHAPES = 10;
+constexpr int DW_N_SHAPES = 12;
 constexpr int DW_SHAPE_KSCH[DW_N_SHAPES][4] = {{3, 1, 144, 56},  {5, 2, 144, 56},  {5, 1, 240, 28}, {3, 2, 240, 28},
                                                {3, 1, 480, 14},  {5, 1, 480, 14},  {5, 1, 672, 14}, {5, 2, 672, 14},
-                                               {5, 1, 1152, 7},  {3, 1, 1152, 7}};
+                                               {5, 1, 1152, 7},  {3, 1, 1152, 7},
+                                               // the two 112-wide layers: used in bf16 mode only (in fp32 the 4-channel-vector
+                                               // kernel already runs them at ~90 % of the HBM peak)
+                                               {3, 1, 32, 112},  {3, 2, 96, 112}};
 
 constexpr int dw_shape_index(int K, int S, int C, int Hin) {
   for (int i = 0; i < DW_N_SHAPES; ++i)
@@ -277,7 +280,7 @@ __host__ __device__ constexpr DwShape dw_make_shape(int K, int S, int C, int Hin
   d.bwin = (d.ptc * d.TW - 1) * S + K;
   d.box_bytes = d.bwin * d.cb * es;
   d.row_bytes = (d.box_bytes + 127) / 128 * 128;
-  d.rows_per_band = d.Hout >= 56 ? 14 : d.Hout;
+  d.rows_per_band = d.Hout >= 112 ? 16 : (d.Hout >= 56 ? 14 : d.Hout);
   d.nbands = (d.Hout + d.rows_per_band - 1) / d.rows_per_band;
   d.threads = (d.cgt * d.ptc + 31) / 32 * 32 + 32;
   const int fixed = 128 + 2 * d.ptc * d.cb * 4 + 2 * 8 * 8;
@@ -582,7 +585,8 @@ inline int dw_plan_reg(DwLayer* l, const BlockCfg& b, bool f32) {
 inline int dw_plan_layer(DwLayer* l, const BlockCfg& b, bool f32) {
   l->K = b.k; l->S = b.stride; l->C = b.c_mid; l->Hin = b.h_in; l->Hout = b.h_out; l->pad = b.pad;
   static const bool vec_env = getenv("MC_DW_VEC") != nullptr;   // experiment switch: 4-channel-vector kernel everywhere
-  if (!vec_env && b.h_in < 112) return dw_plan_reg(l, b, f32);   // the two 112-wide layers keep the 4-channel-vector kernel
+  // fp32: the two 112-wide layers keep the 4-channel-vector kernel (HBM-bound there); bf16: register-weight kernel everywhere
+  if (!vec_env && (b.h_in < 112 || !f32)) return dw_plan_reg(l, b, f32);
   l->TW = dw_pick_tw(b.k, b.stride, b.h_out);
   l->pt = (b.h_out + l->TW - 1) / l->TW;
   l->cgt = dw_pick_cgt(b.c_mid / 4, l->pt, f32);
@@ -655,6 +659,8 @@ inline int dw_reg_launch(DwLayer& l, const CUtensorMap& tm, const DwRegArgs& a, 
     case 7: return dw_reg_launch_shape<T, 7>(l, tm, a, grid, block, st);
     case 8: return dw_reg_launch_shape<T, 8>(l, tm, a, grid, block, st);
     case 9: return dw_reg_launch_shape<T, 9>(l, tm, a, grid, block, st);
+    case 10: return dw_reg_launch_shape<T, 10>(l, tm, a, grid, block, st);
+    case 11: return dw_reg_launch_shape<T, 11>(l, tm, a, grid, block, st);
   }
   return fail(MC_ERR_UNSUPPORTED, "depthwise layer shape");
 }
