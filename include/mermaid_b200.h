@@ -165,6 +165,25 @@ int mc_head_scores_host(mc_head* h, const float* features_host, int64_t n, doubl
                         int32_t* labels_host, void* stream);
 int64_t mc_head_launches(const mc_head* h); /* kernels launched so far by this handle */
 
+/* ---- A8: batched evaluation of MermaidTrainer (mermaid_classifier/pyspacer/trainer.py:295-342):
+ *      accuracy_score of the argmax labels and sklearn.metrics.log_loss(labels=classes) of
+ *      predict_proba against integer targets y_dev (positions in classes_), without materialising the
+ *      (n x K) matrix.  Returns host values (synchronises `stream`): n_correct = #(argmax == y),
+ *      loss_sum = sum_i -log(clip(p[i, y_i], eps, 1 - eps)), eps = DBL_EPSILON; a target outside
+ *      [0, K) makes loss_sum NaN.  Fixed-order reduction: bit-reproducible. ------------------- */
+int mc_head_evaluate(mc_head* h, const float* features_dev, const int32_t* y_dev, int64_t n,
+                     int64_t* n_correct, double* loss_sum, void* stream);
+
+/* ---- (f)3: Platt calibration of MermaidTrainer._calibrate_in_batches (trainer.py:344-396), i.e.
+ *      sklearn 1.5.2 _sigmoid_calibration(proba[:, k], y == k) for every class k at once.
+ *      proba_dev: n x K float64 (mc_head_scores of the uncalibrated head), y_dev: n int32 targets.
+ *      Newton + backtracking on the device until every class has |grad|_inf < gtol (sum form) or
+ *      max_passes matrix passes are spent.  a_out/b_out (host, K doubles): sigmoid(-(a p + b));
+ *      loss_out (host, K, or NULL): the per-class objective at (a, b); passes_out: passes used. */
+int mc_platt_fit(const double* proba_dev, const int32_t* y_dev, int64_t n, int32_t n_classes,
+                 int32_t device, double gtol, int32_t max_passes, double* a_out, double* b_out,
+                 double* loss_out, int32_t* passes_out, void* stream);
+
 /* ---- A7: TorchMLPClassifier.partial_fit inner loop
  *      (mermaid_classifier/pyspacer/torch_classifier.py:226-303): per mini-batch
  *      weighted CE + 0.5*alpha/mb*sum(W^2), backward, Adam.  Parameters and Adam state live

@@ -75,6 +75,8 @@ SIGNATURES = {
     "mc_head_scores": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "mc_head_scores_host": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "mc_head_launches": (_i64, [_vp]),
+    "mc_head_evaluate": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mc_platt_fit": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.c_double, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mc_mlp_create": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i32, _pp]),
     "mc_mlp_destroy": (C.c_int, [_vp]),
     "mc_dp_unique_id": (C.c_int, [_vp]),

@@ -12,6 +12,7 @@
 #include "dwconv_se.cuh"
 #include "dw_tma.cuh"
 #include "head.cuh"
+#include "platt.cuh"
 #include "layers.h"
 #include "mlp_train.cuh"
 #include "pw_simt.cuh"
@@ -659,6 +660,11 @@ struct mc_head {
   // tensor-core Linear chain (tcgen05, 3xTF32): used by the device scoring path unless `exact` is requested
   PwTcPlan* tc = nullptr;
   float* d_ones = nullptr;
+  // mc_head_evaluate workspaces: per-row log-loss terms and labels, reduction partials, [loss_sum | hits]
+  double* d_row_loss = nullptr;
+  int32_t* d_eval_labels = nullptr;
+  int64_t cap_row_loss = 0, cap_eval_labels = 0;
+  double* d_eval_parts = nullptr;  // EVAL_PARTS doubles, EVAL_PARTS int64, then the two results
   bool exact = false;   // MC_HEAD_EXACT / mc_head_set_exact: run the Linear chain on the exact-fp32 CUDA-core GEMM
 };
 
@@ -761,15 +767,19 @@ int mc_head_destroy(mc_head* h) {
   for (float* p : h->d_w) if (p) cudaFree(p);
   for (float* p : h->d_b) if (p) cudaFree(p);
   for (float* p : h->d_act) if (p) cudaFree(p);
-  void* ptrs[] = {h->d_a, h->d_pb, h->d_in_pad, h->d_feats, h->d_proba, h->d_labels, h->d_ones};
+  void* ptrs[] = {h->d_a, h->d_pb, h->d_in_pad, h->d_feats, h->d_proba, h->d_labels, h->d_ones,
+                  h->d_row_loss, h->d_eval_labels, h->d_eval_parts};
   for (void* p : ptrs) if (p) cudaFree(p);
   pw_tc_free(h->tc);
   delete h;
   return MC_OK;
 }
 
-int mc_head_scores(mc_head* h, const float* features_dev, int64_t n, double* proba_dev, int32_t* labels_dev,
-                   int32_t topk, int32_t* topk_idx_dev, float* topk_val_dev, void* stream) {
+}  // extern "C"
+
+static int head_scores_impl(mc_head* h, const float* features_dev, int64_t n, double* proba_dev, int32_t* labels_dev,
+                            int32_t topk, int32_t* topk_idx_dev, float* topk_val_dev, const int32_t* y_dev,
+                            double* row_loss_dev, void* stream) {
   if (!h) return fail(MC_ERR_BAD_ARG, "null handle");
   if (n == 0) return MC_OK;
   if (!features_dev || n < 0) return fail(MC_ERR_BAD_ARG, "mc_head_scores: null features");
@@ -819,10 +829,54 @@ int mc_head_scores(mc_head* h, const float* features_dev, int64_t n, double* pro
     head_rows_kernel<<<cdiv(m, warps), warps * 32, smem, st>>>(
         x, h->dims_p[L], K, h->d_a, h->d_pb, proba_dev ? proba_dev + s * K : nullptr,
         labels_dev ? labels_dev + s : nullptr, topk, topk_idx_dev ? topk_idx_dev + s * topk : nullptr,
-        topk_val_dev ? topk_val_dev + s * topk : nullptr, m);
+        topk_val_dev ? topk_val_dev + s * topk : nullptr, m, y_dev ? y_dev + s : nullptr,
+        row_loss_dev ? row_loss_dev + s : nullptr);
     MC_CHECK_LAUNCH();
     h->launches++;
   }
+  return MC_OK;
+}
+
+extern "C" {
+
+int mc_head_scores(mc_head* h, const float* features_dev, int64_t n, double* proba_dev, int32_t* labels_dev,
+                   int32_t topk, int32_t* topk_idx_dev, float* topk_val_dev, void* stream) {
+  return head_scores_impl(h, features_dev, n, proba_dev, labels_dev, topk, topk_idx_dev, topk_val_dev, nullptr, nullptr,
+                          stream);
+}
+
+int mc_head_evaluate(mc_head* h, const float* features_dev, const int32_t* y_dev, int64_t n, int64_t* n_correct,
+                     double* loss_sum, void* stream) {
+  if (!h) return fail(MC_ERR_BAD_ARG, "null handle");
+  if (!n_correct || !loss_sum) return fail(MC_ERR_BAD_ARG, "mc_head_evaluate: null outputs");
+  *n_correct = 0;
+  *loss_sum = 0.0;
+  if (n == 0) return MC_OK;
+  if (!features_dev || !y_dev || n < 0) return fail(MC_ERR_BAD_ARG, "mc_head_evaluate: null features / targets");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = grow(&h->d_row_loss, &h->cap_row_loss, n))) return rc;
+  if ((rc = grow(&h->d_eval_labels, &h->cap_eval_labels, n))) return rc;
+  if (!h->d_eval_parts) MC_CUDA(cudaMalloc(&h->d_eval_parts, (2 * EVAL_PARTS + 2) * sizeof(double)));
+  if ((rc = head_scores_impl(h, features_dev, n, nullptr, h->d_eval_labels, 0, nullptr, nullptr, y_dev, h->d_row_loss,
+                             stream)))
+    return rc;
+  double* part_loss = h->d_eval_parts;
+  long long* part_hits = reinterpret_cast<long long*>(h->d_eval_parts + EVAL_PARTS);
+  double* res = h->d_eval_parts + 2 * EVAL_PARTS;
+  eval_partial_kernel<<<EVAL_PARTS, 256, 0, st>>>(h->d_row_loss, h->d_eval_labels, y_dev, n, part_loss, part_hits);
+  MC_CHECK_LAUNCH();
+  eval_final_kernel<<<1, 32, 0, st>>>(part_loss, part_hits, EVAL_PARTS, res, reinterpret_cast<long long*>(res + 1));
+  MC_CHECK_LAUNCH();
+  h->launches += 2;
+  double out[2];
+  MC_CUDA(cudaMemcpyAsync(out, res, sizeof(out), cudaMemcpyDeviceToHost, st));
+  MC_CUDA(cudaStreamSynchronize(st));
+  *loss_sum = out[0];
+  long long hits;
+  memcpy(&hits, &out[1], sizeof(hits));
+  *n_correct = hits;
   return MC_OK;
 }
 
@@ -860,3 +914,4 @@ int64_t mc_head_launches(const mc_head* h) { return h ? h->launches : 0; }
 }  // extern "C"
 
 #include "mlp_api.inl"
+#include "calib_api.inl"

@@ -26,6 +26,14 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// One row's term of sklearn.metrics.log_loss (scikit-learn 1.5.2, _classification.py: clip the
+// probability to [eps, 1 - eps] with eps = finfo(float64).eps, then -log) -- what
+// MermaidTrainer._calc_acc_and_log_loss_batched averages (mermaid_classifier/pyspacer/trainer.py:310-342).
+__device__ __forceinline__ double clipped_nll(double p) {
+  const double eps = 2.220446049250313e-16;
+  return -log(fmin(fmax(p, eps), 1.0 - eps));
+}
+
 // np.argmax semantics over the warp's strided slice: larger value wins, ties -> lower index.
 __device__ __forceinline__ void warp_argmax(float& v, int& i) {
 #pragma unroll
@@ -42,7 +50,8 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
 __global__ void head_rows_kernel(const float* __restrict__ logits, int ld, int K,
                                  const float* __restrict__ pa, const float* __restrict__ pb,
                                  double* __restrict__ proba, int32_t* __restrict__ labels, int topk,
-                                 int32_t* __restrict__ topk_idx, float* __restrict__ topk_val, int64_t n) {
+                                 int32_t* __restrict__ topk_idx, float* __restrict__ topk_val, int64_t n,
+                                 const int32_t* __restrict__ y = nullptr, double* __restrict__ row_loss = nullptr) {
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,6 +93,11 @@ __global__ void head_rows_kernel(const float* __restrict__ logits, int ld, int K
       s[k] = pr;
       if (proba) proba[row * K + k] = (double)pr;
     }
+    if (y) {
+      __syncwarp();
+      const int t = y[row];
+      if (lane == 0) row_loss[row] = (t >= 0 && t < K) ? clipped_nll((double)s[t]) : NAN;
+    }
   } else {
     // uncalibrated: fp32 softmax, then renormalise in fp64 so rows sum to exactly 1
     double dsum = 0.0;
@@ -95,6 +109,11 @@ __global__ void head_rows_kernel(const float* __restrict__ logits, int ld, int K
     dsum = warp_sum_d(dsum);
     if (proba)
       for (int k = lane; k < K; k += 32) proba[row * K + k] = (double)s[k] / dsum;
+    if (y) {
+      __syncwarp();
+      const int t = y[row];
+      if (lane == 0) row_loss[row] = (t >= 0 && t < K) ? clipped_nll((double)s[t] / dsum) : NAN;
+    }
   }
   __syncwarp();
 
@@ -120,6 +139,49 @@ __global__ void head_rows_kernel(const float* __restrict__ logits, int ld, int K
     }
     __syncwarp();
   }
+}
+
+// Fixed-shape, fixed-order reduction of the per-row evaluation terms: `parts` CTAs each fold a
+// strided slice (thread-serial, then a shared-memory tree), a last single-CTA launch folds the
+// partials.  Same n and same launch shape -> bit-identical sums.
+constexpr int EVAL_PARTS = 148;
+__global__ void eval_partial_kernel(const double* __restrict__ row_loss, const int32_t* __restrict__ labels,
+                                    const int32_t* __restrict__ y, int64_t n, double* __restrict__ part_loss,
+                                    long long* __restrict__ part_hits) {
+  __shared__ double sl[256];
+  __shared__ long long sh[256];
+  double l = 0.0;
+  long long c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    l += row_loss[i];
+    c += labels[i] == y[i];
+  }
+  sl[threadIdx.x] = l;
+  sh[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sl[threadIdx.x] += sl[threadIdx.x + o];
+      sh[threadIdx.x] += sh[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part_loss[blockIdx.x] = sl[0];
+    part_hits[blockIdx.x] = sh[0];
+  }
+}
+__global__ void eval_final_kernel(const double* __restrict__ part_loss, const long long* __restrict__ part_hits, int parts,
+                                  double* __restrict__ loss_sum, long long* __restrict__ hits) {
+  if (threadIdx.x || blockIdx.x) return;
+  double l = 0.0;
+  long long c = 0;
+  for (int i = 0; i < parts; ++i) {
+    l += part_loss[i];
+    c += part_hits[i];
+  }
+  *loss_sum = l;
+  *hits = c;
 }
 
 // Copy an (n x d) fp32 matrix into a zero-padded (n x dp) one.

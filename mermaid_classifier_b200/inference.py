@@ -165,6 +165,37 @@ class DeviceHead:
                 _lib.stream_ptr()))
         return out
 
+    def evaluate_device(self, feats: torch.Tensor, y_idx: torch.Tensor, exact: bool = True) -> tuple[int, float]:
+        """``(n_correct, loss_sum)`` of this head against int32 targets, reduced on the device
+        (``trainer.py:295-342``: accuracy of the argmax labels and the un-averaged ``log_loss`` terms)."""
+        self._set_exact(exact)
+        if feats.dtype != torch.float32 or feats.dim() != 2 or feats.shape[1] != self.dims[0] or not feats.is_contiguous():
+            raise ValueError(f"features must be contiguous CUDA float32 (N, {self.dims[0]}); got {tuple(feats.shape)}")
+        if y_idx.dtype != torch.int32 or y_idx.shape != (feats.shape[0],) or not y_idx.is_contiguous():
+            raise ValueError("targets must be contiguous CUDA int32 class indices, one per row")
+        hits, loss = C.c_int64(0), C.c_double(0.0)
+        with torch.cuda.device(feats.device):
+            _lib.check(_lib.load().mc_head_evaluate(self._h, feats.data_ptr(), y_idx.data_ptr(), feats.shape[0],
+                                                    C.byref(hits), C.byref(loss), _lib.stream_ptr()))
+        return int(hits.value), float(loss.value)
+
+
+def platt_fit_device(proba: torch.Tensor, y_idx: torch.Tensor, gtol: float = 1e-9, max_passes: int = 400):
+    """Per-class Platt parameters ``(a, b, loss, passes)`` from a CUDA float64 ``(n, K)`` probability matrix and
+    int32 targets -- every class's ``_sigmoid_calibration(proba[:, k], y == k)`` at once (``trainer.py:344-396``)."""
+    if proba.dtype != torch.float64 or proba.dim() != 2 or not proba.is_contiguous() or not proba.is_cuda:
+        raise ValueError("proba must be a contiguous CUDA float64 (n, K) matrix")
+    if y_idx.dtype != torch.int32 or y_idx.shape != (proba.shape[0],) or not y_idx.is_contiguous():
+        raise ValueError("targets must be contiguous CUDA int32 class indices, one per row")
+    n, k = proba.shape
+    a, b, loss = (np.empty(k, dtype=np.float64) for _ in range(3))
+    passes = C.c_int32(0)
+    with torch.cuda.device(proba.device):
+        _lib.check(_lib.load().mc_platt_fit(proba.data_ptr(), y_idx.data_ptr(), n, k, proba.device.index, float(gtol),
+                                            int(max_passes), a.ctypes.data, b.ctypes.data, loss.ctypes.data,
+                                            C.byref(passes), _lib.stream_ptr()))
+    return a, b, loss, int(passes.value)
+
 
 class Predictor:
     """A loaded classifier head: feature batch -> calibrated probabilities (on the GPU)."""

@@ -362,6 +362,24 @@ class TorchMLPClassifier:
         return self
 
     # -- inference -----------------------------------------------------------------------------------
+    def _ensure_head(self) -> DeviceHead:
+        """Uncalibrated device head over the current parameters (rebuilt after every training pass)."""
+        if not hasattr(self, "_h"):
+            raise RuntimeError("TorchMLPClassifier is not fitted. Call partial_fit or fit before predict/predict_proba.")
+        if self._head is None:
+            ws, bs = self._pull_params()
+            self._head = DeviceHead(ws, bs, None, None, device=self._dev_index)
+        return self._head
+
+    def evaluate_device(self, X_dev: torch.Tensor, y_idx_dev: torch.Tensor) -> tuple[int, float]:
+        """``(n_correct, sum of log-loss terms)`` on device-resident data: the two accumulators behind
+        ``_calc_acc_batched`` / ``_calc_acc_and_log_loss_batched`` (``trainer.py:295-342``), no ``(N, K)`` matrix."""
+        return self._ensure_head().evaluate_device(X_dev, y_idx_dev)
+
+    def predict_proba_device(self, X_dev: torch.Tensor) -> torch.Tensor:
+        """``predict_proba`` that stays on the device: CUDA float64 ``(n, K)``."""
+        return self._ensure_head().scores_device(X_dev, want_proba=True)["proba"]
+
     def _forward_probs(self, X) -> np.ndarray:
         if not hasattr(self, "_h"):
             raise RuntimeError("TorchMLPClassifier is not fitted. Call partial_fit or fit before predict/predict_proba.")
@@ -370,10 +388,7 @@ class TorchMLPClassifier:
             raise ValueError(f"X must be 2D, got shape {X_arr.shape}")
         if X_arr.shape[1] != self.n_features_in_:
             raise ValueError(f"X has {X_arr.shape[1]} features, expected {self.n_features_in_}")
-        if self._head is None:
-            ws, bs = self._pull_params()
-            self._head = DeviceHead(ws, bs, None, None, device=self._dev_index)
-        proba, _ = self._head.scores_host(np.ascontiguousarray(X_arr), want_proba=True, want_labels=False)
+        proba, _ = self._ensure_head().scores_host(np.ascontiguousarray(X_arr), want_proba=True, want_labels=False)
         row_sums = proba.sum(axis=1)
         max_drift = float(np.max(np.abs(row_sums - 1.0))) if proba.size else 0.0
         if max_drift > _EXPECTED_FP_DRIFT_TOL:

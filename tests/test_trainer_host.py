@@ -1,0 +1,100 @@
+"""Host-side logic of the trainer / export mirrors that needs no GPU: argument validation, the calibrated-model
+attribute surface, the portable TorchScript head and the export parity gate (checked against the oracle)."""
+import json
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from mermaid_classifier_b200 import synth
+from mermaid_classifier_b200.export import PortableHead, build_calibrated_head, export_artifact
+from mermaid_classifier_b200.inference import ParityError, extract_head_params
+from mermaid_classifier_b200.trainer import MermaidTrainer, SigmoidCalibrator
+from oracle import head as ohead
+
+
+def _stub_model(n_classes=12, input_dim=32, hidden=(24, 16), skew=0.0):
+    """A calibrated model with the CalibratedClassifierCV(prefit) attribute surface; predict_proba is the oracle's."""
+    w, bb, a, b, _ = synth.synth_head(input_dim=input_dim, hidden=hidden, n_classes=n_classes, seed=7)
+    classes = np.asarray([f"ba{i:02d}::gf{i:02d}" for i in range(n_classes)])
+    linears = [SimpleNamespace(weight=x, bias=y) for x, y in zip(w, bb)]
+    est = SimpleNamespace(classes_=classes, n_features_in_=input_dim, _module=SimpleNamespace(linears=linears))
+    inner = SimpleNamespace(estimator=est, calibrators=[SigmoidCalibrator(float(x), float(y)) for x, y in zip(a, b)])
+    model = SimpleNamespace(calibrated_classifiers_=[inner], classes_=classes,
+                            predict_proba=lambda X: ohead.calibrated_proba(X, w, bb, a, b) + skew)
+    return model, (w, bb, a, b)
+
+
+def test_trainer_rejects_bad_patience():
+    for bad in (0, -1):
+        with pytest.raises(ValueError, match="early_stopping_patience"):
+            MermaidTrainer(batch_size=100, early_stopping_patience=bad)
+    t = MermaidTrainer(batch_size=100, early_stopping_patience=None)
+    assert t._early_stop_info is None and t.serialize() == {"batch_size": 100}
+
+
+def test_sigmoid_calibrator_predict():
+    c = SigmoidCalibrator(-7.5, 2.0)
+    p = np.linspace(0, 1, 11)
+    np.testing.assert_allclose(c.predict(p), 1.0 / (1.0 + np.exp(-7.5 * p + 2.0)), rtol=1e-15)
+    assert c.predict(p).dtype == np.float64
+
+
+def test_portable_head_is_the_oracle_head_and_is_readable():
+    model, (w, bb, a, b) = _stub_model()
+    head = build_calibrated_head(model).eval()
+    x = np.random.default_rng(0).standard_normal((64, 32)).astype(np.float32)
+    with torch.no_grad():
+        got = head(torch.from_numpy(x)).numpy().astype(np.float64)
+    assert np.array_equal(got, ohead.calibrated_proba(x, w, bb, a, b))
+    frozen = torch.jit.freeze(torch.jit.script(head))
+    ws, bs, a2, b2 = extract_head_params(frozen)
+    assert all(torch.equal(p, q) for p, q in zip(ws, w)) and all(torch.equal(p, q) for p, q in zip(bs, bb))
+    assert torch.equal(a2, a) and torch.equal(b2, b)
+
+
+def test_build_calibrated_head_rejections():
+    model, _ = _stub_model()
+    model.calibrated_classifiers_ = model.calibrated_classifiers_ * 2
+    with pytest.raises(ValueError, match="exactly one"):
+        build_calibrated_head(model)
+    model, _ = _stub_model()
+    model.classes_ = model.classes_[::-1]
+    with pytest.raises(ValueError, match="classes_"):
+        build_calibrated_head(model)
+    model, _ = _stub_model()
+    model.calibrated_classifiers_[0].calibrators.pop()
+    with pytest.raises(ValueError, match="per-class calibrators"):
+        build_calibrated_head(model)
+    model, _ = _stub_model(n_classes=2)
+    with pytest.raises(ValueError, match="K > 2"):
+        build_calibrated_head(model)
+    with pytest.raises(ValueError):
+        PortableHead([], [], torch.zeros(3), torch.zeros(3))
+    with pytest.raises(ValueError):
+        PortableHead([torch.zeros(3, 4)], [torch.zeros(3)], torch.zeros(3, 1), torch.zeros(3, 1))
+
+
+def test_export_artifact_manifest_and_gate(tmp_path):
+    model, (w, bb, a, b) = _stub_model()
+    x = np.random.default_rng(1).standard_normal((32, 32)).astype(np.float32)
+    path, manifest, diff = export_artifact(model, tmp_path / "art", x, config={"patch_size": 224, "note": "t"})
+    assert path == tmp_path / "art" / "model.pt" and diff <= 1e-6
+    on_disk = json.loads((tmp_path / "art" / "model.json").read_text())
+    assert on_disk == manifest
+    assert manifest["schema_version"] == 1 and manifest["task"] == "pyspacer_mlp_classifier"
+    assert manifest["classes"] == model.classes_.tolist() and manifest["input_dim"] == 32
+    assert manifest["config"] == {"patch_size": 224, "note": "t"}
+    assert set(manifest["trained_with"]) >= {"torch", "sklearn", "pyspacer"}
+    graph = torch.jit.load(str(path), map_location="cpu")
+    with torch.no_grad():
+        out = graph(torch.from_numpy(x)).numpy().astype(np.float64)
+    assert np.array_equal(out, ohead.calibrated_proba(x, w, bb, a, b))
+    # default config, and the gate refusing a model that disagrees with its own frozen graph
+    _, manifest2, _ = export_artifact(model, tmp_path / "art2", x)
+    assert manifest2["config"] == {"patch_size": 224}
+    skewed, _ = _stub_model(skew=5e-6)
+    with pytest.raises(ParityError, match="Refusing to ship"):
+        export_artifact(skewed, tmp_path / "art3", x)
+    assert not (tmp_path / "art3" / "model.pt").exists()
