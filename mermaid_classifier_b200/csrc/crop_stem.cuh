@@ -167,9 +167,10 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const mc_image* __restrict
     }
     __syncthreads();
     if (tile + 1 < NT) gather(ox0 + TS);   // in flight during the convolution below
-    float acc[32];
+    // output channels in pairs: one packed FMA (FFMA2) per pair and tap, the weight pair a 64-bit constant operand
+    float2 acc[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int c = 0; c < 16; ++c) acc[c] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -177,8 +178,10 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const mc_image* __restrict
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci) {
           const float v = in_s[2 * ty + ky][(2 * tx + kx) * 3 + ci];
+          const float2 vv = make_float2(v, v);
+          const float* wt = P.w + ((ky * 3 + kx) * 3 + ci) * 32;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, P.w[((ky * 3 + kx) * 3 + ci) * 32 + c], acc[c]);
+          for (int c = 0; c < 16; ++c) acc[c] = __ffma2_rn(vv, make_float2(wt[2 * c], wt[2 * c + 1]), acc[c]);
         }
       }
     }
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const mc_image* __restrict
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
         const int c = q * VN + e;
-        v.v[e] = bn_silu<T>(acc[c], P.scale[c], P.bias[c]);
+        v.v[e] = bn_silu<T>((c & 1) ? acc[c >> 1].y : acc[c >> 1].x, P.scale[c], P.bias[c]);
       }
       v.store(o + q * VN);
     }

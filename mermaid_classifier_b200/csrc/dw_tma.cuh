@@ -410,11 +410,14 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
   const bool active = tid < n_cons;           // the last consumer warp may be partly idle
   const int cg = active ? tid % CGT : 0, sl = active ? tid / CGT : 0;
   const int c = cb0 + cg * CH;
-  float w[K * K][CH], sc[CH], bi[CH];
+  // CH == 2: the channel pair rides in 64-bit register pairs and every tap is ONE packed FMA (FFMA2, sm_100):
+  // the three-register scalar FFMA issues every other cycle per scheduler, which capped the 5x5 layers at ~45 % FMA-pipe
+  // utilisation with the memory system half idle.
+  static_assert(CH == 2, "dw_reg_kernel packs a channel pair per thread");
+  float2 w[K * K];
+  float sc[CH], bi[CH];
 #pragma unroll
-  for (int i = 0; i < K * K; ++i)
-#pragma unroll
-    for (int e = 0; e < CH; ++e) w[i][e] = a.w[(int64_t)i * C + c + e];
+  for (int i = 0; i < K * K; ++i) w[i] = make_float2(a.w[(int64_t)i * C + c], a.w[(int64_t)i * C + c + 1]);
 #pragma unroll
   for (int e = 0; e < CH; ++e) {
     sc[e] = a.scale[c + e];
@@ -428,13 +431,11 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
   int pbuf = 0;
   for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
     T* out_n = (T*)a.out + ((int64_t)n * HOUT * HOUT + ox0) * C + c;
-    float acc[NL][TW][CH];
+    float2 acc[NL][TW];
 #pragma unroll
     for (int l = 0; l < NL; ++l)
 #pragma unroll
-      for (int q = 0; q < TW; ++q)
-#pragma unroll
-        for (int e = 0; e < CH; ++e) acc[l][q][e] = 0.f;
+      for (int q = 0; q < TW; ++q) acc[l][q] = make_float2(0.f, 0.f);
     float psum[CH];
 #pragma unroll
     for (int e = 0; e < CH; ++e) psum[e] = 0.f;
@@ -445,9 +446,13 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
         if (t < nsteps) {
           ptx::mbar_wait(&full[s], ph);
           const uint32_t rowbase = ring_u32 + (uint32_t)s * (uint32_t)ROW_BYTES;
-          float v[NCOL][CH];
+          float2 v[NCOL];
 #pragma unroll
-          for (int j = 0; j < NCOL; ++j) dw_load_ch<T, CH>(rowbase + (uint32_t)j * col_pitch, v[j]);
+          for (int j = 0; j < NCOL; ++j) {
+            float t2[2];
+            dw_load_ch<T, CH>(rowbase + (uint32_t)j * col_pitch, t2);
+            v[j] = make_float2(t2[0], t2[1]);
+          }
           const int iy = iy0 + t;
           if (iy >= 0 && iy < HIN) {
 #pragma unroll
@@ -457,9 +462,7 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-                  for (int q = 0; q < TW; ++q)
-#pragma unroll
-                    for (int e = 0; e < CH; ++e) acc[slot][q][e] = fmaf(v[q * S + kx][e], w[ky * K + kx][e], acc[slot][q][e]);
+                  for (int q = 0; q < TW; ++q) acc[slot][q] = __ffma2_rn(v[q * S + kx], w[ky * K + kx], acc[slot][q]);
               }
             }
           }
@@ -478,19 +481,16 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
               for (int q = 0; q < TW; ++q) {
                 if (ox0 + q < HOUT) {
                   float y[CH];
-#pragma unroll
-                  for (int e = 0; e < CH; ++e) {
-                    y[e] = bn_silu<T>(acc[done][q][e], sc[e], bi[e]);
-                    psum[e] += y[e];
-                  }
+                  y[0] = bn_silu<T>(acc[done][q].x, sc[0], bi[0]);
+                  y[1] = bn_silu<T>(acc[done][q].y, sc[1], bi[1]);
+                  psum[0] += y[0];
+                  psum[1] += y[1];
                   dw_store_ch<T, CH>(orow + q * C, y);
                 }
               }
             }
 #pragma unroll
-            for (int q = 0; q < TW; ++q)
-#pragma unroll
-              for (int e = 0; e < CH; ++e) acc[done][q][e] = 0.f;
+            for (int q = 0; q < TW; ++q) acc[done][q] = make_float2(0.f, 0.f);
           }
         }
       }
