@@ -20,19 +20,6 @@
 
 using namespace mc;
 
-#ifdef MC_PAD
-// placement experiment: a dummy kernel of MC_PAD FMAs shifts the code addresses of the kernels linked after it
-__global__ void mc_pad_kernel(float* p) {
-  float x = p[0];
-#pragma unroll
-  for (int i = 0; i < MC_PAD; ++i) x = fmaf(x, 1.0001f, 0.5f + (float)i);
-  p[0] = x;
-}
-void* mc_pad_ref = (void*)mc_pad_kernel;
-#endif
-
-
-
 namespace {
 
 struct DeviceGuard {
