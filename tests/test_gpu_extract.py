@@ -198,3 +198,46 @@ def test_features_bf16_mode(ext16, backbone_sd):
     cs = cosines(got, want)
     assert cs.min() >= BF16_MIN_COS, cs.min()
     assert np.abs(got - want).max() <= BF16_MAX_ABS
+
+
+def test_full_size_sub_batch_properties(backbone_sd):
+    """BASELINE config C2 at its real shapes -- 4000x3000 images, 100 sorted points each (30 % in the reflect band,
+    the four corners in image 0), one 1 000-patch sub-batch -- checked through size-independent properties, plus the
+    CPU oracle on a sample:
+      * a patch's features do not depend on what else is in the sub-batch or where it sits in it (bit-identical when
+        the same points run alone, reversed, or duplicated);
+      * the sample (corners, edge and interior points) meets the fp32 parity bound against the oracle."""
+    H, W, n_img, n_pts = 3000, 4000, 10, 100
+    images = [synth_image_device(synth.DEFAULT_SEED, i, H, W) for i in range(n_img)]
+    per_img = [synth.synth_points(synth.DEFAULT_SEED, i, H, W, n_pts, corners=(i == 0)) for i in range(n_img)]
+    points = np.array([(i, r, c) for i, rc in enumerate(per_img) for r, c in rc], dtype=np.int32)
+    assert points.shape[0] == 1000
+    big = EfficientNetExtractor(state_dict=backbone_sd, mode="fp32", max_batch=1000)
+    try:
+        full = big.extract_device(images, points).cpu().numpy()
+        assert np.isfinite(full).all() and full.shape == (1000, 1280)
+        # same points, reversed order, in one sub-batch
+        rev = big.extract_device(images, points[::-1].copy()).cpu().numpy()
+        assert np.array_equal(rev[::-1], full)
+        # image 3 alone (100 patches) and a duplicated point list
+        sel = points[points[:, 0] == 3]
+        alone = big.extract_device(images, sel).cpu().numpy()
+        assert np.array_equal(alone, full[300:400])
+        dup = big.extract_device(images, np.concatenate([sel[:5], sel[:5]])).cpu().numpy()
+        assert np.array_equal(dup[:5], dup[5:]) and np.array_equal(dup[:5], full[300:305])
+    finally:
+        big.close()
+    # oracle on a sample of image 0: the four corners + two edge-band + two interior points
+    im0 = synth.synth_image(synth.DEFAULT_SEED, 0, H, W)
+    assert np.array_equal(images[0].cpu().numpy(), im0)
+    pts0 = per_img[0]
+    corners = [(0, 0), (0, W - 1), (H - 1, 0), (H - 1, W - 1)]
+    edge = [p for p in pts0 if p not in corners and (min(p[0], H - 1 - p[0]) < 112 or min(p[1], W - 1 - p[1]) < 112)][:2]
+    inner = [p for p in pts0 if 112 <= p[0] < H - 112 and 112 <= p[1] < W - 112][:2]
+    sample = corners + edge + inner
+    idx = [pts0.index(p) for p in sample]
+    want = oeff.extract_features(
+        backbone_sd, torch.from_numpy(ocrop.normalize_patches(ocrop.crop_patches(im0, sample)))).numpy()
+    got = full[idx]
+    assert np.abs(got - want).max() <= FP32_MAX_ABS
+    assert cosines(got, want).min() >= FP32_MIN_COS

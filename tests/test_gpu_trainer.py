@@ -205,3 +205,29 @@ def test_export_round_trip_of_a_gpu_trained_model(g, tmp_path):
     assert np.abs(got - want).max() <= 1e-6
     assert np.abs(got - clf_cal.predict_proba(g["Xv"])).max() <= 1e-6
     assert (pred.predict(g["Xv"]) == clf_cal.predict(g["Xv"])).all()
+
+
+def test_full_size_evaluation_is_additive():
+    """Production head (1280 -> 500 -> 300 -> 100 -> 500) over 200 000 rows: hits add up exactly and the log-loss sum
+    to fp64 rounding when the rows are evaluated in two ragged pieces; per-row terms agree with the oracle on a
+    subsample."""
+    from mermaid_classifier_b200 import synth
+
+    w, b, _, _, _ = synth.synth_head(input_dim=1280, hidden=(500, 300, 100), n_classes=500, seed=0)
+    head = DeviceHead([x.numpy() for x in w], [x.numpy() for x in b], None, None)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    n = 200_000
+    X = torch.randn(n, 1280, device="cuda", generator=gen) * 0.25
+    y = torch.randint(0, 500, (n,), device="cuda", generator=gen, dtype=torch.int32)
+    hits, loss = head.evaluate_device(X, y)
+    cut = 77_777
+    h1, l1 = head.evaluate_device(X[:cut].contiguous(), y[:cut].contiguous())
+    h2, l2 = head.evaluate_device(X[cut:].contiguous(), y[cut:].contiguous())
+    assert h1 + h2 == hits
+    assert l1 + l2 == pytest.approx(loss, rel=1e-12)
+    sub = slice(1000, 1512)
+    p = ohead.softmax_proba(X[sub].cpu().numpy(), w, b)
+    ysub = y[sub].cpu().numpy()
+    hs, ls = head.evaluate_device(X[sub].contiguous(), y[sub].contiguous())
+    assert ls == pytest.approx(float(otr.log_loss_terms(ysub, p).sum()), rel=1e-5)
+    assert abs(hs - int((p.argmax(1) == ysub).sum())) <= 1
