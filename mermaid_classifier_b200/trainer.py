@@ -227,6 +227,8 @@ class MermaidTrainer:
         hidden_layer_sizes: Sequence[int] = (500, 300, 100),
         learning_rate_init: float = 1e-4,
         device: int | None = None,
+        data_parallel: Any = None,
+        dp_mode: str = "parity",
     ):
         if early_stopping_patience is not None and early_stopping_patience < 1:
             raise ValueError(f"early_stopping_patience must be >= 1 or None, got {early_stopping_patience!r}")
@@ -237,14 +239,63 @@ class MermaidTrainer:
         self.hidden_layer_sizes = tuple(hidden_layer_sizes)
         self.learning_rate_init = learning_rate_init
         self.device = device
+        # One process per GPU (torch_classifier.DataParallel).  "parity": every rank holds the SAME splits, each
+        # 200-row mini-batch is divided over the ranks and the gradient all-reduced -> the single-GPU trajectory;
+        # evaluation and calibration run replicated.  "throughput": every rank holds ITS OWN shard of each split;
+        # evaluation counts are summed and the reference-split probabilities gathered over the ranks, so all ranks
+        # report the same metrics, take the same early-stopping decisions and fit the same calibrators.
+        if dp_mode not in ("parity", "throughput"):
+            raise ValueError("dp_mode must be 'parity' or 'throughput'")
+        self.data_parallel = data_parallel
+        self.dp_mode = dp_mode
         self._early_stop_info: dict[str, Any] | None = None
+
+    @property
+    def _sharded(self) -> bool:
+        dp = self.data_parallel
+        return dp is not None and dp.world > 1 and self.dp_mode == "throughput"
+
+    def _sum_over_ranks(self, hits: int, loss: float, n: int, device: int) -> tuple[int, float, int]:
+        if not self._sharded:
+            return hits, loss, n
+        import torch.distributed as dist
+
+        t = torch.tensor([float(hits), loss, float(n)], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.data_parallel.group)
+        h, l, m = t.tolist()
+        return int(round(h)), l, int(round(m))
+
+    def _gather_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """Concatenate every rank's rows (ragged first dimension) in rank order, on every rank."""
+        if not self._sharded:
+            return t
+        import torch.distributed as dist
+
+        group, world = self.data_parallel.group, self.data_parallel.world
+        sizes = torch.zeros(world, dtype=torch.int64, device=t.device)
+        sizes[self.data_parallel.rank] = t.shape[0]
+        dist.all_reduce(sizes, op=dist.ReduceOp.SUM, group=group)
+        cap = int(sizes.max().item())
+        padded = torch.zeros((cap, *t.shape[1:]), dtype=t.dtype, device=t.device)
+        padded[: t.shape[0]] = t
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded, group=group)
+        return torch.cat([p[: int(sizes[r].item())] for r, p in enumerate(parts)]).contiguous()
 
     def __call__(self, labels: Any, nbr_epochs: int, pc_models: Sequence[Any] = (), **_kwargs: Any):
         classes_list = list(labels.ref.classes_set)
+        if self._sharded:  # a shard may miss classes: every rank trains on the union
+            import torch.distributed as dist
+
+            sets: list[Any] = [None] * self.data_parallel.world
+            dist.all_gather_object(sets, sorted(classes_list), group=self.data_parallel.group)
+            classes_list = sorted(set().union(*map(set, sets)))
         clf = TorchMLPClassifier(hidden_layer_sizes=self.hidden_layer_sizes, learning_rate_init=self.learning_rate_init,
                                  class_weight=self.class_weight, random_state=0)
         if self.device is not None:
             clf.set_device(self.device)
+        if self.data_parallel is not None:
+            clf.enable_data_parallel(self.data_parallel, self.dp_mode)
         ref_accs: list[float] = []
         t0 = time.time()
         best_val_loss = float("inf")
@@ -310,6 +361,16 @@ class MermaidTrainer:
 
     def _train_epoch(self, clf: TorchMLPClassifier, train: Any, classes_list: list[Any], epoch: int) -> None:
         """``trainer.py:138-145``: one ``partial_fit`` per chunk, chunks drawn with ``random_seed=epoch``."""
+        if self._sharded:
+            # every partial_fit pass all-reduces per Adam step: ranks must make the same number of passes
+            import torch.distributed as dist
+
+            n_chunks = -(-train.label_count // self.batch_size)
+            t = torch.tensor([n_chunks, -n_chunks], dtype=torch.int64, device=f"cuda:{self.data_parallel.device}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.data_parallel.group)
+            if int(t[0]) != -int(t[1]):
+                raise ValueError(f"throughput mode needs the same number of training chunks on every rank "
+                                 f"(this rank: {n_chunks}, max {int(t[0])}, min {-int(t[1])}); use equal-size shards")
         if hasattr(train, "device_batches"):
             clf.init_for(int(train.X.shape[1]), classes_list)
             for xd, yd in train.device_batches(self.batch_size, clf.classes_, random_seed=epoch):
@@ -324,6 +385,7 @@ class MermaidTrainer:
             h, _ = clf.evaluate_device(xd.contiguous(), yd)
             hits += h
             n += int(yd.shape[0])
+        hits, _, n = self._sum_over_ranks(hits, 0.0, n, clf._dev_index)
         return hits / n
 
     def _calc_acc_and_log_loss_batched(self, clf: TorchMLPClassifier, labels: Any, classes_list: list[Any]) -> tuple[float, float]:
@@ -336,6 +398,7 @@ class MermaidTrainer:
             hits += h
             loss += l
             n += int(yd.shape[0])
+        hits, loss, n = self._sum_over_ranks(hits, loss, n, clf._dev_index)
         return hits / n, loss / n
 
     def _calibrate_in_batches(self, clf: TorchMLPClassifier, ref_labels: Any) -> CalibratedClassifier:
@@ -348,6 +411,7 @@ class MermaidTrainer:
             ys.append(yd)
         proba = torch.cat(probs) if len(probs) > 1 else probs[0]
         y = (torch.cat(ys) if len(ys) > 1 else ys[0]).contiguous()
+        proba, y = self._gather_rows(proba.contiguous()), self._gather_rows(y)
         a, b, _, passes = platt_fit_device(proba.contiguous(), y)
         logger.debug(f"Platt calibration: {k} classes, {proba.shape[0]} rows, {passes} matrix passes")
         return CalibratedClassifier(clf, a, b)
