@@ -132,6 +132,41 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
         : "memory");
   }
 }
+// Convergent-warp forms: the WHOLE warp executes these and one elected lane issues.  Under a divergent
+// `if (lane == 0)` ptxas cannot prove the uniform-register operands warp-uniform and wraps every tcgen05 instruction in an
+// elect / broadcast / branch waterfall (6 extra instructions each, all on the slow uniform datapath): measured ~150
+// cycles of issue work per MMA, more than a 128 x 128 x 8 TF32 MMA takes to execute.
+// a_lo / b_lo: low descriptor words ((smem address >> 4) | LBO << 16); hi: the constant high word.
+template <bool TF32>
+__device__ __forceinline__ void mma_ss_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p, el;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "elect.sync _|el, 0xffffffff;\n\t"
+        "@el tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, el;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "elect.sync _|el, 0xffffffff;\n\t"
+        "@el tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred el;\n\telect.sync _|el, 0xffffffff;\n\t"
+      "@el tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
 // mbarrier arrives when every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -392,9 +427,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == WARP_MMA) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
+    // All 32 lanes walk the loop convergently; elect.sync inside each tcgen05 asm picks the issuing lane (always the same
+    // one for the full mask, so tcgen05.commit tracks the MMAs it follows).
+    {
       const uint32_t idesc = (1u << 4) | (Cfg::FMT << 7) | (Cfg::FMT << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
+      constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);   // SBO = 1024 >> 4, version 1, SWIZZLE_128B
+      constexpr uint32_t DESC_LBO = 1u << 16;
       int s = 0;
       uint32_t ph = 0;
       int li = 0;
@@ -404,6 +443,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         ptx::mbar_wait(wbar, 0);
         ptx::tc_fence_after();
       }
+      const uint32_t stage_lo = ptx::smem_u32(stage_base) >> 4, w_lo_base = ptx::smem_u32(w_base) >> 4;
+      const uint32_t stage_step = (uint32_t)STAGE_BYTES >> 4, w_step = (uint32_t)W_BYTES >> 4;
       for (int it = blockIdx.x; it < items; it += gridDim.x, ++li) {
         const int as = li % NAS;
         const uint32_t use = (uint32_t)(li / NAS);
@@ -414,36 +455,39 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           w_full += ptx::mbar_wait_timed(transform ? &ready[s] : &full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+          __syncwarp();
+          // low descriptor words: all operand tiles live below 256 KB, so (address >> 4) never leaves the 14-bit field
+          const uint32_t a_lo = (stage_lo + (uint32_t)s * stage_step) | DESC_LBO;
           // W tile of (n-block, k-chunk): resident region, or behind the A operands of this stage
-          const uint32_t w_addr = w_res ? ptx::smem_u32(w_base + (size_t)((nb_i * p.k_chunks + kc) * Cfg::NW) * W_BYTES)
-                                        : a_addr + Cfg::NA * Cfg::A_BYTES;
+          const uint32_t w_lo = w_res ? ((w_lo_base + (uint32_t)((nb_i * p.k_chunks + kc) * Cfg::NW) * w_step) | DESC_LBO)
+                                      : a_lo + (uint32_t)((Cfg::NA * Cfg::A_BYTES) >> 4);
           const int krem = p.K - kc * Cfg::KC;
-          const int ksteps = (min(krem, Cfg::KC) + Cfg::UK - 1) / Cfg::UK;
-          for (int ks = 0; ks < ((p.exp_flags & 16) ? 0 : ksteps); ++ks) {
-            const uint32_t acc = (kc | ks) != 0;
-            const uint32_t koff = (uint32_t)ks * 32u;  // UK elements = 32 bytes
-            if (Cfg::TF32) {
-              const uint64_t ahi = umma_desc_sw128(a_addr + koff);
-              const uint64_t alo = umma_desc_sw128(a_addr + Cfg::A_BYTES + koff);
-              const uint64_t whi = umma_desc_sw128(w_addr + koff);
-              const uint64_t wlo = umma_desc_sw128(w_addr + W_BYTES + koff);
-              ptx::mma_ss<true>(d_tmem, alo, whi, idesc, acc);
-              ptx::mma_ss<true>(d_tmem, ahi, wlo, idesc, 1u);
-              ptx::mma_ss<true>(d_tmem, ahi, whi, idesc, 1u);
-            } else {
-              ptx::mma_ss<false>(d_tmem, umma_desc_sw128(a_addr + koff), umma_desc_sw128(w_addr + koff), idesc, acc);
+          const int ksteps = (p.exp_flags & 16) ? 0 : (min(krem, Cfg::KC) + Cfg::UK - 1) / Cfg::UK;
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KC / Cfg::UK; ++ks) {
+            if (ks < ksteps) {
+              const uint32_t acc = (kc | ks) != 0;
+              const uint32_t ko = (uint32_t)ks * 2u;   // UK elements = 32 bytes = 2 descriptor units
+              if (Cfg::TF32) {
+                const uint32_t ahi = a_lo + ko, alo = a_lo + (uint32_t)(Cfg::A_BYTES >> 4) + ko;
+                const uint32_t whi = w_lo + ko, wlo = w_lo + w_step + ko;
+                ptx::mma_ss_elect<true>(d_tmem, alo, whi, DESC_HI, idesc, acc);
+                ptx::mma_ss_elect<true>(d_tmem, ahi, wlo, DESC_HI, idesc, 1u);
+                ptx::mma_ss_elect<true>(d_tmem, ahi, whi, DESC_HI, idesc, 1u);
+              } else {
+                ptx::mma_ss_elect<false>(d_tmem, a_lo + ko, w_lo + ko, DESC_HI, idesc, acc);
+              }
             }
           }
-          ptx::mma_commit(&empty[s]);
+          ptx::mma_commit_elect(&empty[s]);
           if (++s == S) {
             s = 0;
             ph ^= 1;
           }
         }
-        ptx::mma_commit(&tfull[as]);
+        ptx::mma_commit_elect(&tfull[as]);
       }
-      if (MC_TC_TIMING && p.dbg && blockIdx.x == 0) {
+      if (MC_TC_TIMING && p.dbg && blockIdx.x == 0 && lane == 0) {
         p.dbg[2] = w_tempty;
         p.dbg[3] = w_full;
         p.dbg[4] = ptx::tc_clock() - t_begin;
