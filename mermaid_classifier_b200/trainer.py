@@ -255,12 +255,14 @@ class MermaidTrainer:
         dp = self.data_parallel
         return dp is not None and dp.world > 1 and self.dp_mode == "throughput"
 
-    def _sum_over_ranks(self, hits: int, loss: float, n: int, device: int) -> tuple[int, float, int]:
+    def _sum_over_ranks(self, hits: int, loss: float, n: int, device: Any) -> tuple[int, float, int]:
+        """``device``: CUDA index of the estimator (NCCL groups), or a ``torch.device`` (the gloo tests pass "cpu")."""
         if not self._sharded:
             return hits, loss, n
         import torch.distributed as dist
 
-        t = torch.tensor([float(hits), loss, float(n)], dtype=torch.float64, device=f"cuda:{device}")
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        t = torch.tensor([float(hits), loss, float(n)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.data_parallel.group)
         h, l, m = t.tolist()
         return int(round(h)), l, int(round(m))

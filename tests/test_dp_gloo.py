@@ -124,3 +124,58 @@ def test_image_sharding_covers_all_images_once():
     for world in (1, 2, 4, 8):
         cover = sorted(i for r in range(world) for i in images_for_rank(100, r, world))
         assert cover == list(range(100))
+
+
+# ---- trainer-level reductions of the throughput (sharded) mode ---------------------------------------------------
+class _Group:
+    """What trainer.MermaidTrainer reads from torch_classifier.DataParallel (which itself needs NCCL + a GPU)."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world, self.group, self.device = rank, world, None, "cpu"
+
+
+def _trainer_rank(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mermaid_classifier_b200.trainer import MermaidTrainer
+
+    tr = MermaidTrainer(batch_size=100, data_parallel=_Group(rank, world), dp_mode="throughput")
+    assert tr._sharded
+    # evaluation counts: rank r saw (10 + r) hits, loss sum 1.5 * (r + 1), 100 + r rows
+    hits, loss, n = tr._sum_over_ranks(10 + rank, 1.5 * (rank + 1), 100 + rank, "cpu")
+    # ragged row gather in rank order (what calibration feeds to the Platt fit)
+    rows = torch.arange((3 + 2 * rank) * 4, dtype=torch.float64).reshape(3 + 2 * rank, 4) + 100.0 * rank
+    gathered = tr._gather_rows(rows)
+    y = tr._gather_rows(torch.full((3 + 2 * rank,), rank, dtype=torch.int32))
+    # parity mode and single-process trainers leave everything alone
+    plain = MermaidTrainer(batch_size=100, data_parallel=_Group(rank, world), dp_mode="parity")
+    untouched = plain._sum_over_ranks(7, 0.25, 9, "cpu") == (7, 0.25, 9) and plain._gather_rows(rows) is rows
+    if rank == 0:
+        out.put((hits, loss, n, gathered.numpy(), y.numpy(), untouched))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trainer_sharded_reductions_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_trainer_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    hits, loss, n, gathered, y, untouched = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (hits, loss, n) == (21, 4.5, 201) and untouched
+    want = np.concatenate([np.arange(12, dtype=np.float64).reshape(3, 4), np.arange(20, dtype=np.float64).reshape(5, 4) + 100.0])
+    assert np.array_equal(gathered, want)
+    assert y.tolist() == [0, 0, 0, 1, 1, 1, 1, 1]
+
+
+def test_trainer_rejects_unknown_dp_mode():
+    from mermaid_classifier_b200.trainer import MermaidTrainer
+
+    with pytest.raises(ValueError, match="dp_mode"):
+        MermaidTrainer(batch_size=10, dp_mode="fast")
