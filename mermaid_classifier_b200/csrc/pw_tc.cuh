@@ -343,7 +343,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr int ntw = GATED ? 8 : 4;
   constexpr int n_groups = (TC_THREADS / 32 - 2 - ntw) / 4;   // 4 ungated, 2 gated
   constexpr int WARP_MMA = TC_THREADS / 32 - 2, WARP_TMA = TC_THREADS / 32 - 1;
-  constexpr int NAS = n_groups;   // accumulator stages of 128 TMEM columns each (BN <= 128), one per epilogue group
+  // Accumulator stages of 128 TMEM columns each (BN <= 128): the four 128-column blocks are shared out evenly, so a group of
+  // the gated kernel (2 groups) owns TWO stages and the MMAs of its next item overlap the epilogue of the current one; the
+  // ungated kernel (4 groups) has one stage per group.  Item li -> group li % n_groups, that group's (li / n_groups)-th item
+  // -> stage group + n_groups * (j % ACC_DEPTH), use j / ACC_DEPTH.  A stage is only ever waited on by its own group, which
+  // sees every one of its phases (a parity wait is only meaningful for the current or the immediately preceding phase).
+  constexpr int NAS = 4;
+  constexpr int ACC_DEPTH = NAS / n_groups;
   constexpr int acc_cols = 128;
   constexpr bool transform = Cfg::TF32 || GATED;
   // 32-bit work-item arithmetic throughout: a 64-bit divide by a run-time value is a ~100-instruction
@@ -446,8 +452,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t stage_lo = ptx::smem_u32(stage_base) >> 4, w_lo_base = ptx::smem_u32(w_base) >> 4;
       const uint32_t stage_step = (uint32_t)STAGE_BYTES >> 4, w_step = (uint32_t)W_BYTES >> 4;
       for (int it = blockIdx.x; it < items; it += gridDim.x, ++li) {
-        const int as = li % NAS;
-        const uint32_t use = (uint32_t)(li / NAS);
+        const int gj = li / n_groups;                                           // index among its group's items
+        const int as = li % n_groups + n_groups * (gj % ACC_DEPTH);
+        const uint32_t use = (uint32_t)(gj / ACC_DEPTH);
         const int nb_i = (int)((uint32_t)it - ((uint32_t)it / nblk) * nblk);   // n-block of this item
         w_tempty += ptx::mbar_wait_timed(&tempty[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
@@ -636,11 +643,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     long long w_tfull = 0, t_work = 0;
     const long long t_begin = ptx::tc_clock();
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++li) {
-      // A group follows EVERY phase of the accumulator stage it serves (a parity wait is only
-      // meaningful for the current or the immediately preceding phase) but drains only its own items.
-      const int as = li % NAS;
-      if (as != eg) continue;                      // NAS == n_groups: stage `as` belongs to group `as`
-      const uint32_t use = (uint32_t)(li / NAS);
+      if (li % n_groups != eg) continue;           // not this group's item
+      const int gj = li / n_groups;
+      const int as = eg + n_groups * (gj % ACC_DEPTH);
+      const uint32_t use = (uint32_t)(gj / ACC_DEPTH);
       const uint32_t mt = (uint32_t)it / nblk;
       const int n0 = (int)((uint32_t)it - mt * nblk) * p.BN;
       w_tfull += ptx::mbar_wait_timed(&tfull[as], use & 1);
