@@ -28,7 +28,6 @@ from . import _lib, weights as _weights
 from .spacer_compat import (
     ExtractFeaturesReturnMsg,
     ImageFeatures,
-    check_extract_inputs,
     image_features_from_array,
     storage_factory,
 )

@@ -15,7 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 from pathlib import Path
-from typing import Any, Sequence
+from typing import Any
 
 import numpy as np
 import torch

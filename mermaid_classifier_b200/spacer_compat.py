@@ -17,7 +17,7 @@ from __future__ import annotations
 import io
 import json
 import time
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from pathlib import Path
 from typing import Any
 

@@ -1,7 +1,6 @@
 """Cross-check the EfficientNet-B0 oracle against an independent construction of the same
 topology: torchvision's ``efficientnet_b0`` with stride-2 convs re-padded TF-"SAME"
 (asymmetric) and every BatchNorm at eps=1e-3, loaded through a pyspacer->torchvision key map."""
-import numpy as np
 import pytest
 import torch
 

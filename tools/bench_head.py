@@ -5,7 +5,7 @@ head (500 classes) on one B200, labels on the device; a CPU-oracle subsample che
 """
 import argparse, json, sys, time
 from pathlib import Path
-import numpy as np, torch
+import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from mermaid_classifier_b200 import synth
 from mermaid_classifier_b200.inference import DeviceHead

@@ -1,5 +1,5 @@
 """Condense gpurun_out/ ncu captures into the tracked summaries under profiles/ (round tag as argv[1])."""
-import csv, io, json, subprocess, sys, collections
+import csv, json, sys, collections
 from pathlib import Path
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 mode = sys.argv[2] if len(sys.argv) > 2 else "fp32"
