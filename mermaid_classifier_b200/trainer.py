@@ -229,6 +229,7 @@ class MermaidTrainer:
         device: int | None = None,
         data_parallel: Any = None,
         dp_mode: str = "parity",
+        clf_factory: Callable[..., Any] | None = None,
     ):
         if early_stopping_patience is not None and early_stopping_patience < 1:
             raise ValueError(f"early_stopping_patience must be >= 1 or None, got {early_stopping_patience!r}")
@@ -248,6 +249,7 @@ class MermaidTrainer:
             raise ValueError("dp_mode must be 'parity' or 'throughput'")
         self.data_parallel = data_parallel
         self.dp_mode = dp_mode
+        self.clf_factory = clf_factory   # estimator class; default: the GPU TorchMLPClassifier
         self._early_stop_info: dict[str, Any] | None = None
 
     @property
@@ -292,8 +294,9 @@ class MermaidTrainer:
             sets: list[Any] = [None] * self.data_parallel.world
             dist.all_gather_object(sets, sorted(classes_list), group=self.data_parallel.group)
             classes_list = sorted(set().union(*map(set, sets)))
-        clf = TorchMLPClassifier(hidden_layer_sizes=self.hidden_layer_sizes, learning_rate_init=self.learning_rate_init,
-                                 class_weight=self.class_weight, random_state=0)
+        clf = (self.clf_factory or TorchMLPClassifier)(
+            hidden_layer_sizes=self.hidden_layer_sizes, learning_rate_init=self.learning_rate_init,
+            class_weight=self.class_weight, random_state=0)
         if self.device is not None:
             clf.set_device(self.device)
         if self.data_parallel is not None:

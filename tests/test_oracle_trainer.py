@@ -88,6 +88,15 @@ def test_early_stopping_walk():
     # disabled: nothing tracked
     r = walk([1.0, 2.0, 3.0], 3, None)
     assert (r["enabled"], r["final_epoch"], r["best_val_epoch"], r["best_val_loss"], r["restored_epoch"]) == (False, 3, None, None, 3)
+    # the reference's own scripted cases (tests/pyspacer/test_trainer.py:289-359)
+    r = walk([1.0, 0.9, 0.8, 0.7, 0.6], 5, 2)
+    assert (r["stop_reason"], r["final_epoch"], r["best_val_epoch"], r["best_val_loss"]) == ("budget_exhausted", 5, 5, 0.6)
+    r = walk([1.0, 0.9, 0.8, 0.85, 0.9, 1.0, 1.1], 10, 2)
+    assert (r["stop_reason"], r["final_epoch"], r["best_val_epoch"], r["best_val_loss"]) == ("early_stopping", 5, 3, 0.8)
+    r = walk([1.0, 0.5, 0.6], 10, 1)
+    assert (r["stop_reason"], r["final_epoch"], r["best_val_epoch"]) == ("early_stopping", 3, 2)
+    r = walk([1.0, 0.9, 0.95, 0.96], 10, 2)
+    assert (r["stop_reason"], r["final_epoch"], r["best_val_epoch"]) == ("early_stopping", 4, 2)
     # a tie is not an improvement (strict <)
     r = walk([1.0, 1.0, 1.0], 3, 2)
     assert (r["stop_reason"], r["final_epoch"], r["best_val_epoch"]) == ("early_stopping", 3, 1)

@@ -98,3 +98,108 @@ def test_export_artifact_manifest_and_gate(tmp_path):
     with pytest.raises(ParityError, match="Refusing to ship"):
         export_artifact(skewed, tmp_path / "art3", x)
     assert not (tmp_path / "art3" / "model.pt").exists()
+
+
+# ---- the reference's own early-stopping cases (tests/pyspacer/test_trainer.py:171-359), scripted the same way ----------
+class _FakeClf:
+    """Stands in for the GPU estimator: the loop bookkeeping under test never looks inside it."""
+
+    def __init__(self, **_kw):
+        self.loss_curve_ = []
+        self.classes_ = np.asarray(["c0", "c1", "c2"])
+        self.fits = 0
+
+    def partial_fit(self, x, y, classes=None):
+        self.fits += 1
+        self.loss_curve_.append(1.0 / self.fits)
+        return self
+
+    def predict_proba(self, x):
+        return np.full((len(x), 3), 1.0 / 3.0)
+
+
+def _mock_labels(seed=0):
+    rng = np.random.RandomState(seed)
+    classes = ["c0", "c1", "c2"]
+
+    def split(n):
+        X = rng.randn(n, 16).astype(np.float32)
+        y = list(rng.choice(classes, size=n))
+
+        def gen(batch_size=10, random_seed=None):
+            for i in range(0, n, batch_size):
+                yield [X[j] for j in range(i, min(i + batch_size, n))], list(y[i:i + batch_size])
+
+        return SimpleNamespace(classes_set=set(classes), label_count=n, load_data_in_batches=gen)
+
+    return SimpleNamespace(train=split(30), ref=split(15), val=split(15))
+
+
+def _scripted_run(schedule, patience, n_epochs):
+    remaining = list(schedule)
+    snapshots = []
+
+    class Scripted(MermaidTrainer):
+        def _calc_acc_batched(self, clf, labels):
+            return 0.25
+
+        def _calc_acc_and_log_loss_batched(self, clf, labels, classes_list):
+            assert remaining, "val_loss schedule exhausted; trainer ran for more epochs than expected"
+            return 0.5, float(remaining.pop(0))
+
+        def _calibrate_in_batches(self, clf, ref_labels):
+            snapshots.append(clf.fits)   # how many partial_fit calls the estimator handed to calibration had seen
+            return clf
+
+    captured = []
+    trainer = Scripted(batch_size=10, on_epoch_end=lambda m: captured.append(dict(m)), early_stopping_patience=patience,
+                       clf_factory=_FakeClf)
+    model, val_results, msg = trainer(_mock_labels(), n_epochs, [])
+    return trainer, captured, snapshots[0], msg
+
+
+def test_reference_case_no_patience_runs_full_budget():
+    trainer, captured, fits, msg = _scripted_run([1.0, 0.9, 0.8, 0.7, 0.6], None, 5)
+    assert len(captured) == 5 and len(msg.ref_accs) == 5
+    assert trainer._early_stop_info == {"enabled": False, "patience": None, "stop_reason": "budget_exhausted", "final_epoch": 5,
+                                        "best_val_epoch": None, "best_val_loss": None}
+    assert fits == 15   # 3 chunks x 5 epochs: the last-epoch estimator is calibrated
+
+
+def test_reference_case_monotone_down_no_stop():
+    trainer, captured, fits, _ = _scripted_run([1.0, 0.9, 0.8, 0.7, 0.6], 2, 5)
+    info = trainer._early_stop_info
+    assert len(captured) == 5 and info["enabled"] and info["stop_reason"] == "budget_exhausted"
+    assert info["final_epoch"] == 5 and info["best_val_epoch"] == 5 and info["best_val_loss"] == pytest.approx(0.6)
+    assert fits == 15
+
+
+def test_reference_case_v_shape_triggers_after_patience():
+    trainer, captured, fits, _ = _scripted_run([1.0, 0.9, 0.8, 0.85, 0.9, 1.0, 1.1], 2, 10)
+    info = trainer._early_stop_info
+    assert info["enabled"] and info["stop_reason"] == "early_stopping"
+    assert info["final_epoch"] == 5 and info["best_val_epoch"] == 3 and info["best_val_loss"] == pytest.approx(0.8)
+    assert len(captured) == 5
+    assert captured[-1]["early_stopped"] is True and captured[-1]["final_epoch"] == 5 and captured[-1]["best_val_epoch"] == 3
+    assert fits == 9    # the snapshot taken after epoch 3 (3 chunks x 3 epochs) is what gets calibrated, not the epoch-5 state
+
+
+def test_reference_case_patience_one_immediate_stop():
+    trainer, _, fits, _ = _scripted_run([1.0, 0.5, 0.6], 1, 10)
+    info = trainer._early_stop_info
+    assert (info["stop_reason"], info["final_epoch"], info["best_val_epoch"]) == ("early_stopping", 3, 2)
+    assert fits == 6
+
+
+def test_reference_case_summary_only_on_final_epoch():
+    _, captured, _, _ = _scripted_run([1.0, 0.9, 0.95, 0.96], 2, 10)
+    for cb in captured[:-1]:
+        assert "early_stopped" not in cb and "final_epoch" not in cb
+        assert set(cb) == {"epoch", "ref_accuracy", "val_accuracy", "val_loss", "training_loss", "cumulative_seconds"}
+    for key in ("early_stopped", "final_epoch", "best_val_epoch", "best_val_loss"):
+        assert key in captured[-1]
+
+
+def test_reference_case_constructor():
+    assert MermaidTrainer(batch_size=100).early_stopping_patience is None
+    assert MermaidTrainer(batch_size=100, early_stopping_patience=1).early_stopping_patience == 1
