@@ -155,9 +155,10 @@ def test_platt_fit_matches_oracle_on_reference_probabilities(g):
         assert l_dev <= l_ref + 1e-9 * abs(l_ref)
         assert loss[k] == pytest.approx(l_dev, rel=1e-12)
         assert np.abs(grad).max() < 1e-6
-    # ... and the parameters agree to the precision L-BFGS-B stops at (gtol 1e-6 on a flat valley)
-    np.testing.assert_allclose(a, g["platt_a"], rtol=2e-3)
-    np.testing.assert_allclose(b, g["platt_b"], rtol=2e-3)
+    # ... and the parameters agree within the tolerance the reference's own calibration-equivalence test uses
+    # (tests/pyspacer/test_trainer.py:118-139: rtol 1e-3, atol 5e-3 on a_ / b_)
+    np.testing.assert_allclose(a, g["platt_a"], rtol=1e-3, atol=5e-3)
+    np.testing.assert_allclose(b, g["platt_b"], rtol=1e-3, atol=5e-3)
     cal = otr.calibrated_proba64(g["proba_ref"], a, b)
     assert np.abs(cal - otr.calibrated_proba64(g["proba_ref"], g["platt_a"], g["platt_b"])).max() < 1e-4
     assert 2 <= passes <= 100
