@@ -52,3 +52,20 @@ def test_no_cpu_fallback(backbone_sd):
     h = C.c_void_p()
     status = lib.mc_extractor_create(blob.ctypes.data, blob.size, 0, 0, 8, C.byref(h))
     assert status == _lib.MC_ERR_CUDA and b"no CPU fallback" in lib.mc_last_error()
+
+
+def test_serving_imports_stay_light():
+    """Mirror of the reference's inference/training split (tests/pyspacer/test_inference_decoupling.py): importing the
+    serving-side modules must not drag in the training-only stack (scikit-learn, scipy, pyspacer) -- checked in a fresh
+    interpreter so modules imported by this session cannot mask a regression."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    for target in ("mermaid_classifier_b200.inference", "mermaid_classifier_b200.extractor", "mermaid_classifier_b200.export"):
+        script = (f"import sys\nsys.path.insert(0, {str(root)!r})\nimport {target}\n"
+                  "heavy = [m for m in ('sklearn', 'scipy', 'spacer', 'pandas') if m in sys.modules]\n"
+                  "assert not heavy, heavy\nprint('ok')\n")
+        res = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True)
+        assert res.returncode == 0 and "ok" in res.stdout, (target, res.stderr[-400:])
