@@ -18,8 +18,10 @@ is out of scope); everything numerical runs in libmermaid_b200.
 from __future__ import annotations
 
 import csv
+import json
 import time
 from dataclasses import dataclass, field
+from datetime import datetime, timezone
 from pathlib import Path
 from typing import Any, Iterable, Mapping, Sequence
 
@@ -92,6 +94,10 @@ class RunCounters:
     started: float = field(default_factory=time.monotonic)
 
 
+def _ts() -> str:
+    return datetime.now(timezone.utc).strftime("%Y-%m-%dT%H:%M:%SZ")
+
+
 def build_feature_bucket(
     sources: Mapping[str, Mapping[str, Sequence[tuple[int, int]]]],
     extractor: Any,
@@ -100,19 +106,35 @@ def build_feature_bucket(
     target_root: str | Path,
     source_prefix: str = "",
     skip_existing: bool = True,
+    dry_run: bool = False,
     rank: int = 0,
     world: int = 1,
     error_csv: str | Path | None = None,
+    progress_jsonl: str | Path | None = None,
 ) -> RunCounters:
     """Extract every image of every source into ``target_root/s{sid}/features/i{iid}.featurevector``.
 
     ``sources[sid][iid]`` is the image's rowcols (see :func:`prepare_points`).  Images of a source are walked in
     sorted id order and dealt round-robin to ranks (``index % world == rank``); a failing image is recorded and
-    the run continues (``build_feature_bucket.py:774-786``)."""
+    the run continues (``build_feature_bucket.py:774-786``).  The two logs follow the reference's records:
+    ``progress_jsonl`` one JSON object per image -- ``ts, source_id, image_id, outcome`` (``ok`` / ``skipped`` /
+    ``failed``) plus ``reason`` (``no_rowcols`` / ``exists``), ``error_type`` or ``dry_run``
+    (``record_progress``, ``:794-808``); ``error_csv`` rows ``ts, source_id, image_id, error_type, error_msg`` under
+    that header (``record_failure``, ``:810-822``, header ``:883``).  Both append, so a resumed run extends them."""
     counters = RunCounters()
     source_root, target_root = Path(source_root), Path(target_root)
+    new_err = error_csv is not None and (not Path(error_csv).exists() or Path(error_csv).stat().st_size == 0)
     err_file = open(error_csv, "a", newline="") if error_csv else None
     err = csv.writer(err_file) if err_file else None
+    if err and new_err:
+        err.writerow(["ts", "source_id", "image_id", "error_type", "error_msg"])
+    prog = open(progress_jsonl, "a") if progress_jsonl else None
+
+    def progress(sid, iid, outcome, **extra):
+        if prog:
+            prog.write(json.dumps({"ts": _ts(), "source_id": sid, "image_id": iid, "outcome": outcome, **extra}) + "\n")
+            prog.flush()
+
     try:
         for sid in sorted(sources):
             grouped = sources[sid]
@@ -126,9 +148,15 @@ def build_feature_bucket(
                 floc = DataLocation("filesystem", str(target_root / feature_key(sid, iid)))
                 if not rowcols:
                     counters.images_skipped += 1
+                    progress(sid, iid, "skipped", reason="no_rowcols")
                     continue
                 if skip_existing and storage_factory("filesystem").exists(floc.key):
                     counters.images_skipped += 1
+                    progress(sid, iid, "skipped", reason="exists")
+                    continue
+                if dry_run:
+                    counters.images_ok += 1
+                    progress(sid, iid, "ok", dry_run=True)
                     continue
                 msg = ExtractFeaturesMsg(
                     job_token=f"s{sid}_i{iid}", extractor=extractor, rowcols=rowcols,
@@ -138,16 +166,20 @@ def build_feature_bucket(
                     extract_features(msg)
                     counters.images_ok += 1
                     counters.patches += len(rowcols)
+                    progress(sid, iid, "ok")
                 except KeyboardInterrupt:
                     raise
                 except Exception as exc:  # per-image failure: log and carry on
                     counters.images_failed += 1
                     if err:
-                        err.writerow([sid, iid, type(exc).__name__, str(exc)])
+                        err.writerow([_ts(), sid, iid, type(exc).__name__, str(exc)])
+                    progress(sid, iid, "failed", error_type=type(exc).__name__)
             counters.sources_done += 1
     finally:
         if err_file:
             err_file.close()
+        if prog:
+            prog.close()
     return counters
 
 

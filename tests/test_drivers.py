@@ -1,5 +1,8 @@
 """Host logic either side of the hot path (no GPU): point grouping, bucket key layout, skip-existing,
 per-image error capture, rank sharding of the bucket driver, .featurevector round trip and stacking."""
+import csv
+import json
+
 import numpy as np
 from PIL import Image
 
@@ -52,16 +55,31 @@ def test_bucket_driver_layout_skip_errors_and_sharding(tmp_path):
     sources["12"]["3"] = [(1, 2), (400, 4)]      # out-of-bounds point -> per-image failure, run continues
     sources["12"]["4"] = []                       # no rowcols -> skipped
     ex = FakeExtractor()
+    dry = drivers.build_feature_bucket(sources, ex, source_root=src, target_root=tgt, dry_run=True,
+                                       progress_jsonl=tmp_path / "dry.jsonl")
+    assert dry.images_ok == 6 and dry.images_skipped == 1 and ex.calls == 0 and not tgt.exists()
+    assert all(r["dry_run"] for r in map(json.loads, (tmp_path / "dry.jsonl").read_text().splitlines()) if r["outcome"] == "ok")
     c0 = drivers.build_feature_bucket(sources, ex, source_root=src, target_root=tgt, rank=0, world=2,
-                                      error_csv=tmp_path / "err.csv")
+                                      error_csv=tmp_path / "err.csv", progress_jsonl=tmp_path / "p0.jsonl")
     c1 = drivers.build_feature_bucket(sources, ex, source_root=src, target_root=tgt, rank=1, world=2,
-                                      error_csv=tmp_path / "err.csv")
+                                      error_csv=tmp_path / "err.csv", progress_jsonl=tmp_path / "p1.jsonl")
     assert c0.images_ok + c1.images_ok == 5 and c0.images_failed + c1.images_failed == 1
     assert c0.images_skipped + c1.images_skipped == 1 and c0.sources_done == 2
     assert sorted(p.name for p in (tgt / "s12" / "features").iterdir()) == ["i0.featurevector", "i1.featurevector", "i2.featurevector"]
-    assert "RowColumnInvalidError" in (tmp_path / "err.csv").read_text()
+    err_rows = list(csv.reader((tmp_path / "err.csv").open()))
+    assert err_rows[0] == ["ts", "source_id", "image_id", "error_type", "error_msg"] and len(err_rows) == 2
+    assert err_rows[1][1:4] == ["12", "3", "RowColumnInvalidError"]
+    recs = [json.loads(l) for f in ("p0.jsonl", "p1.jsonl") for l in (tmp_path / f).read_text().splitlines()]
+    outcome = {(r["source_id"], r["image_id"]): r for r in recs}
+    assert len(recs) == 7 and outcome[("12", "4")]["reason"] == "no_rowcols" and outcome[("12", "3")]["outcome"] == "failed"
+    assert outcome[("12", "3")]["error_type"] == "RowColumnInvalidError" and outcome[("7", "1")]["outcome"] == "ok"
+    assert set(outcome[("7", "1")]) == {"ts", "source_id", "image_id", "outcome"}
     calls = ex.calls
-    again = drivers.build_feature_bucket(sources, ex, source_root=src, target_root=tgt, skip_existing=True)
+    again = drivers.build_feature_bucket(sources, ex, source_root=src, target_root=tgt, skip_existing=True,
+                                         error_csv=tmp_path / "err.csv", progress_jsonl=tmp_path / "again.jsonl")
+    again_recs = [json.loads(l) for l in (tmp_path / "again.jsonl").read_text().splitlines()]
+    assert sum(r.get("reason") == "exists" for r in again_recs) == 5
+    assert len(list(csv.reader((tmp_path / "err.csv").open()))) == 3   # appended, header written once
     # only the failing image is retried, and it fails validation again before reaching the extractor
     assert again.images_ok == 0 and again.images_skipped == 6 and again.images_failed == 1 and ex.calls == calls
     X = drivers.stack_feature_files(sorted((tgt / "s7" / "features").iterdir()), tmp_path / "ref.npy")
