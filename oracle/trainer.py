@@ -15,7 +15,7 @@ The metric / calibration arithmetic lives in a third-party dependency, scikit-le
 algorithm is restated here; PINNED by ``tests/test_oracle_trainer.py`` against the scikit-learn installed in
 this image (1.9.0 -- ``log_loss``, ``accuracy_score``, ``_SigmoidCalibration``; the calibration routine is
 unchanged between 1.5.2 and 1.9.0) and against the reference's own ``MermaidTrainer`` helper methods, run
-on the reference's ``TorchMLPClassifier`` (``tests/golden/make_golden.py``, fixture ``trainer_eval.npz``).
+on the reference's ``TorchMLPClassifier`` (``tests/golden/make_golden_trainer.py``, fixture ``trainer_eval.npz``).
 """
 
 from __future__ import annotations
@@ -152,3 +152,43 @@ def run_epochs(clf: Any, train_batches: Callable[[int], Any], evaluate: Callable
             "best_val_epoch": best_idx + 1 if best_idx is not None else None,
             "best_val_loss": best if best != float("inf") else None}
     return clf, history, info
+
+
+def platt_newton(f: np.ndarray, y01: np.ndarray, gtol: float = 1e-9, max_passes: int = 400) -> tuple[float, float, float, int]:
+    """The iteration ``mermaid_classifier_b200/csrc/platt.cuh`` runs per class, restated in numpy: Newton direction with
+    a 1e-12 ridge, backtracking (sufficient decrease 1e-4, halving down to 1e-10), stop on ``|grad|_inf < gtol`` or, once
+    the predicted decrease is below 1e-11 of the objective, one final un-searched Newton step.  Same objective and start as
+    :func:`sigmoid_calibration`; returns ``(a, b, objective at the last evaluated point, passes)``.  Used to check on
+    the CPU that this iteration lands on sklearn's optimum, and on the GPU that the kernel follows it."""
+    f = np.asarray(f, dtype=np.float64)
+    t, prior0, prior1 = platt_targets(np.asarray(y01))
+    A, B = 0.0, log((prior0 + 1.0) / (prior1 + 1.0))
+    tA, tB, first, step, fval, gd, dA, dB, passes, accepted = A, B, True, 1.0, 0.0, 0.0, 0.0, 0.0, 0, 0
+    while passes < max_passes:
+        r = -(tA * f + tB)
+        e = np.exp(-np.abs(r))
+        p = np.where(r >= 0, 1.0, e) / (1.0 + e)
+        L = float((np.log1p(e) + np.maximum(r, 0.0) - t * r).sum())
+        g, h = p - t, p * (1.0 - p)
+        gA, gB = float(-(g * f).sum()), float(-g.sum())
+        hAA, hAB, hBB = float((h * f * f).sum()) + 1e-12, float((h * f).sum()), float(h.sum()) + 1e-12
+        passes += 1
+        if first or L < fval + 1e-4 * step * gd:
+            first, A, B, fval = False, tA, tB, L
+            accepted += 1
+            if (abs(gA) < gtol and abs(gB) < gtol) or accepted > 100:
+                break
+            det = hAA * hBB - hAB * hAB
+            dA, dB = -(hBB * gA - hAB * gB) / det, -(-hAB * gA + hAA * gB) / det
+            gd, step = gA * dA + gB * dB, 1.0
+            if not gd < 0.0 or not np.isfinite(dA) or not np.isfinite(dB):
+                break
+            if -gd < 1e-11 * max(1.0, abs(fval)):
+                A, B = A + dA, B + dB
+                break
+        else:
+            step *= 0.5
+            if step < 1e-10:
+                break
+        tA, tB = A + step * dA, B + step * dB
+    return A, B, fval, passes

@@ -126,3 +126,30 @@ def test_calibrated_proba_matches_reference_run(g):
     # and the fp32 head form (what the artifact computes) sits within the reference's 1e-6 export gate of it
     head = ohead.calibrated_proba(g["Xv"], w, b, torch.from_numpy(g["platt_a"]).float(), torch.from_numpy(g["platt_b"]).float())
     assert np.abs(head - got).max() < 1e-6
+
+
+@pytest.mark.parametrize("case", ["skewed", "rare", "no_positive", "all_positive", "near_separable", "uninformative"])
+def test_newton_iteration_reaches_the_lbfgsb_optimum(case):
+    """The device algorithm (restated as ``platt_newton``) and sklearn's L-BFGS-B minimise the same convex objective:
+    Newton's end point is never worse, its gradient is at rounding level, and the calibration curves coincide."""
+    rng = np.random.default_rng(7)
+    n = 20000
+    f = rng.random(n) ** 6
+    y = {"skewed": rng.random(n) < 0.05 + 0.9 * f,
+         "rare": rng.random(n) < 0.002 + 0.3 * f,
+         "no_positive": np.zeros(n, bool),
+         "all_positive": np.ones(n, bool),
+         "near_separable": (f > 0.3) ^ (rng.random(n) < 0.01),
+         "uninformative": rng.random(n) < 0.1}[case].astype(int)
+    a, b, loss, passes = otr.platt_newton(f, y)
+    ra, rb = otr.sigmoid_calibration(f, y)
+    t = otr.platt_targets(y)[0]
+    l_newton, grad = otr.platt_objective(a, b, f, t)
+    l_ref = otr.platt_objective(ra, rb, f, t)[0]
+    assert passes <= 60
+    assert l_newton <= l_ref + 1e-9 * max(1.0, abs(l_ref))
+    assert np.abs(grad).max() < 1e-6
+    assert loss == pytest.approx(l_newton, rel=1e-9, abs=1e-9)
+    q = np.linspace(0.0, 1.0, 201)
+    curve = lambda A, B: 1.0 / (1.0 + np.exp(A * q + B))
+    assert np.abs(curve(a, b) - curve(ra, rb)).max() < 2e-3
