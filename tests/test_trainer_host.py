@@ -203,3 +203,35 @@ def test_reference_case_summary_only_on_final_epoch():
 def test_reference_case_constructor():
     assert MermaidTrainer(batch_size=100).early_stopping_patience is None
     assert MermaidTrainer(batch_size=100, early_stopping_patience=1).early_stopping_patience == 1
+
+
+# ---- host-side contracts of the estimator mirror (reference: tests/pyspacer/test_mlp_benchmark.py:409-570) -----------------
+def test_estimator_batching_and_label_contracts_host_side():
+    from mermaid_classifier_b200.torch_classifier import TorchMLPClassifier, split_steps
+
+    auto = TorchMLPClassifier(hidden_layer_sizes=(16,), batch_size="auto", random_state=42)
+    assert auto._resolve_batch_size(500) == 200 and auto._resolve_batch_size(50) == 50      # min(200, n_samples)
+    assert TorchMLPClassifier(batch_size=128)._resolve_batch_size(50) == 50                  # explicit size is clipped
+    # ceil(n / batch) Adam steps per partial_fit call, one step when the input is smaller than the batch
+    for n, mb, steps in ((500, 100, 5), (500, 200, 3), (50, 200, 1), (650, 200, 4)):
+        pos, offsets = split_steps(n, min(mb, n))
+        assert len(offsets) - 1 == steps and offsets[0] == 0 and offsets[-1] == n and np.array_equal(pos, np.arange(n))
+    # string labels handed over as an object array (what pyspacer's loaders yield) map onto sorted unique classes_
+    y = np.array(["a", "b", "c"] * 166 + ["a", "b"], dtype=object)
+    auto.classes_ = np.unique(np.asarray(["c", "a", "b"]))
+    assert list(auto.classes_) == ["a", "b", "c"]
+    idx = auto._labels_to_indices(y)
+    assert idx.tolist() == ([0, 1, 2] * 166 + [0, 1])
+    with pytest.raises(ValueError, match="not in classes_"):
+        auto._labels_to_indices(np.array(["a", "z"], dtype=object))
+    # class weights follow classes_ order; missing or negative weights are rejected (torch_classifier.py:188-214)
+    auto.class_weight = {"b": 2.0, "a": 1.0, "c": 0.5}
+    assert auto._build_class_weight().tolist() == [1.0, 2.0, 0.5]
+    auto.class_weight = {"a": 1.0, "b": 2.0}
+    with pytest.raises(ValueError, match="missing weights"):
+        auto._build_class_weight()
+    auto.class_weight = {"a": 1.0, "b": -2.0, "c": 1.0}
+    with pytest.raises(ValueError, match="negative"):
+        auto._build_class_weight()
+    # the shuffle is re-seeded from random_state inside every call (same state -> same order, call after call)
+    assert np.array_equal(auto._seed_rng().permutation(10), auto._seed_rng().permutation(10))
