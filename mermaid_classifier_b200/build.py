@@ -24,7 +24,10 @@ STAMP = PKG / ".libmermaid_b200.stamp"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "--use_fast_math",
+    # No --use_fast_math: the head / Platt / Adam kernels need IEEE division, sqrt and accurate expf / logf (the
+    # reference's 1e-6 export gate).  Backbone kernels name their fast intrinsics (__expf, __fdividef, tanh.approx)
+    # explicitly.  Denormals are flushed (irrelevant at the tolerances in play, and it keeps MUFU sequences short).
+    "-ftz=true",
     "-Xcompiler", "-fPIC",
     "-shared",
 ]

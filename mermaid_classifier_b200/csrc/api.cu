@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -17,6 +18,7 @@
 #include "mlp_train.cuh"
 #include "pw_simt.cuh"
 #include "pw_tc.cuh"
+#include "mbconv_fused.cuh"
 
 using namespace mc;
 
@@ -109,6 +111,8 @@ struct mc_extractor {
   PwTcPlan* tc = nullptr;  // tcgen05 GEMM plans (pw_tc.cuh)
   StemParams stem;          // stem weights + folded BN, passed by value (kernel parameter / constant bank)
   std::vector<DwLayer> dw;  // TMA-staged depthwise plans (dw_tma.cuh), one per block
+  std::vector<FusedLayer> fused;  // WIP: expand + depthwise in one kernel (mbconv_fused.cuh), MC_FUSE_MASK bit b = block b
+  unsigned fuse_mask = 0;
   int64_t launches = 0;
   int64_t l2_budget = 0;  // bytes of per-chunk working set kept L2-resident (0 = no chunking)
   int tap_layer = -1;
@@ -296,6 +300,43 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
       const T* Xc = X + (int64_t)c0 * HWi * b.c_in;
       T* Yc = Y + (int64_t)c0 * HW * b.c_out;
       const T* dw_in = Xc;
+      // WIP fused expand + depthwise (fp32, blocks b1..b4, whole batch, no taps): MC_FUSE_MASK selects blocks
+      if (std::is_same<T, float>::value && b.expand != 1 && ((h->fuse_mask >> bi) & 1u) && chunk == nb && !tapping && h->tc &&
+          pw_tc_has(h->tc, (int)bi * 2)) {
+        if (h->fused.size() != net.blocks.size()) h->fused.resize(net.blocks.size());
+        FusedLayer& fl = h->fused[bi];
+        if (fl.shape == -1) {
+          const PwTcLayer& el = h->tc->layers[(int)bi * 2];
+          if ((rc = fused_plan_layer(&fl, b.k, b.stride, b.c_in, b.c_mid, b.h_in, el.d_w, el.d_wlo))) return rc;
+          if (!fl.present) fl.shape = -2;   // not a fusable shape: remember, fall through to the two-kernel path
+        }
+        if (fl.present) {
+          FusedArgs fa;
+          fa.w_dw = P + b.w_dw;
+          fa.s_dw = P + b.s_dw;
+          fa.b_dw = P + b.b_dw;
+          fa.s_exp = P + b.s_exp;
+          fa.b_exp = P + b.b_exp;
+          fa.out = (float*)D;
+          fa.pool_partial = h->d_pool;
+          fa.nb = nb;
+          {
+            ProfScope ps(h, 2 + 4 * (int)bi, st);
+            if ((rc = fused_launch(fl, (const float*)Xc, b.c_in, b.h_in, fa, st))) return rc;
+          }
+          MC_CHECK_LAUNCH();
+          h->launches++;
+          {
+            ProfScope ps(h, 3 + 4 * (int)bi, st);
+            se_kernel<<<nb, 256, (b.c_mid + b.c_se) * sizeof(float), st>>>(
+                h->d_pool, fused_shape_of(fl.shape).nbands, 1.f / (float)(b.h_out * b.h_out), P + b.w_se1, P + b.b_se1,
+                P + b.w_se2, P + b.b_se2, h->d_gate, h->d_gate_h, b.c_mid, b.c_se);
+          }
+          MC_CHECK_LAUNCH();
+          h->launches++;
+          goto project;
+        }
+      }
       if (b.expand != 1) {
         ProfScope ps(h, 1 + 4 * (int)bi, st);
         if (h->tc && pw_tc_has(h->tc, (int)bi * 2)) {
@@ -310,6 +351,7 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
       if ((rc = launch_dw<T>(h, b, b.expand != 1 ? 0 : c0, D, cn, st))) return rc;
       if ((rc = tap<T>(h, 2 + 4 * (int)bi, D, Mout * b.c_mid, st))) return rc;
       if ((rc = tap<float>(h, 3 + 4 * (int)bi, h->d_gate, (int64_t)cn * b.c_mid, st))) return rc;
+    project:
       {
         ProfScope ps_proj(h, 4 + 4 * (int)bi, st);
         if (h->tc && pw_tc_has(h->tc, (int)bi * 2 + 1)) {
@@ -331,15 +373,15 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
     std::swap(X, Y);
   }
   const int64_t Mh = (int64_t)nb * 49;
-  ProfScope ps_head(h, 65, st);
-  if (h->tc && pw_tc_has(h->tc, 32)) {
-    if ((rc = pw_tc_run(h->tc, 32, X, 0, nullptr, nullptr, Hb, Mh, 49, st))) return rc;
-    h->launches++;
-  } else if ((rc = launch_pw_simt<T, ACT_SILU, false, false>(h, X, P + net.w_head, P + net.s_head, P + net.b_head,
-                                                             nullptr, nullptr, Hb, Mh, 1280, 320, 1, st)))
-    return rc;
-  ps_head.~ProfScope();
-  ps_head.on = false;
+  {
+    ProfScope ps_head(h, 65, st);
+    if (h->tc && pw_tc_has(h->tc, 32)) {
+      if ((rc = pw_tc_run(h->tc, 32, X, 0, nullptr, nullptr, Hb, Mh, 49, st))) return rc;
+      h->launches++;
+    } else if ((rc = launch_pw_simt<T, ACT_SILU, false, false>(h, X, P + net.w_head, P + net.s_head, P + net.b_head,
+                                                               nullptr, nullptr, Hb, Mh, 1280, 320, 1, st)))
+      return rc;
+  }
   if ((rc = tap<T>(h, 65, Hb, Mh * 1280, st))) return rc;
   {
     ProfScope ps(h, 66, st);
@@ -497,6 +539,7 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
   // convs run on the tcgen05 kernel; default: all of them.  Bring-up / bisecting aid only.
   unsigned long long tc_mask = ~0ull;
   if (const char* env = getenv("MC_TC_MASK")) tc_mask = strtoull(env, nullptr, 16);
+  if (const char* env = getenv("MC_FUSE_MASK")) h->fuse_mask = (unsigned)strtoul(env, nullptr, 16);   // WIP, default off
   if ((rc = pw_tc_build(&h->tc, h->net, params, h->d_params, mode, max_batch, device, (unsigned)(tc_mask & 0xffffffffu),
                         (unsigned)(tc_mask >> 32)))) {
     mc_extractor_destroy(h);

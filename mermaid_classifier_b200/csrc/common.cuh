@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/mermaid_b200.h"
@@ -29,8 +30,9 @@ inline int fail(int code, const std::string& msg) {
 #define MC_CHECK_LAUNCH() MC_CUDA(cudaGetLastError())
 
 // ---- math -----------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// backbone activations: fast intrinsics by name (the library is NOT built with --use_fast_math)
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // swish of bn = acc * scale + bias in the activation mode of T.
 //   fp32 mode: exact form, 2 MUFU ops (ex2, rcp).
 //   bf16 mode: x * sigmoid(x) = h + h * tanh(h) with h = x / 2 and ONE MUFU op (tanh.approx, rel. error 2^-11,
@@ -142,5 +144,14 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
 }
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Function attributes (max dynamic shared memory) are per DEVICE: a `static bool` would set them on the first device
+// of the process only.  `mask` is a function-local static; true exactly once per (call site, current device).
+inline bool first_use_on_device(std::atomic<unsigned long long>& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  return (mask.fetch_or(bit) & bit) == 0;
+}
 
 }  // namespace mc

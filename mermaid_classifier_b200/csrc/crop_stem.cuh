@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(192) crop_kernel(const mc_image* __restrict__ 
   const mc_point pt = points[k];
   const mc_image im = images[pt.image];
   const int x0 = pt.col - 112;
-  // one pixel of slack on the right: the last aligned word of a misaligned segment reaches up to 3 bytes past it
-  const bool interior = x0 >= 0 && x0 + 225 <= im.width;
+  // one pixel of slack on either side: the first / last aligned word of a misaligned segment reaches up to 3 bytes
+  // before / past it, and must stay inside the row even when the image base or pitch is not 4-byte aligned
+  const bool interior = x0 >= 1 && x0 + 225 <= im.width;
   const int tid = threadIdx.x;
   __shared__ uint8_t row_s[224 * 3];
 #pragma unroll 7

@@ -613,11 +613,9 @@ inline int dw_tma_launch(DwLayer& l, const CUtensorMap& tm, const DwArgs& a, int
   dim3 grid(l.nbands, nb, l.cz), block(l.threads);
 #define DW_CASE(KK, SS, TT)                                                                                          \
   if (l.K == KK && l.S == SS && l.TW == TT) {                                                                        \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
+    static std::atomic<unsigned long long> attr_mask{0};                                                              \
+    if (first_use_on_device(attr_mask))                                                                               \
       MC_CUDA(cudaFuncSetAttribute(dw_tma_kernel<T, KK, SS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); \
-      attr_set = true;                                                                                                \
-    }                                                                                                                 \
     dw_tma_kernel<T, KK, SS, TT><<<grid, block, l.smem, st>>>(tm, a);                                                 \
     MC_CHECK_LAUNCH();                                                                                                \
     return MC_OK;                                                                                                     \
@@ -633,11 +631,9 @@ inline int dw_tma_launch(DwLayer& l, const CUtensorMap& tm, const DwArgs& a, int
 
 template <typename T, int SHAPE>
 inline int dw_reg_launch_shape(DwLayer& l, const CUtensorMap& tm, const DwRegArgs& a, dim3 grid, dim3 block, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_mask{0};
+  if (first_use_on_device(attr_mask))
     MC_CUDA(cudaFuncSetAttribute(dw_reg_kernel<T, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    attr_set = true;
-  }
   dw_reg_kernel<T, SHAPE><<<grid, block, l.smem, st>>>(tm, a);
   MC_CHECK_LAUNCH();
   return MC_OK;

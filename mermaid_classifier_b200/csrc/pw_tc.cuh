@@ -160,6 +160,11 @@ __device__ __forceinline__ void mma_ss_elect(uint32_t d_tmem, uint32_t a_lo, uin
         : "memory");
   }
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred el;\n\telect.sync _|el, 0xffffffff;\n\t"
@@ -182,6 +187,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns (thread t: lane base + t, columns c..c+15).  No wait inside.
+__device__ __forceinline__ void tmem_ld32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -433,13 +448,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == WARP_MMA) {
     // ================================ MMA issuer ==================================
-    // All 32 lanes walk the loop convergently; elect.sync inside each tcgen05 asm picks the issuing lane (always the same
-    // one for the full mask, so tcgen05.commit tracks the MMAs it follows).
-    {
+    if (ptx::elect_one()) {
       const uint32_t idesc = (1u << 4) | (Cfg::FMT << 7) | (Cfg::FMT << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
-      constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);   // SBO = 1024 >> 4, version 1, SWIZZLE_128B
+      constexpr uint64_t DESC_HI64 = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;   // SBO = 1024 >> 4, version 1, SWIZZLE_128B
       constexpr uint32_t DESC_LBO = 1u << 16;
+      const uint32_t stage_lo = ptx::smem_u32(stage_base) >> 4, w_lo_base = ptx::smem_u32(w_base) >> 4;
+      const uint32_t stage_step = (uint32_t)STAGE_BYTES >> 4, w_step = (uint32_t)W_BYTES >> 4;
       int s = 0;
       uint32_t ph = 0;
       int li = 0;
@@ -449,23 +464,19 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         ptx::mbar_wait(wbar, 0);
         ptx::tc_fence_after();
       }
-      const uint32_t stage_lo = ptx::smem_u32(stage_base) >> 4, w_lo_base = ptx::smem_u32(w_base) >> 4;
-      const uint32_t stage_step = (uint32_t)STAGE_BYTES >> 4, w_step = (uint32_t)W_BYTES >> 4;
       for (int it = blockIdx.x; it < items; it += gridDim.x, ++li) {
-        const int gj = li / n_groups;                                           // index among its group's items
+        const int gj = li / n_groups;
         const int as = li % n_groups + n_groups * (gj % ACC_DEPTH);
         const uint32_t use = (uint32_t)(gj / ACC_DEPTH);
-        const int nb_i = (int)((uint32_t)it - ((uint32_t)it / nblk) * nblk);   // n-block of this item
+        const int nb_i = (int)((uint32_t)it - ((uint32_t)it / nblk) * nblk);
         w_tempty += ptx::mbar_wait_timed(&tempty[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_cols);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           w_full += ptx::mbar_wait_timed(transform ? &ready[s] : &full[s], ph);
           ptx::tc_fence_after();
-          __syncwarp();
-          // low descriptor words: all operand tiles live below 256 KB, so (address >> 4) never leaves the 14-bit field
+          // low descriptor words ((address >> 4) | LBO); every operand tile lives below 256 KB, so the 14-bit field never wraps
           const uint32_t a_lo = (stage_lo + (uint32_t)s * stage_step) | DESC_LBO;
-          // W tile of (n-block, k-chunk): resident region, or behind the A operands of this stage
           const uint32_t w_lo = w_res ? ((w_lo_base + (uint32_t)((nb_i * p.k_chunks + kc) * Cfg::NW) * w_step) | DESC_LBO)
                                       : a_lo + (uint32_t)((Cfg::NA * Cfg::A_BYTES) >> 4);
           const int krem = p.K - kc * Cfg::KC;
@@ -476,25 +487,25 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const uint32_t acc = (kc | ks) != 0;
               const uint32_t ko = (uint32_t)ks * 2u;   // UK elements = 32 bytes = 2 descriptor units
               if (Cfg::TF32) {
-                const uint32_t ahi = a_lo + ko, alo = a_lo + (uint32_t)(Cfg::A_BYTES >> 4) + ko;
-                const uint32_t whi = w_lo + ko, wlo = w_lo + w_step + ko;
-                ptx::mma_ss_elect<true>(d_tmem, alo, whi, DESC_HI, idesc, acc);
-                ptx::mma_ss_elect<true>(d_tmem, ahi, wlo, DESC_HI, idesc, 1u);
-                ptx::mma_ss_elect<true>(d_tmem, ahi, whi, DESC_HI, idesc, 1u);
+                const uint64_t ahi = DESC_HI64 | (a_lo + ko), alo = DESC_HI64 | (a_lo + (uint32_t)(Cfg::A_BYTES >> 4) + ko);
+                const uint64_t whi = DESC_HI64 | (w_lo + ko), wlo = DESC_HI64 | (w_lo + w_step + ko);
+                ptx::mma_ss<true>(d_tmem, alo, whi, idesc, acc);
+                ptx::mma_ss<true>(d_tmem, ahi, wlo, idesc, 1u);
+                ptx::mma_ss<true>(d_tmem, ahi, whi, idesc, 1u);
               } else {
-                ptx::mma_ss_elect<false>(d_tmem, a_lo + ko, w_lo + ko, DESC_HI, idesc, acc);
+                ptx::mma_ss<false>(d_tmem, DESC_HI64 | (a_lo + ko), DESC_HI64 | (w_lo + ko), idesc, acc);
               }
             }
           }
-          ptx::mma_commit_elect(&empty[s]);
+          ptx::mma_commit(&empty[s]);
           if (++s == S) {
             s = 0;
             ph ^= 1;
           }
         }
-        ptx::mma_commit_elect(&tfull[as]);
+        ptx::mma_commit(&tfull[as]);
       }
-      if (MC_TC_TIMING && p.dbg && blockIdx.x == 0 && lane == 0) {
+      if (MC_TC_TIMING && p.dbg && blockIdx.x == 0) {
         p.dbg[2] = w_tempty;
         p.dbg[3] = w_full;
         p.dbg[4] = ptx::tc_clock() - t_begin;
@@ -803,6 +814,7 @@ struct PwTcLayer {
 struct PwTcPlan {
   int mode = 0, device = 0, num_sms = 148, max_batch = 0;
   bool relu_variant = false;   // launch the RELU instantiation (MLP head)
+  long long* dbg_buf = nullptr;   // MC_TC_DBG role counters (device memory of this plan's device)
   std::vector<PwTcLayer> layers;  // 2*b = expand of block b, 2*b+1 = project, 32 = head conv
 };
 
@@ -814,6 +826,7 @@ inline void pw_tc_free(PwTcPlan* p) {
     if (l.d_w) cudaFree(l.d_w);
     if (l.d_wlo) cudaFree(l.d_wlo);
   }
+  if (p->dbg_buf) cudaFree(p->dbg_buf);
   delete p;
 }
 
@@ -941,12 +954,11 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   a.exp_flags = exp_flags;
   // MC_TC_DBG=<layer id>: after that layer's launch, print CTA 0's per-role wait/total cycles (synchronises)
   static const int dbg_layer = getenv("MC_TC_DBG") ? atoi(getenv("MC_TC_DBG")) : -1;
-  static long long* dbg_buf = nullptr;
   a.dbg = nullptr;
   if (dbg_layer == id) {
-    if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 32 * sizeof(long long));
-    cudaMemsetAsync(dbg_buf, 0, 32 * sizeof(long long), st);
-    a.dbg = dbg_buf;
+    if (!plan->dbg_buf) cudaMalloc((void**)&plan->dbg_buf, 32 * sizeof(long long));
+    cudaMemsetAsync(plan->dbg_buf, 0, 32 * sizeof(long long), st);
+    a.dbg = plan->dbg_buf;
   }
   a.N = l.N;
   a.K = l.K;
@@ -971,11 +983,9 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   const int grid = (int)std::min<int64_t>(items, plan->num_sms);
   const bool gated = a.gate != nullptr;
   if (plan->relu_variant) {   // MLP head (fp32, ungated)
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
-      attr_set = true;
-    }
     pw_tc_kernel<float, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
   } else if (f32 && gated)
     pw_tc_kernel<float, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
@@ -989,7 +999,7 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   if (a.dbg) {
     long long d[32];
     cudaStreamSynchronize(st);
-    cudaMemcpy(d, dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
+    cudaMemcpy(d, plan->dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
     static int printed = 0;
     if (printed++ < 3) {
       const double it = (double)std::max<long long>(d[5], 1);

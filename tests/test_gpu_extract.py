@@ -241,3 +241,22 @@ def test_full_size_sub_batch_properties(backbone_sd):
     got = full[idx]
     assert np.abs(got - want).max() <= FP32_MAX_ABS
     assert cosines(got, want).min() >= FP32_MIN_COS
+
+
+@pytest.mark.parametrize("mask", ["2", "4", "8", "10", "1e"])
+def test_fused_expand_depthwise_matches_two_kernel_path(backbone_sd, mask, monkeypatch):
+    """WIP branch: MC_FUSE_MASK routes blocks b1..b4 through mbconv_fused_kernel; same arithmetic in the same order as the
+    expand + depthwise pair, so the features must come out bit-identical."""
+    im = synth.synth_image(13, 2, 500, 700)
+    pts = synth.synth_points(13, 2, 500, 700, 20, corners=True)
+    monkeypatch.delenv("MC_FUSE_MASK", raising=False)
+    ref = EfficientNetExtractor(state_dict=backbone_sd, mode="fp32", max_batch=24)
+    want = ref.extract_array(im, pts)
+    ref.close()
+    monkeypatch.setenv("MC_FUSE_MASK", mask)
+    fused = EfficientNetExtractor(state_dict=backbone_sd, mode="fp32", max_batch=24)
+    try:
+        got = fused.extract_array(im, pts)
+    finally:
+        fused.close()
+    assert np.array_equal(got, want)
