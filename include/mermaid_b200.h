@@ -126,6 +126,22 @@ int mc_extract_image_host(mc_extractor* h, const uint8_t* img_host, int32_t heig
                           int64_t row_pitch, const int32_t* rowcols_host, int64_t n_points,
                           float* feats_host, void* stream);
 
+/* ---- The bulk reference-facing call with HOST buffers: the per-image loop of process_source
+ *      (scripts/build_feature_bucket.py:749-788: load image, extractor(img, rowcols), store) and, with a
+ *      head, the extract + classify sequence of AnnotationRun (mermaid_classifier/pyspacer/annotation.py:235-251)
+ *      for a whole list of decoded images in one call.  images_host[i].data are HOST pointers (pinned memory is
+ *      DMA'd directly, pageable memory goes through the handle's pinned staging buffers); points_host must be
+ *      grouped by image (non-decreasing .image).  Inside: a three-slot pipeline on the handle's own copy streams --
+ *      one cudaMemcpyAsync per image into a device arena, the backbone (+ head) on `stream`, features / labels
+ *      back -- so the copy of one group of images overlaps the compute of the previous one.  feats_host
+ *      (n_points x 1280 fp32) and labels_host (n_points int32, needs `head`) may each be NULL.  Synchronises
+ *      before returning. ------------------------------------------------------------------------------------ */
+int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_image* images_host, int32_t n_images,
+                           const mc_point* points_host, int64_t n_points, float* feats_host,
+                           int32_t* labels_host, void* stream);
+/* Bytes copied host->device / device->host and image groups of the last mc_extract_images_host call. */
+int mc_extractor_pipe_stats(const mc_extractor* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* groups);
+
 /* Debug/parity tap: during the NEXT extract call, copy one internal NHWC activation of the
  * first sub-batch to `out_dev` as fp32 (at most `capacity` elements).
  * layer: 0 = stem, 1+4*b+{0,1,2,3} = block b {expand, depthwise, SE gate, block out},

@@ -66,6 +66,8 @@ SIGNATURES = {
     "mc_extract_points": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "mc_extract_patches": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "mc_extract_image_host": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp]),
+    "mc_extract_images_host": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "mc_extractor_pipe_stats": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mc_extractor_set_tap": (C.c_int, [_vp, _i32, _vp, _i64]),
     "mc_extractor_profile": (C.c_int, [_vp, _i32]),
     "mc_extractor_profile_read": (C.c_int, [_vp, _vp, _vp, _i32]),

@@ -22,6 +22,11 @@
 
 using namespace mc;
 
+#ifndef MC_FUSE_DEFAULT
+#define MC_FUSE_DEFAULT 0x2u   // blocks fused by default (bit b = block b): b1 (measured -28 % fp32 / -33 % bf16 against expand + depthwise);
+                               // b2 / b3 measure equal or slower fused (stride-1 consumers are the bound), b4 does not fit in fp32
+#endif
+
 namespace {
 
 struct DeviceGuard {
@@ -91,6 +96,10 @@ int grow(T** p, int64_t* cap, int64_t need) {
 // =====================================================================================
 // extractor
 // =====================================================================================
+struct HostPipe;   // host_pipe.inl: staging ring + streams of mc_extract_images_host
+namespace {
+void host_pipe_free(HostPipe* p);
+}
 struct mc_extractor {
   int device = 0, mode = 0, max_batch = 0;
   NetCfg net;
@@ -111,8 +120,9 @@ struct mc_extractor {
   PwTcPlan* tc = nullptr;  // tcgen05 GEMM plans (pw_tc.cuh)
   StemParams stem;          // stem weights + folded BN, passed by value (kernel parameter / constant bank)
   std::vector<DwLayer> dw;  // TMA-staged depthwise plans (dw_tma.cuh), one per block
-  std::vector<FusedLayer> fused;  // WIP: expand + depthwise in one kernel (mbconv_fused.cuh), MC_FUSE_MASK bit b = block b
+  std::vector<FusedLayer> fused;  // expand + depthwise in one kernel (mbconv_fused.cuh); fuse_mask bit b = block b
   unsigned fuse_mask = 0;
+  HostPipe* pipe = nullptr;        // mc_extract_images_host
   int64_t launches = 0;
   int64_t l2_budget = 0;  // bytes of per-chunk working set kept L2-resident (0 = no chunking)
   int tap_layer = -1;
@@ -300,42 +310,32 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
       const T* Xc = X + (int64_t)c0 * HWi * b.c_in;
       T* Yc = Y + (int64_t)c0 * HW * b.c_out;
       const T* dw_in = Xc;
-      // WIP fused expand + depthwise (fp32, blocks b1..b4, whole batch, no taps): MC_FUSE_MASK selects blocks
-      if (std::is_same<T, float>::value && b.expand != 1 && ((h->fuse_mask >> bi) & 1u) && chunk == nb && !tapping && h->tc &&
-          pw_tc_has(h->tc, (int)bi * 2)) {
-        if (h->fused.size() != net.blocks.size()) h->fused.resize(net.blocks.size());
+      // fused expand + depthwise (mbconv_fused.cuh): whole batch, no taps (the expanded map does not exist to be tapped)
+      if (b.expand != 1 && ((h->fuse_mask >> bi) & 1u) && chunk == nb && !tapping && h->fused[bi].present) {
         FusedLayer& fl = h->fused[bi];
-        if (fl.shape == -1) {
-          const PwTcLayer& el = h->tc->layers[(int)bi * 2];
-          if ((rc = fused_plan_layer(&fl, b.k, b.stride, b.c_in, b.c_mid, b.h_in, el.d_w, el.d_wlo))) return rc;
-          if (!fl.present) fl.shape = -2;   // not a fusable shape: remember, fall through to the two-kernel path
+        FusedArgs fa;
+        fa.w_dw = P + b.w_dw;
+        fa.s_dw = P + b.s_dw;
+        fa.b_dw = P + b.b_dw;
+        fa.b_exp = P + b.b_exp;
+        fa.out = D;
+        fa.pool_partial = h->d_pool;
+        fa.nb = nb;
+        {
+          ProfScope ps(h, 2 + 4 * (int)bi, st);
+          if ((rc = fused_launch<T>(fl, Xc, b.c_in, b.h_in, fa, st))) return rc;
         }
-        if (fl.present) {
-          FusedArgs fa;
-          fa.w_dw = P + b.w_dw;
-          fa.s_dw = P + b.s_dw;
-          fa.b_dw = P + b.b_dw;
-          fa.s_exp = P + b.s_exp;
-          fa.b_exp = P + b.b_exp;
-          fa.out = (float*)D;
-          fa.pool_partial = h->d_pool;
-          fa.nb = nb;
-          {
-            ProfScope ps(h, 2 + 4 * (int)bi, st);
-            if ((rc = fused_launch(fl, (const float*)Xc, b.c_in, b.h_in, fa, st))) return rc;
-          }
-          MC_CHECK_LAUNCH();
-          h->launches++;
-          {
-            ProfScope ps(h, 3 + 4 * (int)bi, st);
-            se_kernel<<<nb, 256, (b.c_mid + b.c_se) * sizeof(float), st>>>(
-                h->d_pool, fused_shape_of(fl.shape).nbands, 1.f / (float)(b.h_out * b.h_out), P + b.w_se1, P + b.b_se1,
-                P + b.w_se2, P + b.b_se2, h->d_gate, h->d_gate_h, b.c_mid, b.c_se);
-          }
-          MC_CHECK_LAUNCH();
-          h->launches++;
-          goto project;
+        h->launches++;
+        {
+          ProfScope ps(h, 3 + 4 * (int)bi, st);
+          se_kernel<<<nb, 256, (b.c_mid + b.c_se) * sizeof(float), st>>>(
+              h->d_pool, fused_shape_of(fl.shape, (int)sizeof(T)).nbands, 1.f / (float)(b.h_out * b.h_out), P + b.w_se1,
+              P + b.b_se1, P + b.w_se2, P + b.b_se2, h->d_gate, h->d_gate_h, b.c_mid, b.c_se);
         }
+        MC_CHECK_LAUNCH();
+        h->launches++;
+        if ((rc = debug_sync(2 + 4 * (int)bi, st))) return rc;
+        goto project;
       }
       if (b.expand != 1) {
         ProfScope ps(h, 1 + 4 * (int)bi, st);
@@ -539,7 +539,9 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
   // convs run on the tcgen05 kernel; default: all of them.  Bring-up / bisecting aid only.
   unsigned long long tc_mask = ~0ull;
   if (const char* env = getenv("MC_TC_MASK")) tc_mask = strtoull(env, nullptr, 16);
-  if (const char* env = getenv("MC_FUSE_MASK")) h->fuse_mask = (unsigned)strtoul(env, nullptr, 16);   // WIP, default off
+  // MC_FUSE_MASK (hex, bit b = block b): which MBConv blocks run expand + depthwise as one kernel (mbconv_fused.cuh)
+  h->fuse_mask = MC_FUSE_DEFAULT;
+  if (const char* env = getenv("MC_FUSE_MASK")) h->fuse_mask = (unsigned)strtoul(env, nullptr, 16);
   if ((rc = pw_tc_build(&h->tc, h->net, params, h->d_params, mode, max_batch, device, (unsigned)(tc_mask & 0xffffffffu),
                         (unsigned)(tc_mask >> 32)))) {
     mc_extractor_destroy(h);
@@ -548,6 +550,16 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
   memcpy(h->stem.w, params + h->net.w_stem, sizeof(h->stem.w));
   memcpy(h->stem.scale, params + h->net.s_stem, sizeof(h->stem.scale));
   memcpy(h->stem.bias, params + h->net.b_stem, sizeof(h->stem.bias));
+  h->fused.resize(h->net.blocks.size());
+  for (size_t bi = 0; bi < h->net.blocks.size(); ++bi) {
+    const BlockCfg& b = h->net.blocks[bi];
+    if (b.expand != 1 && ((h->fuse_mask >> bi) & 1u) &&
+        (rc = fused_plan_layer(&h->fused[bi], mode == MC_MODE_FP32, b.k, b.stride, b.c_in, b.c_mid, b.h_in, params + b.w_exp,
+                               params + b.s_exp))) {
+      mc_extractor_destroy(h);
+      return rc;
+    }
+  }
   h->dw.resize(h->net.blocks.size());
   for (size_t bi = 0; bi < h->net.blocks.size(); ++bi) {
     const BlockCfg& b = h->net.blocks[bi];
@@ -567,6 +579,8 @@ int mc_extractor_destroy(mc_extractor* h) {
   if (!h) return MC_OK;
   DeviceGuard g(h->device);
   pw_tc_free(h->tc);
+  host_pipe_free(h->pipe);
+  for (auto& fl : h->fused) fused_free(fl);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   void* ptrs[] = {h->d_params, h->d_lut, h->bufX, h->bufY,    h->bufE, h->bufD,
                   h->bufH,     h->d_pool, h->d_gate, h->d_gate_h, h->d_images, h->d_points, h->d_img, h->d_feats};
@@ -943,5 +957,6 @@ int64_t mc_head_launches(const mc_head* h) { return h ? h->launches : 0; }
 
 }  // extern "C"
 
+#include "host_pipe.inl"
 #include "mlp_api.inl"
 #include "calib_api.inl"

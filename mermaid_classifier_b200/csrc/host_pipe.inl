@@ -24,6 +24,7 @@ struct HostPipe {
     uint8_t* pinned = nullptr;     // staging for pageable sources
     int64_t cap_pinned = 0;
     uint8_t* tab_host = nullptr;   // pinned: [mc_image table | mc_point table] of the group
+    int64_t cap_tab_host = 0;
     uint8_t* tab_dev = nullptr;
     int64_t cap_tab = 0;
     float* d_feats = nullptr;
@@ -180,13 +181,9 @@ extern "C" int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_i
     }
     // the pinned table / staging buffers are rewritten by the host: the slot's previous H2D must have finished
     if (s.used) MC_CUDA(cudaEventSynchronize(s.copied));
-    {
-      int64_t cap = s.tab_host ? s.cap_tab : 0;   // tab_host mirrors tab_dev's capacity
-      if (!s.tab_host || cap < tab_bytes || s.cap_tab != cap) {
-        if (s.tab_host) cudaFreeHost(s.tab_host);
-        s.tab_host = nullptr;
-        MC_CUDA(cudaHostAlloc((void**)&s.tab_host, (size_t)s.cap_tab, cudaHostAllocDefault));
-      }
+    if ((rc = pinned_grow(&s.tab_host, &s.cap_tab_host, tab_bytes))) {
+      restore();
+      return rc;
     }
     mc_image* t_im = reinterpret_cast<mc_image*>(s.tab_host);
     mc_point* t_pt = reinterpret_cast<mc_point*>(s.tab_host + (ims.size() * sizeof(mc_image) + 15) / 16 * 16);

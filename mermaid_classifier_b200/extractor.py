@@ -168,6 +168,66 @@ class EfficientNetExtractor:
                 out.ctypes.data, _lib.stream_ptr()))
         return out
 
+    def extract_many(self, images: Sequence[Any], rowcols_list: Sequence[Sequence[tuple[int, int]]], head: Any = None,
+                     out: np.ndarray | None = None, labels_out: np.ndarray | None = None, want_features: bool = True):
+        """A list of host images + their rowcols through ``mc_extract_images_host``: the per-image loop of
+        ``process_source`` (``scripts/build_feature_bucket.py:749-788``) as ONE call.  The library copies image
+        ``i+1`` while it convolves image ``i`` and reads the features of image ``i-1`` back (pinned staging ring,
+        copy streams); with ``head`` (a :class:`~mermaid_classifier_b200.inference.DeviceHead`) the labels of every
+        point come back too (extract + classify, ``pyspacer/annotation.py:235-251``).
+
+        ``images``: HxWx3 uint8 NumPy arrays or CPU torch tensors (pinned tensors are DMA'd without a staging copy).
+        Returns ``(features, labels)``: ``(n, 1280) float32`` rows in image order then rowcol order (``None`` when
+        ``want_features`` is false), ``(n,) int32`` class indices (``None`` without a head)."""
+        h = self._ensure_handle()
+        torch = _lib.require_cuda()
+        if len(images) != len(rowcols_list):
+            raise ValueError("images and rowcols_list differ in length")
+        keep = []   # keep the arrays alive for the duration of the call
+        tab = (_lib.McImage * max(len(images), 1))()
+        pts = []
+        for i, (im, rcs) in enumerate(zip(images, rowcols_list)):
+            if hasattr(im, "data_ptr"):   # torch CPU tensor
+                if im.is_cuda or im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or im.stride(2) != 1 or im.stride(1) != 3:
+                    raise ValueError("torch images must be CPU uint8 HxWx3 tensors with packed pixels")
+                tab[i] = _lib.McImage(im.data_ptr(), im.shape[0], im.shape[1], im.stride(0))
+                keep.append(im)
+            else:
+                arr = _as_hwc_u8(im)
+                tab[i] = _lib.McImage(arr.ctypes.data, arr.shape[0], arr.shape[1], arr.strides[0])
+                keep.append(arr)
+            rc = np.asarray(rcs, dtype=np.int32).reshape(-1, 2)
+            pts.append(np.concatenate([np.full((rc.shape[0], 1), i, dtype=np.int32), rc], axis=1))
+        pts = np.ascontiguousarray(np.concatenate(pts, axis=0)) if pts else np.zeros((0, 3), dtype=np.int32)
+        n = pts.shape[0]
+        feats = None
+        if want_features:
+            feats = out if out is not None else np.empty((n, self.feature_dim), dtype=np.float32)
+            if feats.shape != (n, self.feature_dim) or feats.dtype != np.float32 or not feats.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous (n, 1280) float32 array")
+        labels = None
+        if head is not None:
+            labels = labels_out if labels_out is not None else np.empty((n,), dtype=np.int32)
+            if labels.shape != (n,) or labels.dtype != np.int32:
+                raise ValueError("labels_out must be an (n,) int32 array")
+        if not want_features and head is None:
+            raise ValueError("nothing to compute: want_features is false and no head was given")
+        if n == 0:
+            return feats, labels
+        with torch.cuda.device(self._device_index):
+            _lib.check(_lib.load().mc_extract_images_host(
+                h, head._h if head is not None else None, C.addressof(tab), len(images), pts.ctypes.data, n,
+                feats.ctypes.data if feats is not None else None, labels.ctypes.data if labels is not None else None,
+                _lib.stream_ptr()))
+        del keep
+        return feats, labels
+
+    def pipe_stats(self) -> dict:
+        """Bytes moved by the last :meth:`extract_many` call (``h2d``, ``d2h``) and its image ``groups``."""
+        a, b, g = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().mc_extractor_pipe_stats(self._ensure_handle(), C.byref(a), C.byref(b), C.byref(g)))
+        return {"h2d": a.value, "d2h": b.value, "groups": g.value}
+
     def patches_to_features(self, patch_list: Sequence[Any]):
         """Pre-cropped 224x224x3 patches -> ``(list[list[float]], loaded_remote)``."""
         feats = self.patches_to_array(patch_list)
