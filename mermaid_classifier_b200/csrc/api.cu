@@ -125,6 +125,7 @@ struct mc_extractor {
   HostPipe* pipe = nullptr;        // mc_extract_images_host
   int64_t launches = 0;
   int64_t l2_budget = 0;  // bytes of per-chunk working set kept L2-resident (0 = no chunking)
+  bool no_pool_fusion = false;   // MC_NO_POOL_FUSION: head conv and average pool as two launches (A/B timing)
   int tap_layer = -1;
   float* tap_out = nullptr;
   int64_t tap_cap = 0;
@@ -280,7 +281,6 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
   T* Y = (T*)h->bufY;
   T* E = (T*)h->bufE;
   T* D = (T*)h->bufD;
-  T* Hb = (T*)h->bufH;
   int rc;
   {
     ProfScope ps(h, 0, st);
@@ -373,6 +373,22 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
     std::swap(X, Y);
   }
   const int64_t Mh = (int64_t)nb * 49;
+  // K7: head conv + BN + swish + global average pool in ONE launch (pw_tc_kernel POOL instantiation): the 49 x 1280 map
+  // per patch never reaches HBM.  The two-launch form (conv to bufH, then avgpool_kernel) only remains for the layer-65
+  // tap and for MC_TC_MASK bisecting with the CUDA-core GEMM; bufH is allocated on first use.
+  const bool want_map = (h->tap_layer == 65 && h->tap_out != nullptr) || !(h->tc && pw_tc_has(h->tc, 32)) || h->no_pool_fusion;
+  if (!want_map) {
+    ProfScope ps_head(h, 65, st);
+    if ((rc = pw_tc_run_pool(h->tc, 32, X, nb, feats_dev, st))) return rc;
+    h->launches++;
+    return debug_sync(65, st);
+  }
+  if (!h->bufH) {
+    const size_t es = h->mode == MC_MODE_FP32 ? 4 : 2;
+    cudaError_t e = cudaMalloc(&h->bufH, (size_t)h->max_batch * 49 * 1280 * es);
+    if (e != cudaSuccess) return fail(MC_ERR_NOMEM, std::string("cudaMalloc head-conv map: ") + cudaGetErrorString(e));
+  }
+  T* Hb = (T*)h->bufH;
   {
     ProfScope ps_head(h, 65, st);
     if (h->tc && pw_tc_has(h->tc, 32)) {
@@ -517,7 +533,6 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
       (rc = dmalloc((void**)&h->d_lut, sizeof(lut))) ||
       (rc = dmalloc(&h->bufX, nb * net.max_in_out * es)) || (rc = dmalloc(&h->bufY, nb * net.max_in_out * es)) ||
       (rc = dmalloc(&h->bufE, nb * net.max_mid * es)) || (rc = dmalloc(&h->bufD, nb * net.max_dw * es)) ||
-      (rc = dmalloc(&h->bufH, nb * 49 * 1280 * es)) ||
       (rc = dmalloc((void**)&h->d_pool, nb * MAX_BANDS * net.max_c_mid * sizeof(float))) ||
       (rc = dmalloc((void**)&h->d_gate, nb * net.max_c_mid * sizeof(float))) ||
       (mode == MC_MODE_BF16 && (rc = dmalloc((void**)&h->d_gate_h, nb * net.max_c_mid * sizeof(__nv_bfloat16))))) {
@@ -540,6 +555,7 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
   unsigned long long tc_mask = ~0ull;
   if (const char* env = getenv("MC_TC_MASK")) tc_mask = strtoull(env, nullptr, 16);
   // MC_FUSE_MASK (hex, bit b = block b): which MBConv blocks run expand + depthwise as one kernel (mbconv_fused.cuh)
+  h->no_pool_fusion = getenv("MC_NO_POOL_FUSION") != nullptr;
   h->fuse_mask = MC_FUSE_DEFAULT;
   if (const char* env = getenv("MC_FUSE_MASK")) h->fuse_mask = (unsigned)strtoul(env, nullptr, 16);
   if ((rc = pw_tc_build(&h->tc, h->net, params, h->d_params, mode, max_batch, device, (unsigned)(tc_mask & 0xffffffffu),

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <atomic>
 #include <string>
@@ -124,6 +125,32 @@ template <>
 __device__ __forceinline__ float from_f<float>(float x) { return x; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// 3xTF32 split of an fp32 value a (bit pattern `bits`): hi = a truncated to TF32 (what the tensor core reads when it is
+// handed the raw fp32: it ignores the low 13 mantissa bits), lo = a - hi, exact in fp32 with up to 13 significant bits.
+// The tensor core would TRUNCATE lo to TF32's 11 bits as well -- a bias toward zero of up to 2^-21 |a| on every product;
+// rounding lo to nearest TF32 here halves that error and removes its sign.
+#ifndef MC_TF32_LO_RN
+#define MC_TF32_LO_RN 1
+#endif
+__host__ __device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t bits) {
+#ifdef __CUDA_ARCH__
+  const float lo = __uint_as_float(bits) - __uint_as_float(bits & 0xFFFFE000u);
+  uint32_t lb = __float_as_uint(lo);
+#else
+  float a, h;
+  const uint32_t hb = bits & 0xFFFFE000u;
+  memcpy(&a, &bits, 4);
+  memcpy(&h, &hb, 4);
+  const float lo = a - h;
+  uint32_t lb;
+  memcpy(&lb, &lo, 4);
+#endif
+#if MC_TF32_LO_RN
+  lb = (lb + 0x1000u) & 0xFFFFE000u;
+#endif
+  return lb;
+}
 
 // NumPy mode='reflect' index (periodic mirror without repeating the edge sample).
 __device__ __forceinline__ int reflect_idx(int t, int n) {

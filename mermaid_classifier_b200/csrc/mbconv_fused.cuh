@@ -372,10 +372,10 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
               for (int j = 0; j < NCH; ++j) {
                 uint4 lo;
-                lo.x = __float_as_uint(__uint_as_float(raw[j].x) - __uint_as_float(raw[j].x & 0xFFFFE000u));
-                lo.y = __float_as_uint(__uint_as_float(raw[j].y) - __uint_as_float(raw[j].y & 0xFFFFE000u));
-                lo.z = __float_as_uint(__uint_as_float(raw[j].z) - __uint_as_float(raw[j].z & 0xFFFFE000u));
-                lo.w = __float_as_uint(__uint_as_float(raw[j].w) - __uint_as_float(raw[j].w & 0xFFFFE000u));
+                lo.x = tf32_lo_bits(raw[j].x);
+                lo.y = tf32_lo_bits(raw[j].y);
+                lo.z = tf32_lo_bits(raw[j].z);
+                lo.w = tf32_lo_bits(raw[j].w);
                 ptx::sts128(lo0 + (uint32_t)((j >> 3) * A_TILE) + ((((uint32_t)j & 7u) ^ xr) << 4), lo);
               }
             }
@@ -536,13 +536,15 @@ inline int fused_plan_layer(FusedLayer* l, bool f32, int K, int S, int Cin, int 
     for (int c = 0; c < C; ++c)
       for (int k = 0; k < Cin; ++k) {
         const float wf = w_host[(size_t)c * Cin + k] * scale_host[c];
-        uint32_t bits;
+        uint32_t bits, bits0;
         memcpy(&bits, &wf, 4);
+        bits0 = bits;
         bits &= 0xFFFFE000u;
         float h;
         memcpy(&h, &bits, 4);
         hi[(size_t)c * Cin + k] = h;
-        lo[(size_t)c * Cin + k] = wf - h;
+        const uint32_t lb = tf32_lo_bits(bits0);
+        memcpy(&lo[(size_t)c * Cin + k], &lb, 4);
       }
     MC_CUDA(cudaMalloc(&l->d_w, n * 4));
     MC_CUDA(cudaMalloc(&l->d_wlo, n * 4));

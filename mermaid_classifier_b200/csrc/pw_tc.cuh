@@ -262,7 +262,13 @@ struct PwTcArgs {
   int w_res;          // 1: the layer's whole weight (all n-blocks x k-chunks, hi+lo) stays resident in smem
   int a_row_off;      // first row of this launch inside the activation tensor map (chunked execution)
   int64_t m_tiles;
+  int pool_nb;        // POOL instantiation: patches in this launch (a work item's 128-row tile = two 49-row patches)
 };
+
+// POOL instantiation (head conv + global average pool, K7): rows of a patch's 7x7 map per tile half, and the shared
+// memory the four epilogue groups use to combine the column sums of their warps
+constexpr int TC_POOL_HW = 49;
+constexpr int TC_POOL_BYTES = TC_EPI_GROUPS * 4 * 128 * 4;
 
 template <typename T>
 struct TcCfg;
@@ -319,7 +325,12 @@ inline int tc_num_stages_res(int w_bytes) {
 // RELU: a separate instantiation for the MLP-head Linear layers.  The conv instantiations must not even carry the
 // (never taken) ReLU branch: b1.expand sits on a scheduling knife-edge between 4.7 and 3.1 TB/s, and that branch alone
 // tipped it (measured, round 1).
-template <typename T, bool GATED, bool RELU = false>
+// POOL: the head conv with the global average pool in its epilogue (K7).  A work item's 128-row tile holds TWO patches:
+// rows 0..48 = the 7x7 map of patch 2t, rows 64..112 = patch 2t+1 (two TMA boxes of 49 rows; a patch starts on a warp
+// boundary of the epilogue, the other rows of the tile are never read back).  The epilogue applies BN + swish, sums each
+// column over the patch's 49 rows in a fixed order (in-thread, lane shuffles, then the two warps of the patch through
+// shared memory) and writes mean features [patch][N] in fp32: the 49 x 1280 map per patch never exists in global memory.
+template <typename T, bool GATED, bool RELU = false, bool POOL = false>
 __global__ void __launch_bounds__(tc_threads<GATED>(), 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmWlo, const PwTcArgs p) {
@@ -337,7 +348,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* w_base = smem;                                      // resident weights (1024-aligned tiles), may be empty
   uint8_t* stage_base = smem + W_RES_BYTES;
   uint8_t* epi_base = stage_base + (size_t)S * STAGE_BYTES;
-  float* sc_s = (float*)(epi_base + TC_EPI_BYTES);
+  float* pool_s = (float*)epi_base;                            // POOL: [group][warp of the group][128 columns]
+  float* sc_s = (float*)(epi_base + TC_EPI_BYTES + (POOL ? TC_POOL_BYTES : 0));
   float* bi_s = sc_s + 1280;
   uint64_t* bars = (uint64_t*)(bi_s + 1280);
   uint64_t* full = bars;                          // [S]   TMA landed
@@ -425,8 +437,15 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           w_empty += ptx::mbar_wait_timed(&empty[s], ph ^ 1);
           uint8_t* st = stage_base + (size_t)s * STAGE_BYTES;
-          ptx::mbar_expect_tx(&full[s], tx);
-          ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, m0);
+          if constexpr (POOL) {
+            // two patches: rows [0, 49) and [64, 113) of the tile (tmA's box is 49 rows)
+            ptx::mbar_expect_tx(&full[s], tx - (uint32_t)Cfg::A_BYTES + 2u * TC_POOL_HW * 128u);
+            ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, (int)mt * 2 * TC_POOL_HW);
+            ptx::tma_load_2d(st + 64 * 128, &tmA, &full[s], kc * Cfg::KC, ((int)mt * 2 + 1) * TC_POOL_HW);
+          } else {
+            ptx::mbar_expect_tx(&full[s], tx);
+            ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, m0);
+          }
           if (!w_res) {
             if (Cfg::TF32) {
               ptx::tma_load_2d(st + 2 * Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
@@ -582,9 +601,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               uint32_t* lp = &lo.x;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const uint32_t hbits = __float_as_uint(v[e]) & 0xFFFFE000u;  // exact TF32 value
-                hp[e] = hbits;
-                lp[e] = __float_as_uint(v[e] - __uint_as_float(hbits));      // exact remainder
+                hp[e] = __float_as_uint(v[e]) & 0xFFFFE000u;   // exact TF32 value
+                lp[e] = tf32_lo_bits(__float_as_uint(v[e]));     // remainder, rounded to TF32
               }
               if (gated) ptx::sts128(phys, hi);
               ptx::sts128(phys + Cfg::A_BYTES, lo);
@@ -630,10 +648,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint4 lo = make_uint4(0u, 0u, 0u, 0u);   // zero-filled K tail: the lo copy must be zero too
             if (j < nch && !(p.exp_flags & 4)) {
               const uint4 raw = ptx::lds128(phys);
-              lo.x = __float_as_uint(__uint_as_float(raw.x) - __uint_as_float(raw.x & 0xFFFFE000u));
-              lo.y = __float_as_uint(__uint_as_float(raw.y) - __uint_as_float(raw.y & 0xFFFFE000u));
-              lo.z = __float_as_uint(__uint_as_float(raw.z) - __uint_as_float(raw.z & 0xFFFFE000u));
-              lo.w = __float_as_uint(__uint_as_float(raw.w) - __uint_as_float(raw.w & 0xFFFFE000u));
+              lo.x = tf32_lo_bits(raw.x);
+              lo.y = tf32_lo_bits(raw.y);
+              lo.z = tf32_lo_bits(raw.z);
+              lo.w = tf32_lo_bits(raw.w);
+              if (p.exp_flags & 8)   // experiment: write the truncated hi operand explicitly instead of leaving the raw fp32 in place
+                ptx::sts128(phys, make_uint4(raw.x & 0xFFFFE000u, raw.y & 0xFFFFE000u, raw.z & 0xFFFFE000u, raw.w & 0xFFFFE000u));
             }
             ptx::sts128(phys + Cfg::A_BYTES, lo);
           }
@@ -679,6 +699,79 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // restrict: the residual (block input) never aliases the output, so its loads may be hoisted above earlier stores
       T* __restrict__ out_t = (T*)p.out + m_warp * (int64_t)p.N + n0;
       const T* __restrict__ res_t = p.res != nullptr ? (const T*)p.res + m_warp * (int64_t)p.N + n0 : nullptr;
+      if constexpr (POOL) {
+        // rows of this warp: patch 2 mt + quarter / 2, rows (quarter & 1) * 32 .. + 31 of its 49
+        const int patch = (int)mt * 2 + (quarter >> 1);
+        const int local0 = (quarter & 1) * 32;
+        const bool patch_ok = patch < p.pool_nb;
+        float* my_pool = pool_s + (eg * 4 + quarter) * 128;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t v[2][16];
+          ptx::tmem_ld16x256b_x4(taddr + (uint32_t)c0, v[0]);
+          ptx::tmem_ld16x256b_x4(taddr + (16u << 16) + (uint32_t)c0, v[1]);
+          ptx::tmem_ld_wait();
+          // thread (lr, q): columns 8 i + 2 q + {0, 1} of the group for i = 0..3, rows lr, lr + 8, lr + 16, lr + 24
+          float cs[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 s2 = *reinterpret_cast<const float2*>(sc_s + n0 + c0 + 8 * i + 2 * q);
+            const float2 b2 = *reinterpret_cast<const float2*>(bi_s + n0 + c0 + 8 * i + 2 * q);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+              for (int rh = 0; rh < 2; ++rh) {
+                const int row = 16 * h2 + 8 * rh + lr;
+                float y0 = fmaf(__uint_as_float(v[h2][4 * i + 2 * rh]), s2.x, b2.x);
+                float y1 = fmaf(__uint_as_float(v[h2][4 * i + 2 * rh + 1]), s2.y, b2.y);
+                if (Cfg::TF32 || !MC_BF16_TANH) {
+                  y0 = __fdividef(y0, 1.f + __expf(-y0));
+                  y1 = __fdividef(y1, 1.f + __expf(-y1));
+                } else {
+                  y0 = fmaf(y0, ptx::tanh_approx(y0), y0);
+                  y1 = fmaf(y1, ptx::tanh_approx(y1), y1);
+                }
+                if (local0 + row < TC_POOL_HW) {   // rows past the patch's 49 hold stale shared memory: never summed
+                  a0 += y0;
+                  a1 += y1;
+                }
+              }
+            cs[2 * i] = a0;
+            cs[2 * i + 1] = a1;
+          }
+          // fixed-order tree over the eight row groups lr (lane bits 2..4)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 4);
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+          }
+          if (lr == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float2*>(my_pool + c0 + 8 * i + 2 * q) = make_float2(cs[2 * i], cs[2 * i + 1]);
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty[as]);
+        // the two warps of a patch combine; thread t of the group owns column t of both patches
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
+        {
+          const int t = quarter * 32 + lane;
+          if (t < ncols) {
+            const float* gp = pool_s + eg * 4 * 128 + t;
+            const float inv = 1.f / (float)TC_POOL_HW;
+            float* feats = (float*)p.out;
+            const int pa = (int)mt * 2;
+            if (pa < p.pool_nb) feats[(int64_t)pa * p.N + n0 + t] = (gp[0] + gp[128]) * inv;
+            if (pa + 1 < p.pool_nb) feats[(int64_t)(pa + 1) * p.N + n0 + t] = (gp[256] + gp[384]) * inv;
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
+        (void)patch_ok;
+        t_work += ptx::tc_clock() - t_item;
+        continue;
+      }
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         // both 16-lane halves in flight before the single wait: the tcgen05.ld round trip is the longest
         // latency of the epilogue (serialising the halves cost 40 % on the expand layers)
@@ -809,6 +902,9 @@ struct PwTcLayer {
   const void* a_ptr[2] = {nullptr, nullptr};
   int64_t a_rows[2] = {0, 0};
   CUtensorMap tmA[2];
+  // POOL launch (head conv): map with a 49-row box over the same buffer
+  const void* apool_ptr = nullptr;
+  CUtensorMap tmApool;
 };
 
 struct PwTcPlan {
@@ -859,11 +955,10 @@ inline int pw_tc_add(PwTcPlan* plan, int id, const float* w_host, const float* d
     for (size_t i = 0; i < n; ++i) {
       uint32_t bits;
       memcpy(&bits, &w_host[i], 4);
+      const uint32_t lb = tf32_lo_bits(bits);
       bits &= 0xFFFFE000u;
-      float h;
-      memcpy(&h, &bits, 4);
-      hi[i] = h;
-      lo[i] = w_host[i] - h;
+      memcpy(&hi[i], &bits, 4);
+      memcpy(&lo[i], &lb, 4);
     }
     MC_CUDA(cudaMalloc(&l.d_w, n * 4));
     MC_CUDA(cudaMalloc(&l.d_wlo, n * 4));
@@ -901,6 +996,8 @@ inline int pw_tc_build(PwTcPlan** out, const NetCfg& net, const float* params_ho
     MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
     MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
   }
+  if (f32) MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+  else MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
   auto enabled = [&](int id) { return id < 32 ? ((layer_mask_lo >> id) & 1u) != 0 : ((layer_mask_hi >> (id - 32)) & 1u) != 0; };
   int rc = MC_OK;
   for (size_t bi = 0; bi < net.blocks.size() && rc == MC_OK; ++bi) {
@@ -950,7 +1047,9 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   a.out = outp;
   a.M = M;
   a.a_row_off = (int)a_row_off;
-  static const int exp_flags = getenv("MC_TC_EXP") ? atoi(getenv("MC_TC_EXP")) : 0;
+  a.pool_nb = 0;
+  const char* exp_env = getenv("MC_TC_EXP");   // read per launch: experiments switch it inside one process
+  const int exp_flags = exp_env ? atoi(exp_env) : 0;
   a.exp_flags = exp_flags;
   // MC_TC_DBG=<layer id>: after that layer's launch, print CTA 0's per-role wait/total cycles (synchronises)
   static const int dbg_layer = getenv("MC_TC_DBG") ? atoi(getenv("MC_TC_DBG")) : -1;
@@ -1011,6 +1110,46 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
       fprintf(stderr, "\n");
     }
   }
+  return MC_OK;
+}
+
+// Head conv + global average pool in one launch (the POOL instantiation): A = block output [nb * 49][K], feats = [nb][N] fp32.
+inline int pw_tc_run_pool(PwTcPlan* plan, int id, const void* A, int nb, float* feats, cudaStream_t st) {
+  PwTcLayer& l = plan->layers[id];
+  const bool f32 = plan->mode == MC_MODE_FP32;
+  if (l.apool_ptr != A) {
+    int rc = make_map(&l.tmApool, f32, A, (int64_t)plan->max_batch * TC_POOL_HW, l.K, TC_POOL_HW);
+    if (rc) return rc;
+    l.apool_ptr = A;
+  }
+  PwTcArgs a;
+  a.scale = l.scale;
+  a.bias = l.bias;
+  a.gate = nullptr;
+  a.res = nullptr;
+  a.out = feats;
+  a.M = (int64_t)nb * TC_POOL_HW;
+  a.a_row_off = 0;
+  a.exp_flags = 0;
+  a.dbg = nullptr;
+  a.N = l.N;
+  a.K = l.K;
+  a.HW = TC_POOL_HW;
+  a.BN = l.BN;
+  a.n_blocks = l.n_blocks;
+  a.k_chunks = l.k_chunks;
+  a.act = l.act;
+  a.w_res = 0;
+  a.pool_nb = nb;
+  const int stage_bytes = f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN);
+  a.stages = std::min(TC_MAX_STAGES, (TC_SMEM_BUDGET - TC_FIXED_BYTES - TC_POOL_BYTES) / stage_bytes);
+  const size_t smem = TC_FIXED_BYTES + TC_POOL_BYTES + (size_t)a.stages * stage_bytes;
+  a.m_tiles = (nb + 1) / 2;
+  const int64_t items = a.m_tiles * a.n_blocks;
+  const int grid = (int)std::min<int64_t>(items, plan->num_sms);
+  if (f32) pw_tc_kernel<float, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, a);
+  else pw_tc_kernel<__nv_bfloat16, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, a);
+  MC_CHECK_LAUNCH();
   return MC_OK;
 }
 

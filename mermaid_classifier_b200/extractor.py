@@ -214,6 +214,8 @@ class EfficientNetExtractor:
             raise ValueError("nothing to compute: want_features is false and no head was given")
         if n == 0:
             return feats, labels
+        if head is not None:
+            head._set_exact(False)   # labels: the tensor-core Linear chain, as DeviceHead.scores_device
         with torch.cuda.device(self._device_index):
             _lib.check(_lib.load().mc_extract_images_host(
                 h, head._h if head is not None else None, C.addressof(tab), len(images), pts.ctypes.data, n,

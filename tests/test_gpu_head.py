@@ -95,3 +95,23 @@ def test_tensor_core_chain_matches_exact_chain(hidden):
         assert np.max(np.abs(fast["proba"].cpu().numpy() - want)) <= 1e-5
         assert (fast["labels"].cpu().numpy() == want.argmax(1)).mean() >= 0.999
         assert (fast["labels"] == exact["labels"]).float().mean().item() >= 0.999
+
+
+def test_saturated_rows_and_steep_platt_slopes():
+    """Confident rows (softmax p -> 1) with steep Platt slopes |a| ~ 10-20: the exact chain must hold the reference's 1e-6
+    export gate there too (the library is built without --use_fast_math: expf / division in the head are IEEE)."""
+    rng = np.random.default_rng(7)
+    K, D = 40, 64
+    w = [torch.from_numpy(rng.normal(0, 0.6, (K, D)).astype(np.float32))]
+    bb = [torch.from_numpy(rng.normal(0, 0.1, (K,)).astype(np.float32))]
+    a = torch.from_numpy(-rng.uniform(10, 20, K).astype(np.float32))
+    b = torch.from_numpy(rng.uniform(0, 6, K).astype(np.float32))
+    X = rng.normal(0, 1, (4000, D)).astype(np.float32)
+    X[::3] *= 6.0   # a third of the rows saturate the softmax
+    want = ohead.calibrated_proba(X, w, bb, a, b)
+    assert (ohead.softmax_proba(X, w, bb).max(1) > 0.999).mean() > 0.2
+    head = DeviceHead([x.numpy() for x in w], [x.numpy() for x in bb], a.numpy(), b.numpy())
+    proba, labels = head.scores_host(X)
+    assert np.max(np.abs(proba - want)) <= 1e-6
+    assert np.abs(proba.sum(1) - 1).max() <= 1e-5
+    assert (labels == want.argmax(1)).mean() >= 0.999
