@@ -11,8 +11,12 @@ synthetic checkpoint (`synth.synth_backbone_state_dict`).
 
 Numbers on the JSON line
   value     : whole-job point-patches/s with every input already resident in HBM.
-  e2e       : the same workload through the host-buffer path: every step copies every image from
-              pinned host memory to the device, and copies features + labels back.
+  e2e       : the same workload through the PRODUCT's host-buffer call -- EfficientNetExtractor.extract_many ->
+              mc_extract_images_host (pinned staging ring + copy streams inside the library): every step copies
+              every image from pinned host memory to the device and copies features + labels back.
+  c3_bf16 / c4_scoring / c5_train_dp : bounded runs of BASELINE configs 3-5 on the same GPUs (bf16 bucket
+              extraction, 10 M-feature scoring sharded by rows, MLP-head training with the NCCL gradient
+              all-reduce at N > 1).
   roofline  : the dominant kernel, timed with CUDA events on the launching stream during the
               timed steps, against the measured HBM peak in MEASURED_PEAKS.json.
   cpu_baseline : the oracle (CPU restatement of the pyspacer path) on a bounded sample of the
@@ -171,17 +175,21 @@ def cpu_reference_run(n_images: int, n_points: int, warmup_images: int = 1, batc
         x = torch.from_numpy(ocrop.normalize_patches(np.stack(patches)))
         feats = oeff.extract_features_batched(sd, x, batch_size).numpy()
         proba = ohead.calibrated_proba(feats, w, bb, a, b)
-        _ = proba.argmax(1)
-        return time.perf_counter() - t0, len(pts)
+        labels = proba.argmax(1)
+        return time.perf_counter() - t0, len(pts), labels, feats
 
     for i in range(warmup_images):
         one(10_000 + i)
     t, n = 0.0, 0
+    all_labels, all_feats = [], []
     for i in range(n_images):
-        dt, k = one(i)
+        dt, k, lab, ft = one(i)
         t += dt
         n += k
+        all_labels.append(lab)
+        all_feats.append(ft)
     return {"value": n / t, "unit": "point-patches/s", "cores": cores, "kind": "port",
+            "labels": np.concatenate(all_labels), "features": np.concatenate(all_feats),
             "sample": f"{n_images} synthetic {W_IMG}x{H_IMG} images x {n_points} points, batch {batch_size}, "
                       f"torch {torch.get_num_threads()} threads (image synthesis untimed)",
             "seconds": t, "patches": n}
@@ -290,8 +298,21 @@ def run_b200(args, rank: int, world: int, local: int):
     _lib.check(lib.mc_extractor_profile_read(h, ms_dom.ctypes.data, cnt_dom.ctypes.data, 1))
     _lib.check(lib.mc_extractor_profile(h, -1))
 
-    # ---- timed: end to end from pinned host memory -----------------------------------------------
+    # ---- timed: end to end from pinned host memory, through the product's host-buffer call --------------
     e2e = run_e2e(args, ext, head, pts_per_img, images, dev, barrier)
+    first_labels = labels[: args.cpu_images * n_pts].cpu().numpy() if rank == 0 else None
+    first_feats = feats[: args.cpu_images * n_pts].cpu().numpy() if rank == 0 else None
+
+    # ---- BASELINE configs 3-5 (bounded) -------------------------------------------------------------------
+    sub = {}
+    if not args.no_sub:
+        sub["c3_bf16"] = run_c3(args, sd, head, pts_per_img, e2e["host"], images, dev, barrier, rank, world, local)
+    del images
+    e2e.pop("host")
+    torch.cuda.empty_cache()
+    if not args.no_sub:
+        sub["c4_scoring"] = run_c4(args, dev, barrier, rank, world, local)
+        sub["c5_train_dp"] = run_c5(args, dev, barrier, rank, world, local)
 
     # ---- aggregate over ranks (max time) ------------------------------------------------------------
     t = torch.tensor([ms_total, e2e["ms_total"]], dtype=torch.float64, device=dev)
@@ -337,7 +358,9 @@ def run_b200(args, rank: int, world: int, local: int):
             "weights": "synthetic seeded EfficientNet-B0 checkpoint (pyspacer layout), synthetic head",
         },
         "e2e": {"value": e2e_value, "unit": "point-patches/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                "ms_per_step": ms_e2e / args.steps, "host_pool_images": e2e["pool"], "images_per_group": e2e["group"]},
+                "ms_per_step": ms_e2e / args.steps, "host_pool_images": e2e["pool"], "images_per_group": e2e["group"],
+                "api": "EfficientNetExtractor.extract_many -> mc_extract_images_host (one call per step)",
+                "labels_checksum": e2e["labels_checksum"]},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -348,58 +371,41 @@ def run_b200(args, rank: int, world: int, local: int):
                      "top_kernels_ms_per_step": [[n, round(m, 3)] for m, n in table[:8]]},
         "labels_checksum": int(labels.to(torch.int64).sum().item()),
     }
+    line.update(sub)
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_run(n_images=args.cpu_images, n_points=n_pts)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # the same images / points went through the GPU path (rank 0 holds image ids 0..): parity on the timed sample
+        err = np.abs(first_feats - cb["features"])
+        line["parity_on_cpu_sample"] = {
+            "patches": int(cb["labels"].shape[0]),
+            "labels_agreement": float((first_labels == cb["labels"]).mean()),
+            "features_max_abs": float(err.max()),
+            "features_max_abs_rel_to_row_max": float((err.max(1) / np.maximum(1.0, np.abs(cb["features"]).max(1))).max()),
+        }
     print(json.dumps(line), flush=True)
 
 
 def run_e2e(args, ext, head, pts_per_img, images_dev, dev, barrier) -> dict:
-    """Host-buffer path: every image is copied from pinned host memory each step, features and
-    labels are copied back.  Images are processed in groups (one extract call per group) on two
-    streams so the copy of group g+1 overlaps the compute of group g."""
+    """Host-buffer path through the product: ONE ``extract_many`` call per step over all images (pinned host
+    sources, cycled from a pool of distinct images), features and labels into pinned host arrays.  The library
+    groups images into sub-batches and overlaps H2D / compute / D2H on its own streams."""
     n_img = len(pts_per_img)
     pool = min(args.host_pool, n_img)
-    group = args.group
     host = [torch.empty((H_IMG, W_IMG, 3), dtype=torch.uint8).pin_memory() for _ in range(pool)]
     for i in range(pool):
         host[i].copy_(images_dev[i])  # distinct synthetic images; image i of the step uses host[i % pool]
     torch.cuda.synchronize()
-    n_slots = 3
-    stage = [[torch.empty((H_IMG, W_IMG, 3), dtype=torch.uint8, device=dev) for _ in range(group)] for _ in range(n_slots)]
-    max_pts = max(len(p) for p in pts_per_img) * group
-    feats_dev = [torch.empty((max_pts, 1280), dtype=torch.float32, device=dev) for _ in range(n_slots)]
-    feats_host = [torch.empty((max_pts, 1280), dtype=torch.float32).pin_memory() for _ in range(n_slots)]
-    labels_host = [torch.empty((max_pts,), dtype=torch.int32).pin_memory() for _ in range(n_slots)]
-    copy_stream, comp_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    copied = [torch.cuda.Event() for _ in range(n_slots)]
-    freed = [torch.cuda.Event() for _ in range(n_slots)]
-    groups = [list(range(g, min(g + group, n_img))) for g in range(0, n_img, group)]
-    gpts = [np.array([(j, r, c) for j, i in enumerate(g) for r, c in pts_per_img[i]], dtype=np.int32) for g in groups]
-    h2d = n_img * H_IMG * W_IMG * 3 + sum(p.nbytes for p in gpts)
-    d2h = sum(p.shape[0] for p in gpts) * (1280 * 4 + 4)
+    ims = [host[i % pool] for i in range(n_img)]
+    n = sum(len(p) for p in pts_per_img)
+    feats_host = torch.empty((n, 1280), dtype=torch.float32).pin_memory().numpy()
+    labels_host = torch.empty((n,), dtype=torch.int32).pin_memory().numpy()
 
     def one_step():
-        for gi, g in enumerate(groups):
-            s = gi % n_slots
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[s])
-                for j, i in enumerate(g):
-                    stage[s][j].copy_(host[i % pool], non_blocking=True)
-                copied[s].record(copy_stream)
-            with torch.cuda.stream(comp_stream):
-                comp_stream.wait_event(copied[s])
-                n = gpts[gi].shape[0]
-                ext.extract_device(stage[s][: len(g)], gpts[gi], out=feats_dev[s][:n])
-                freed[s].record(comp_stream)
-                lab = head.scores_device(feats_dev[s][:n])["labels"]
-                feats_host[s][:n].copy_(feats_dev[s][:n], non_blocking=True)
-                labels_host[s][:n].copy_(lab, non_blocking=True)
-        comp_stream.synchronize()
+        ext.extract_many(ims, pts_per_img, head=head, out=feats_host, labels_out=labels_host)
 
-    for s in range(n_slots):
-        freed[s].record(comp_stream)
-    one_step()  # warm-up
+    warm = min(n_img, 40)
+    ext.extract_many(ims[:warm], pts_per_img[:warm], head=head)  # warm-up: staging ring allocation
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -409,7 +415,179 @@ def run_e2e(args, ext, head, pts_per_img, images_dev, dev, barrier) -> dict:
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    return {"ms_total": max(e0.elapsed_time(e1), wall_ms), "h2d": int(h2d), "d2h": int(d2h), "pool": pool, "group": group}
+    st = ext.pipe_stats()
+    return {"ms_total": max(e0.elapsed_time(e1), wall_ms), "h2d": int(st["h2d"]), "d2h": int(st["d2h"]), "pool": pool,
+            "group": int(round(n_img / max(st["groups"], 1))), "host": host,
+            "labels_checksum": int(labels_host.astype(np.int64).sum())}
+
+
+def _lib_grad_size(clf) -> int:
+    from mermaid_classifier_b200 import _lib
+
+    return int(_lib.load().mc_mlp_grad_size(clf._h))
+
+
+def _max_over_ranks(ms: float, dev, world: int) -> float:
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def run_c3(args, sd, head, pts_per_img, host, images_dev, dev, barrier, rank, world, local) -> dict:
+    """BASELINE config 3 (bounded): build_feature_bucket in bf16 mode, images x 50 points sharded per image (every rank
+    its own images, no collective), features through the host-buffer call, then the bucket output -- the stacked
+    (N, 1280) float32 .npy (scripts/extract_reference_features.py:56-60) and per-image .featurevector files --
+    timed separately from the extraction."""
+    import tempfile
+
+    from mermaid_classifier_b200.extractor import EfficientNetExtractor
+    from mermaid_classifier_b200.spacer_compat import DataLocation, image_features_from_array
+
+    n_img = min(args.c3_images, len(pts_per_img))
+    rcs = [p[:50] for p in pts_per_img[:n_img]]
+    ims = [host[i % len(host)] for i in range(n_img)]
+    n = sum(len(r) for r in rcs)
+    ext = EfficientNetExtractor(state_dict=sd, mode="bf16", max_batch=args.batch, device=local)
+    try:
+        points = np.array([(i, r, c) for i, rc in enumerate(rcs) for r, c in rc], dtype=np.int32)
+        out_dev = torch.empty((n, 1280), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            ext.extract_device(images_dev[:n_img], points, out=out_dev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ext.extract_device(images_dev[:n_img], points, out=out_dev)
+        e1.record()
+        barrier()
+        ms_dev = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+        ext.extract_many(ims[:20], rcs[:20])
+        barrier()
+        t0 = time.perf_counter()
+        feats, _ = ext.extract_many(ims, rcs)
+        torch.cuda.synchronize()
+        ms_e2e = _max_over_ranks((time.perf_counter() - t0) * 1e3, dev, world)
+        launches = ext.launches
+    finally:
+        ext.close()
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.perf_counter()
+        np.save(Path(tmp) / f"features_rank{rank}.npy", feats)
+        npy_ms = (time.perf_counter() - t0) * 1e3
+        k = min(n_img, 32)
+        t0 = time.perf_counter()
+        o = 0
+        for i in range(k):
+            image_features_from_array(rcs[i], feats[o:o + len(rcs[i])]).store(
+                DataLocation("filesystem", str(Path(tmp) / f"s1/features/i{rank}_{i}.featurevector")))
+            o += len(rcs[i])
+        fv_ms = (time.perf_counter() - t0) * 1e3 / k
+    return {"workload": f"C3 (bounded): {n_img} images x 50 points per GPU, bf16 mode, sharded per image, no collective",
+            "value": world * n / (ms_dev / 1e3), "e2e": world * n / (ms_e2e / 1e3), "unit": "point-patches/s", "dtype": "bf16",
+            "n_gpus": world, "patches_per_gpu": n, "gpu_launches": int(launches),
+            "bucket_write": {"npy_ms": round(npy_ms, 2), "npy_MB": round(feats.nbytes / 1e6, 1),
+                             "featurevector_ms_per_image": round(fv_ms, 2), "note": "host file I/O, timed apart from extraction"}}
+
+
+def run_c4(args, dev, barrier, rank, world, local) -> dict:
+    """BASELINE config 4: classify_features scoring of 10 M precomputed 1280-d features through the MLP(200,100)/Platt
+    head, rows sharded in contiguous blocks over the ranks (sharding.rows_for_rank), labels on the device; a subsample
+    is bit-compared with the CPU oracle's labels."""
+    from mermaid_classifier_b200 import synth
+    from mermaid_classifier_b200.inference import DeviceHead
+    from mermaid_classifier_b200.sharding import rows_for_rank
+
+    lo, hi = rows_for_rank(args.c4_rows, rank, world)
+    n = hi - lo
+    w, bb, a, b, _ = synth.synth_head(1280, (200, 100), 500, seed=0)
+    head = DeviceHead([x.numpy() for x in w], [x.numpy() for x in bb], a.numpy(), b.numpy(), device=local)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    feats = torch.empty((n, 1280), dtype=torch.float32, device=dev)
+    chunk = 1_000_000
+    for s0 in range(0, n, chunk):   # swish-like pooled features
+        x = torch.randn((min(chunk, n - s0), 1280), generator=g, device=dev)
+        feats[s0:s0 + x.shape[0]] = torch.clamp(x, min=-0.28) * 0.5 + 0.1
+    for _ in range(2):
+        head.scores_device(feats[: min(n, chunk)])
+    l0 = head.launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = head.scores_device(feats)
+    e1.record()
+    barrier()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+    rec = {"workload": f"C4: {args.c4_rows} x 1280 fp32 features -> MLP(200,100)/Platt head (500 classes), labels on device, "
+                       f"rows in contiguous blocks per GPU", "value": args.c4_rows / (ms / 1e3), "unit": "features/s",
+           "n_gpus": world, "ms": ms, "hbm_frac_of_5124B_per_feature": args.c4_rows / world * 5124 / (ms / 1e3) / 1e9 / measured_peaks()[0],
+           "gpu_launches": int(head.launches - l0)}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import head as ohead
+
+        k = min(args.c4_check, n)
+        t0 = time.perf_counter()
+        want = ohead.calibrated_proba(feats[:k].cpu().numpy(), w, bb, a, b).argmax(1)
+        cpu_s = time.perf_counter() - t0
+        rec["labels_checked"] = k
+        rec["labels_agreement_vs_cpu_oracle"] = float((out["labels"][:k].cpu().numpy() == want).mean())
+        rec["cpu_oracle_features_per_s"] = k / cpu_s
+    head.close()
+    del feats, out
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_c5(args, dev, barrier, rank, world, local) -> dict:
+    """BASELINE config 5 (bounded): MLP-head training, (500,300,100), 500 classes, device-resident synthetic features.
+    N = 1: the single-GPU Adam loop.  N > 1: data parallel with the NCCL gradient all-reduce inside the C library, in
+    both labelled modes -- throughput (200 rows per rank per step) and parity (the reference's global mini-batch of 200
+    split over the ranks)."""
+    from mermaid_classifier_b200.torch_classifier import DataParallel, TorchMLPClassifier
+
+    K, rows = 500, args.c5_rows
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    centers = torch.randn((K, 1280), generator=torch.Generator(device=dev).manual_seed(7), device=dev) * 3.0
+    y = torch.randint(0, K, (rows,), generator=g, device=dev, dtype=torch.int64)
+    X = torch.empty((rows, 1280), dtype=torch.float32, device=dev)
+    for s0 in range(0, rows, 250_000):
+        e = min(rows, s0 + 250_000)
+        X[s0:e] = centers[y[s0:e]] + torch.randn((e - s0, 1280), generator=g, device=dev) * 1.3
+    y32 = y.to(torch.int32)
+    dp = DataParallel(device=local) if world > 1 else None
+    rec = {"workload": f"C5 (bounded): MLP(500,300,100) training, 500 classes, {rows} rows x 1280 per GPU device-resident, "
+                       f"mini-batch 200, Adam lr 1e-4", "n_gpus": world, "unit": "samples/s"}
+    modes = ["throughput", "parity"] if world > 1 else ["single"]
+    for mode in modes:
+        clf = TorchMLPClassifier(hidden_layer_sizes=(500, 300, 100), learning_rate_init=1e-4, random_state=0, alpha=1e-4).set_device(local)
+        clf.init_for(1280, list(range(K)))
+        if dp is not None:
+            clf.enable_data_parallel(dp, mode)
+        # parity mode: every rank holds the same rows (the global mini-batch is split inside the library)
+        Xm, ym = (X, y32)
+        if mode == "parity":
+            import torch.distributed as dist
+
+            Xm, ym = X[: rows // 4].clone(), y32[: rows // 4].clone()
+            dist.broadcast(Xm, 0)
+            dist.broadcast(ym, 0)
+        clf.partial_fit_device(Xm[:20000], ym[:20000])  # warm-up
+        s0, l0 = clf.n_steps_, clf.launches
+        barrier()
+        t0 = time.perf_counter()
+        clf.partial_fit_device(Xm, ym)
+        torch.cuda.synchronize()
+        ms = _max_over_ranks((time.perf_counter() - t0) * 1e3, dev, world)
+        steps = clf.n_steps_ - s0
+        samples = Xm.shape[0] * (world if mode == "throughput" else 1)
+        rec[mode] = {"samples_per_s": samples / (ms / 1e3), "adam_steps_per_s": steps / (ms / 1e3), "steps": int(steps),
+                     "loss": float(clf.loss_curve_[-1]), "gpu_launches": int(clf.launches - l0),
+                     "collective": ("ncclAllReduce(sum) of %d floats per step" % int(_lib_grad_size(clf))) if world > 1 else "none"}
+        clf._release()
+    rec["value"] = rec[modes[0]]["samples_per_s"]
+    return rec
 
 
 def main():
@@ -422,11 +600,15 @@ def main():
     ap.add_argument("--images", type=int, default=1000)
     ap.add_argument("--points", type=int, default=100)
     ap.add_argument("--batch", type=int, default=1000, help="patches per sub-batch")
-    ap.add_argument("--group", type=int, default=10, help="images per extract call on the e2e path (x points = one sub-batch)")
     ap.add_argument("--host-pool", type=int, default=64, help="distinct pinned host images cycled by the e2e path")
     ap.add_argument("--cpu-images", type=int, default=3, help="images timed by the cpu_baseline leg")
     ap.add_argument("--ref-images", type=int, default=1, help="images per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the C3 / C4 / C5 sub-records")
+    ap.add_argument("--c3-images", type=int, default=200, help="images (x 50 points) per GPU of the bf16 C3 sub-record")
+    ap.add_argument("--c4-rows", type=int, default=10_000_000, help="feature rows of the C4 scoring sub-record (whole job)")
+    ap.add_argument("--c4-check", type=int, default=100_000, help="rows of C4 bit-compared with the CPU oracle")
+    ap.add_argument("--c5-rows", type=int, default=400_000, help="training rows per GPU of the C5 sub-record")
     ap.add_argument("--profile-out", default=None, help="write the per-layer CUDA-event table (one profiled warm-up step) here")
     args = ap.parse_args()
     rank, world, local = dist_env()

@@ -34,6 +34,7 @@ from .spacer_compat import (
     ExtractFeaturesReturnMsg,
     ImageFeatures,
     check_extract_inputs,
+    image_features_from_array,
     load_image,
     storage_factory,
 )
@@ -94,6 +95,16 @@ class RunCounters:
     started: float = field(default_factory=time.monotonic)
 
 
+def _capture(fn, arg):
+    """``(result, None)`` or ``(None, exception)`` -- lets a thread pool map over items that may fail."""
+    try:
+        return fn(arg), None
+    except KeyboardInterrupt:
+        raise
+    except Exception as exc:
+        return None, exc
+
+
 def _ts() -> str:
     return datetime.now(timezone.utc).strftime("%Y-%m-%dT%H:%M:%SZ")
 
@@ -111,6 +122,8 @@ def build_feature_bucket(
     world: int = 1,
     error_csv: str | Path | None = None,
     progress_jsonl: str | Path | None = None,
+    batch_images: int = 16,
+    io_threads: int = 8,
 ) -> RunCounters:
     """Extract every image of every source into ``target_root/s{sid}/features/i{iid}.featurevector``.
 
@@ -120,7 +133,14 @@ def build_feature_bucket(
     ``progress_jsonl`` one JSON object per image -- ``ts, source_id, image_id, outcome`` (``ok`` / ``skipped`` /
     ``failed``) plus ``reason`` (``no_rowcols`` / ``exists``), ``error_type`` or ``dry_run``
     (``record_progress``, ``:794-808``); ``error_csv`` rows ``ts, source_id, image_id, error_type, error_msg`` under
-    that header (``record_failure``, ``:810-822``, header ``:883``).  Both append, so a resumed run extends them."""
+    that header (``record_failure``, ``:810-822``, header ``:883``).  Both append, so a resumed run extends them.
+
+    Where the reference makes one synchronous ``extract_features`` call per image, images are taken ``batch_images`` at a
+    time: a thread pool loads and decodes them (the reference uses thread pools for its S3 I/O too, ``:308-309``), ONE
+    ``extractor.extract_many`` call runs the batch through the library's pinned-staging pipeline (copy of image i+1
+    overlaps the convolution of image i), and the ``.featurevector`` files are written by the pool.  Records keep image
+    order; an image that fails to load, validate or store is logged and the rest of its batch is unaffected.  Extractors
+    without ``extract_many`` fall back to one ``extract_features`` call per image."""
     counters = RunCounters()
     source_root, target_root = Path(source_root), Path(target_root)
     new_err = error_csv is not None and (not Path(error_csv).exists() or Path(error_csv).stat().st_size == 0)
@@ -135,6 +155,57 @@ def build_feature_bucket(
             prog.write(json.dumps({"ts": _ts(), "source_id": sid, "image_id": iid, "outcome": outcome, **extra}) + "\n")
             prog.flush()
 
+    from concurrent.futures import ThreadPoolExecutor
+
+    batched = hasattr(extractor, "extract_many") and batch_images > 1
+    pool = ThreadPoolExecutor(max_workers=max(1, io_threads)) if batched else None
+
+    def fail_image(sid, iid, exc):
+        counters.images_failed += 1
+        if err:
+            err.writerow([_ts(), sid, iid, type(exc).__name__, str(exc)])
+        progress(sid, iid, "failed", error_type=type(exc).__name__)
+
+    def load_one(item):
+        sid, iid, rowcols, floc = item
+        loc = DataLocation("filesystem", str(source_root / image_key(source_prefix, sid, iid)))
+        img = load_image(loc)
+        check_extract_inputs(img, rowcols, loc.key)
+        return np.asarray(img)
+
+    def run_batch(items):
+        """items: (sid, iid, rowcols, feature_loc) in image order."""
+        loaded = list(pool.map(lambda it: _capture(load_one, it), items))
+        good = [(it, arr) for it, (arr, exc) in zip(items, loaded) if exc is None]
+        outcome = {id(it): exc for it, (arr, exc) in zip(items, loaded) if exc is not None}
+        if good:
+            try:
+                feats, _ = extractor.extract_many([arr for _, arr in good], [it[2] for it, _ in good])
+                o = 0
+                stores = []
+                for it, _ in good:
+                    n = len(it[2])
+                    stores.append((it, feats[o:o + n]))
+                    o += n
+                results = list(pool.map(lambda sf: _capture(
+                    lambda x: image_features_from_array(x[0][2], x[1]).store(x[0][3]), sf), stores))
+                for (it, _), (_, exc) in zip(stores, results):
+                    if exc is not None:
+                        outcome[id(it)] = exc
+            except KeyboardInterrupt:
+                raise
+            except Exception as exc:   # the whole batch failed on the device: every image of it is recorded
+                for it, _ in good:
+                    outcome[id(it)] = exc
+        for it in items:
+            exc = outcome.get(id(it))
+            if exc is None:
+                counters.images_ok += 1
+                counters.patches += len(it[2])
+                progress(it[0], it[1], "ok")
+            else:
+                fail_image(it[0], it[1], exc)
+
     try:
         for sid in sorted(sources):
             grouped = sources[sid]
@@ -142,6 +213,7 @@ def build_feature_bucket(
                 counters.sources_skipped += 1
                 continue
             ids = sorted(grouped)
+            pending: list[tuple] = []
             for k in images_for_rank(len(ids), rank, world):
                 iid = ids[k]
                 rowcols = list(grouped[iid])
@@ -158,6 +230,12 @@ def build_feature_bucket(
                     counters.images_ok += 1
                     progress(sid, iid, "ok", dry_run=True)
                     continue
+                if batched:
+                    pending.append((sid, iid, rowcols, floc))
+                    if len(pending) >= batch_images:
+                        run_batch(pending)
+                        pending = []
+                    continue
                 msg = ExtractFeaturesMsg(
                     job_token=f"s{sid}_i{iid}", extractor=extractor, rowcols=rowcols,
                     image_loc=DataLocation("filesystem", str(source_root / image_key(source_prefix, sid, iid))),
@@ -170,12 +248,13 @@ def build_feature_bucket(
                 except KeyboardInterrupt:
                     raise
                 except Exception as exc:  # per-image failure: log and carry on
-                    counters.images_failed += 1
-                    if err:
-                        err.writerow([_ts(), sid, iid, type(exc).__name__, str(exc)])
-                    progress(sid, iid, "failed", error_type=type(exc).__name__)
+                    fail_image(sid, iid, exc)
+            if pending:
+                run_batch(pending)
             counters.sources_done += 1
     finally:
+        if pool is not None:
+            pool.shutdown(wait=True)
         if err_file:
             err_file.close()
         if prog:

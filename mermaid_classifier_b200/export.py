@@ -87,13 +87,19 @@ def _version(pkg: str):
     try:
         return metadata.version(pkg)
     except metadata.PackageNotFoundError:
-        return None
+        return "not-installed"   # explicit provenance: the artifact was produced without this package
 
 
 def export_artifact(model: Any, output_dir, reference_features: Any, *, config=None, task: str = TASK_NAME,
-                    tol: float = 1e-6):
+                    tol: float = 1e-6, enforce_sklearn_pin: bool = True):
     """Returns ``(model_pt_path, manifest, max_abs_diff)``; raises :class:`ParityError` when the frozen graph and
-    ``model.predict_proba`` disagree beyond ``tol`` on ``reference_features``."""
+    ``model.predict_proba`` disagree beyond ``tol`` on ``reference_features``.
+
+    ``enforce_sklearn_pin`` is accepted for signature compatibility with the reference (``inference/export.py:32,41-49``,
+    where it guards the private sklearn calibrator API).  The B200 trainer fits its Platt calibrators itself
+    (``mc_platt_fit``) and reads none of scikit-learn's internals, so there is nothing to pin: the flag is a documented
+    no-op here, and the manifest records the scikit-learn version as provenance when the package is installed."""
+    del enforce_sklearn_pin
     output_dir = Path(output_dir)
     output_dir.mkdir(parents=True, exist_ok=True)
     frozen = torch.jit.freeze(torch.jit.script(build_calibrated_head(model).eval()))

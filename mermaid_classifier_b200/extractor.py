@@ -202,12 +202,16 @@ class EfficientNetExtractor:
         n = pts.shape[0]
         feats = None
         if want_features:
-            feats = out if out is not None else np.empty((n, self.feature_dim), dtype=np.float32)
+            # default output: pinned host memory (torch's caching host allocator), so the read-back stays asynchronous
+            feats = out if out is not None else (
+                torch.empty((n, self.feature_dim), dtype=torch.float32, pin_memory=True).numpy() if n else
+                np.empty((0, self.feature_dim), dtype=np.float32))
             if feats.shape != (n, self.feature_dim) or feats.dtype != np.float32 or not feats.flags.c_contiguous:
                 raise ValueError("out must be a C-contiguous (n, 1280) float32 array")
         labels = None
         if head is not None:
-            labels = labels_out if labels_out is not None else np.empty((n,), dtype=np.int32)
+            labels = labels_out if labels_out is not None else (
+                torch.empty((n,), dtype=torch.int32, pin_memory=True).numpy() if n else np.empty((0,), dtype=np.int32))
             if labels.shape != (n,) or labels.dtype != np.int32:
                 raise ValueError("labels_out must be an (n,) int32 array")
         if not want_features and head is None:

@@ -257,6 +257,23 @@ class MermaidTrainer:
         dp = self.data_parallel
         return dp is not None and dp.world > 1 and self.dp_mode == "throughput"
 
+    def _collective_device(self) -> torch.device:
+        """Where small control tensors of the collectives live: the GPU for NCCL groups, the host for gloo (CPU tests)."""
+        import torch.distributed as dist
+
+        backend = str(dist.get_backend(self.data_parallel.group)).lower()
+        return torch.device("cuda", self.data_parallel.device) if "nccl" in backend else torch.device("cpu")
+
+    def _gather_lists(self, *lists: list[Any]) -> tuple[list[Any], ...]:
+        """Concatenate per-rank Python lists in rank order on every rank (final validation results of throughput mode)."""
+        if not self._sharded:
+            return lists
+        import torch.distributed as dist
+
+        parts: list[Any] = [None] * self.data_parallel.world
+        dist.all_gather_object(parts, [list(x) for x in lists], group=self.data_parallel.group)
+        return tuple([v for part in parts for v in part[i]] for i in range(len(lists)))
+
     def _sum_over_ranks(self, hits: int, loss: float, n: int, device: Any) -> tuple[int, float, int]:
         """``device``: CUDA index of the estimator (NCCL groups), or a ``torch.device`` (the gloo tests pass "cpu")."""
         if not self._sharded:
@@ -353,10 +370,12 @@ class MermaidTrainer:
 
         clf_calibrated = self._calibrate_in_batches(clf, labels.ref)
         classes = clf_calibrated.classes_.tolist()
-        val_gts, val_ests, val_scores = evaluate_classifier(clf_calibrated, labels.val, self.batch_size)
+        # throughput mode: every rank scored its own validation shard; gather so that all ranks return the SAME
+        # val_results / accuracies over the whole validation split (rank order = shard order)
+        val_gts, val_ests, val_scores = self._gather_lists(*evaluate_classifier(clf_calibrated, labels.val, self.batch_size))
         pc_accs = []
         for pc_model in pc_models:
-            pc_gts, pc_ests, _ = evaluate_classifier(pc_model, labels.val, self.batch_size)
+            pc_gts, pc_ests = self._gather_lists(*evaluate_classifier(pc_model, labels.val, self.batch_size)[:2])
             pc_accs.append(float(np.mean(np.asarray(pc_gts) == np.asarray(pc_ests))))
         val_results = ValResults(scores=val_scores, gt=[classes.index(m) for m in val_gts],
                                  est=[classes.index(m) for m in val_ests], classes=classes)
@@ -366,23 +385,36 @@ class MermaidTrainer:
 
     def _train_epoch(self, clf: TorchMLPClassifier, train: Any, classes_list: list[Any], epoch: int) -> None:
         """``trainer.py:138-145``: one ``partial_fit`` per chunk, chunks drawn with ``random_seed=epoch``."""
-        if self._sharded:
-            # every partial_fit pass all-reduces per Adam step: ranks must make the same number of passes
-            import torch.distributed as dist
-
-            n_chunks = -(-train.label_count // self.batch_size)
-            t = torch.tensor([n_chunks, -n_chunks], dtype=torch.int64, device=f"cuda:{self.data_parallel.device}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.data_parallel.group)
-            if int(t[0]) != -int(t[1]):
-                raise ValueError(f"throughput mode needs the same number of training chunks on every rank "
-                                 f"(this rank: {n_chunks}, max {int(t[0])}, min {-int(t[1])}); use equal-size shards")
         if hasattr(train, "device_batches"):
             clf.init_for(int(train.X.shape[1]), classes_list)
-            for xd, yd in train.device_batches(self.batch_size, clf.classes_, random_seed=epoch):
-                clf.partial_fit_device(xd.contiguous(), yd)
+            chunks = ((xd.contiguous(), yd) for xd, yd in train.device_batches(self.batch_size, clf.classes_, random_seed=epoch))
+            fit = lambda c: clf.partial_fit_device(*c)   # noqa: E731
         else:
-            for x, y in train.load_data_in_batches(batch_size=self.batch_size, random_seed=epoch):
-                clf.partial_fit(x, y, classes=classes_list)
+            chunks = iter(train.load_data_in_batches(batch_size=self.batch_size, random_seed=epoch))
+            fit = lambda c: clf.partial_fit(c[0], c[1], classes=classes_list)   # noqa: E731
+        if not self._sharded:
+            for c in chunks:
+                fit(c)
+            return
+        # Throughput mode: every partial_fit pass all-reduces once per Adam step, so the ranks must make the same number
+        # of passes.  Host ImageLabels batch by whole images, so the count is only known by drawing the chunks: agree on
+        # "one more chunk?" before every pass and fail on ALL ranks together instead of hanging in the collective.
+        import torch.distributed as dist
+
+        n_done = 0
+        while True:
+            c = next(chunks, None)
+            has = 0 if c is None else 1
+            t = torch.tensor([has, -has], dtype=torch.int64, device=self._collective_device())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.data_parallel.group)
+            if int(t[0]) != -int(t[1]):
+                raise ValueError(f"throughput mode needs the same number of training chunks on every rank: after {n_done} "
+                                 f"chunks this rank has {'another' if has else 'no more'} while another rank differs; "
+                                 f"use equal-size shards")
+            if c is None:
+                return
+            fit(c)
+            n_done += 1
 
     def _calc_acc_batched(self, clf: TorchMLPClassifier, labels: Any) -> float:
         hits = n = 0

@@ -174,6 +174,68 @@ def test_trainer_sharded_reductions_gloo():
     assert y.tolist() == [0, 0, 0, 1, 1, 1, 1, 1]
 
 
+class _FakeClf:
+    classes_ = np.arange(3)
+
+    def __init__(self):
+        self.fits = 0
+
+    def partial_fit(self, x, y, classes=None):
+        self.fits += 1
+
+
+class _HostLabels:
+    """ImageLabels stand-in: `n_chunks` host chunks per epoch."""
+
+    def __init__(self, n_chunks):
+        self.n_chunks, self.label_count = n_chunks, 100 * n_chunks
+
+    def load_data_in_batches(self, batch_size, random_seed=None):
+        for i in range(self.n_chunks):
+            yield [[float(i)] * 4] * 5, [0, 1, 2, 0, 1]
+
+
+def _chunk_rank(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mermaid_classifier_b200.trainer import MermaidTrainer
+
+    tr = MermaidTrainer(batch_size=100, data_parallel=_Group(rank, world), dp_mode="throughput")
+    # equal chunk counts: every rank fits all of its chunks
+    clf = _FakeClf()
+    tr._train_epoch(clf, _HostLabels(3), [0, 1, 2], epoch=0)
+    equal_ok = clf.fits == 3
+    # unequal counts (rank 1 draws one chunk more): BOTH ranks raise after the common prefix instead of hanging
+    clf2 = _FakeClf()
+    try:
+        tr._train_epoch(clf2, _HostLabels(2 + rank), [0, 1, 2], epoch=0)
+        raised = False
+    except ValueError:
+        raised = True
+    # final validation lists are concatenated in rank order on every rank
+    g, e = tr._gather_lists([f"gt{rank}a", f"gt{rank}b"], [rank, rank + 10])
+    out.put((rank, equal_ok, raised, clf2.fits, g, e))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trainer_chunk_agreement_and_list_gather_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chunk_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, equal_ok, raised, fits, g, e in res:
+        assert equal_ok and raised and fits == 2
+        assert g == ["gt0a", "gt0b", "gt1a", "gt1b"] and e == [0, 10, 1, 11]
+
+
 def test_trainer_rejects_unknown_dp_mode():
     from mermaid_classifier_b200.trainer import MermaidTrainer
 

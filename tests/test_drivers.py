@@ -101,3 +101,48 @@ def test_classify_features_shapes():
     assert out["classes"] == ["a", "b", "c"] and out["scores"][1][:2] == (3, 4) and len(out["scores"][0][2]) == 3
     top = drivers.classify_features(f, P(), top_k=2)
     assert top["scores"][0][2] == [("b", 0.5), ("c", 0.3)]
+
+
+class FakeBatchExtractor(FakeExtractor):
+    """Adds the batch surface of the GPU extractor (extract_many): one call per group of images."""
+
+    def __init__(self):
+        super().__init__()
+        self.batches = []
+
+    def extract_many(self, images, rowcols_list, head=None, **_kw):
+        self.batches.append(len(images))
+        rows = [[r, c, np.asarray(im).mean()] + [0.0] * 5 for im, rcs in zip(images, rowcols_list) for r, c in rcs]
+        return np.asarray(rows, dtype=np.float32).reshape(-1, 8), None
+
+
+def test_bucket_driver_batched_path_matches_per_image_path(tmp_path):
+    """The driver hands images to extract_many in batches (threaded loads and stores); files, counters and records must
+    equal the one-image-per-call path, and a bad image must not take its batch down."""
+    src = tmp_path / "src"
+    (src / "s5" / "images").mkdir(parents=True)
+    sources = {"5": {}}
+    for i in range(7):
+        Image.fromarray(np.full((40, 50, 3), 10 * i, np.uint8)).save(src / "s5" / "images" / f"{i}.png")
+        (src / "s5" / "images" / f"{i}.png").rename(src / "s5" / "images" / f"{i}.jpg")
+        sources["5"][str(i)] = [(1, 2), (3, 4), (5, 6)]
+    sources["5"]["2"] = [(1, 2), (400, 4)]          # fails validation inside a batch
+    sources["5"]["6"] = []                           # skipped
+    (src / "s5" / "images" / "4.jpg").unlink()      # fails to load inside a batch
+    one, many = FakeExtractor(), FakeBatchExtractor()
+    ca = drivers.build_feature_bucket(sources, one, source_root=src, target_root=tmp_path / "a", progress_jsonl=tmp_path / "a.jsonl")
+    cb = drivers.build_feature_bucket(sources, many, source_root=src, target_root=tmp_path / "b", progress_jsonl=tmp_path / "b.jsonl",
+                                      batch_images=3, io_threads=2)
+    assert many.batches == [2, 2] and many.calls == 0   # images 0..2 -> (0, 1) after the bad one drops out; 3..5 -> (3, 5)
+    for c in (ca, cb):
+        assert (c.images_ok, c.images_failed, c.images_skipped, c.patches) == (4, 2, 1, 12)
+    ra = [{k: v for k, v in json.loads(l).items() if k != "ts"} for l in (tmp_path / "a.jsonl").read_text().splitlines()]
+    rb = [{k: v for k, v in json.loads(l).items() if k != "ts"} for l in (tmp_path / "b.jsonl").read_text().splitlines()]
+    assert sorted(ra, key=lambda r: r["image_id"]) == sorted(rb, key=lambda r: r["image_id"])
+    fa = sorted((tmp_path / "a" / "s5" / "features").iterdir())
+    fb = sorted((tmp_path / "b" / "s5" / "features").iterdir())
+    assert [f.name for f in fa] == [f.name for f in fb] == ["i0.featurevector", "i1.featurevector", "i3.featurevector", "i5.featurevector"]
+    for x, y in zip(fa, fb):
+        gx, gy = ImageFeatures.load(DataLocation("filesystem", str(x))), ImageFeatures.load(DataLocation("filesystem", str(y)))
+        assert [(p.row, p.col) for p in gx.point_features] == [(p.row, p.col) for p in gy.point_features]
+        assert np.array_equal(np.stack([p.data for p in gx.point_features]), np.stack([p.data for p in gy.point_features]))
