@@ -19,6 +19,7 @@
 #include "pw_simt.cuh"
 #include "pw_tc.cuh"
 #include "mbconv_fused.cuh"
+#include "stem_tc.cuh"
 
 using namespace mc;
 
@@ -118,7 +119,9 @@ struct mc_extractor {
   int64_t cap_feats = 0;
   std::vector<mc_point> h_points;
   PwTcPlan* tc = nullptr;  // tcgen05 GEMM plans (pw_tc.cuh)
-  StemParams stem;          // stem weights + folded BN, passed by value (kernel parameter / constant bank)
+  StemParams stem;          // stem weights + folded BN, passed by value (kernel parameter / constant bank): CUDA-core stem (MC_STEM_SIMT)
+  StemTcPlan stem_tc;       // tensor-core stem (stem_tc.cuh), the default
+  bool stem_simt = false;
   std::vector<DwLayer> dw;  // TMA-staged depthwise plans (dw_tma.cuh), one per block
   std::vector<FusedLayer> fused;  // expand + depthwise in one kernel (mbconv_fused.cuh); fuse_mask bit b = block b
   unsigned fuse_mask = 0;
@@ -179,13 +182,6 @@ int prof_collect(mc_extractor* h, cudaStream_t st) {
   h->prof_used = 0;
   h->prof_ids.clear();
   return MC_OK;
-}
-
-// largest divisor of cg that is <= 64
-int pick_cgt(int cg) {
-  for (int d = std::min(cg, 64); d >= 1; --d)
-    if (cg % d == 0) return d;
-  return 1;
 }
 
 template <typename T>
@@ -284,7 +280,8 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
   int rc;
   {
     ProfScope ps(h, 0, st);
-    stem_kernel<T><<<dim3(7, nb), 256, 0, st>>>(h->d_images, h->d_points, h->stem, h->d_lut, X);
+    if (h->stem_simt) stem_kernel<T><<<dim3(7, nb), 256, 0, st>>>(h->d_images, h->d_points, h->stem, h->d_lut, X);
+    else if ((rc = stem_tc_launch<T>(h->stem_tc, h->d_images, h->d_points, P + net.s_stem, X, nb, st))) return rc;
   }
   MC_CHECK_LAUNCH();
   h->launches++;
@@ -563,6 +560,11 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
     mc_extractor_destroy(h);
     return rc;
   }
+  h->stem_simt = getenv("MC_STEM_SIMT") != nullptr;   // A/B switch: the CUDA-core stem kernel of round 1
+  if ((rc = stem_tc_plan(&h->stem_tc, params + h->net.w_stem, params + h->net.s_stem, params + h->net.b_stem, device))) {
+    mc_extractor_destroy(h);
+    return rc;
+  }
   memcpy(h->stem.w, params + h->net.w_stem, sizeof(h->stem.w));
   memcpy(h->stem.scale, params + h->net.s_stem, sizeof(h->stem.scale));
   memcpy(h->stem.bias, params + h->net.b_stem, sizeof(h->stem.bias));
@@ -596,6 +598,7 @@ int mc_extractor_destroy(mc_extractor* h) {
   DeviceGuard g(h->device);
   pw_tc_free(h->tc);
   host_pipe_free(h->pipe);
+  stem_tc_free(h->stem_tc);
   for (auto& fl : h->fused) fused_free(fl);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   void* ptrs[] = {h->d_params, h->d_lut, h->bufX, h->bufY,    h->bufE, h->bufD,

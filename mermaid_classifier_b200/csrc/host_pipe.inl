@@ -146,15 +146,12 @@ extern "C" int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_i
   while (p0 < n) {
     // ---- group: consecutive images while the point count stays within one sub-batch --------------------------------
     int64_t p1 = p0;
-    const int im0 = points[p0].image;
-    int im1 = im0;   // last image of the group (inclusive)
     while (p1 < n) {
       const int im = points[p1].image;
       int64_t q = p1;
       while (q < n && points[q].image == im) ++q;
       if (p1 > p0 && q - p0 > h->max_batch) break;
       p1 = q;
-      im1 = im;
     }
     const int64_t ng = p1 - p0;
     HostPipe::Slot& s = P->slot[gi % HostPipe::SLOTS];
@@ -268,7 +265,6 @@ extern "C" int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_i
     MC_CUDA(cudaEventRecord(s.drained, P->d2h));
     s.used = true;
     P->groups++;
-    (void)im1;
     p0 = p1;
     ++gi;
   }

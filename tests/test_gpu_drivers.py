@@ -36,7 +36,7 @@ def test_bucket_build_stack_and_classify(tmp_path, backbone_sd, golden_dir):
     assert [c.images_ok for c in counters] == [2, 2]   # round-robin over ranks
     files = sorted((tgt / "s3" / "features").iterdir())
     assert [f.name for f in files] == [f"i{i}.featurevector" for i in range(4)]
-    # per-image parity with the oracle in bf16 mode: cosine >= 0.999 (the reference's own device gate)
+    # per-image parity with the oracle in bf16 mode: the stated bf16 bound (tests/test_gpu_extract.py)
     for i in range(4):
         feats = ImageFeatures.load(DataLocation("filesystem", str(files[i])))
         rc = sources["3"][str(i)]
@@ -44,7 +44,7 @@ def test_bucket_build_stack_and_classify(tmp_path, backbone_sd, golden_dir):
         got = np.stack([feats.get_array(x) for x in rc])
         want = oeff.extract_features(backbone_sd, torch.from_numpy(ocrop.normalize_patches(ocrop.crop_patches(ims[str(i)], rc)))).numpy()
         cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
-        assert cos.min() >= 0.999, cos.min()
+        assert cos.min() >= 0.998, cos.min()
     X = drivers.stack_feature_files(files, tmp_path / "bucket.npy")
     assert X.shape == (sum(len(v) for v in sources["3"].values()), 1280) and X.dtype == np.float32
     # skip-existing: a second pass extracts nothing

@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-python tools/h2d_bw.py; nvidia-smi --query-gpu=pcie.link.gen.current,pcie.link.width.current,pcie.link.gen.max --format=csv
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --images 100 --steps 2 --c4-rows 4000000 > gpurun_out/c13_bench2.log 2>&1; echo rc=$?; tail -2 gpurun_out/c13_bench2.log | grep -o '"c5_train_dp.*' | cut -c1-1500
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/c17_tests.log 2>&1; echo tests rc=$?; tail -6 gpurun_out/c17_tests.log | cut -c1-300
+timeout 400 python bench.py --images 200 --steps 2 --no-cpu-baseline --no-sub --profile-out gpurun_out/c17_layers_fp32.csv > gpurun_out/c17_bench_fp32.log 2>&1; echo bench rc=$?; tail -1 gpurun_out/c17_bench_fp32.log | cut -c1-120; head -2 gpurun_out/c17_layers_fp32.csv | tail -1
+python -c "import __graft_entry__ as g; g.smoke()"
