@@ -142,6 +142,21 @@ int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_image* image
 /* Bytes copied host->device / device->host and image groups of the last mc_extract_images_host call. */
 int mc_extractor_pipe_stats(const mc_extractor* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* groups);
 
+/* ---- (f)2: image decode feeding the crop kernel: spacer.storage.load_image (call site
+ *      mermaid_classifier/pyspacer/annotation.py:235; inside spacer.tasks.extract_features,
+ *      scripts/build_feature_bucket.py:775) for JPEG streams.  Huffman decoding runs on the calling host thread,
+ *      IDCT / upsampling / colour conversion on the GPU (nvJPEG), RGB8 interleaved straight into a device buffer that
+ *      mc_extract_points reads: the decoded image never crosses PCIe.  A grayscale stream becomes three equal channels
+ *      (PIL convert("RGB")); CMYK streams are rejected with MC_ERR_UNSUPPORTED.  mc_jpeg_decode is asynchronous on
+ *      `stream` once the host part is done.  One decoder handle per host thread. ------------------------------------ */
+typedef struct mc_jpeg mc_jpeg;
+int mc_jpeg_create(int32_t device, mc_jpeg** out);
+int mc_jpeg_destroy(mc_jpeg* d);
+int mc_jpeg_info(mc_jpeg* d, const uint8_t* jpeg_host, int64_t n_bytes, int32_t* height, int32_t* width,
+                 int32_t* components);
+int mc_jpeg_decode(mc_jpeg* d, const uint8_t* jpeg_host, int64_t n_bytes, uint8_t* rgb_dev, int64_t row_pitch,
+                   int32_t height, int32_t width, void* stream);
+
 /* Debug/parity tap: during the NEXT extract call, copy one internal NHWC activation of the
  * first sub-batch to `out_dev` as fp32 (at most `capacity` elements).
  * layer: 0 = stem, 1+4*b+{0,1,2,3} = block b {expand, depthwise, SE gate, block out},

@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     digest = _sources_digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, *_extra_defs(), "-I", str(INCLUDE), "-o", str(LIB), str(CSRC / "api.cu"), "-lcuda"]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *_extra_defs(), "-I", str(INCLUDE), "-o", str(LIB), str(CSRC / "api.cu"), "-lcuda", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)

@@ -977,5 +977,6 @@ int64_t mc_head_launches(const mc_head* h) { return h ? h->launches : 0; }
 }  // extern "C"
 
 #include "host_pipe.inl"
+#include "jpeg_api.inl"
 #include "mlp_api.inl"
 #include "calib_api.inl"

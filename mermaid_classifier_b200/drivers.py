@@ -124,6 +124,7 @@ def build_feature_bucket(
     progress_jsonl: str | Path | None = None,
     batch_images: int = 16,
     io_threads: int = 8,
+    decode: str = "host",
 ) -> RunCounters:
     """Extract every image of every source into ``target_root/s{sid}/features/i{iid}.featurevector``.
 
@@ -140,7 +141,11 @@ def build_feature_bucket(
     ``extractor.extract_many`` call runs the batch through the library's pinned-staging pipeline (copy of image i+1
     overlaps the convolution of image i), and the ``.featurevector`` files are written by the pool.  Records keep image
     order; an image that fails to load, validate or store is logged and the rest of its batch is unaffected.  Extractors
-    without ``extract_many`` fall back to one ``extract_features`` call per image."""
+    without ``extract_many`` fall back to one ``extract_features`` call per image.
+
+    ``decode="device"`` reads the image files as bytes and decodes JPEG streams ON the GPU
+    (:mod:`mermaid_classifier_b200.decode`, one nvJPEG decoder per pool thread): the decoded image never crosses PCIe and
+    ``extractor.extract_device`` reads it where it lands."""
     counters = RunCounters()
     source_root, target_root = Path(source_root), Path(target_root)
     new_err = error_csv is not None and (not Path(error_csv).exists() or Path(error_csv).stat().st_size == 0)
@@ -157,8 +162,16 @@ def build_feature_bucket(
 
     from concurrent.futures import ThreadPoolExecutor
 
-    batched = hasattr(extractor, "extract_many") and batch_images > 1
+    if decode not in ("host", "device"):
+        raise ValueError("decode must be 'host' or 'device'")
+    batched = (hasattr(extractor, "extract_many") and batch_images > 1) or decode == "device"
     pool = ThreadPoolExecutor(max_workers=max(1, io_threads)) if batched else None
+    decode_pool = None
+    if decode == "device":
+        from .decode import DecodePool
+
+        extractor._ensure_handle()
+        decode_pool = DecodePool(max(1, io_threads), device=extractor._device_index)
 
     def fail_image(sid, iid, exc):
         counters.images_failed += 1
@@ -173,8 +186,59 @@ def build_feature_bucket(
         check_extract_inputs(img, rowcols, loc.key)
         return np.asarray(img)
 
+    def run_batch_device(items):
+        """Device decode: file bytes -> nvJPEG -> extract_device -> features back -> threaded stores."""
+        def read_bytes(it):
+            loc = DataLocation("filesystem", str(source_root / image_key(source_prefix, it[0], it[1])))
+            return storage_factory("filesystem").load(loc.key).getvalue()
+
+        blobs = list(pool.map(lambda it: _capture(read_bytes, it), items))
+        outcome = {id(it): exc for it, (_, exc) in zip(items, blobs) if exc is not None}
+        todo = [(it, b) for it, (b, exc) in zip(items, blobs) if exc is None]
+        decoded = decode_pool.decode_many([b for _, b in todo])
+        good = []
+        for (it, _), (img, exc) in zip(todo, decoded):
+            if exc is None:
+                try:
+                    check_extract_inputs(np.empty((img.shape[0], img.shape[1], 0), np.uint8), it[2], str(it[1]))
+                except Exception as e2:
+                    exc = e2
+            if exc is not None:
+                outcome[id(it)] = exc
+            else:
+                good.append((it, img))
+        if good:
+            try:
+                pts = np.array([(k, r, c) for k, (it, _) in enumerate(good) for r, c in it[2]], dtype=np.int32)
+                feats = extractor.extract_device([img for _, img in good], pts).cpu().numpy()
+                o = 0
+                stores = []
+                for it, _ in good:
+                    stores.append((it, feats[o:o + len(it[2])]))
+                    o += len(it[2])
+                results = list(pool.map(lambda sf: _capture(
+                    lambda x: image_features_from_array(x[0][2], x[1]).store(x[0][3]), sf), stores))
+                for (it, _), (_, exc) in zip(stores, results):
+                    if exc is not None:
+                        outcome[id(it)] = exc
+            except KeyboardInterrupt:
+                raise
+            except Exception as exc:
+                for it, _ in good:
+                    outcome[id(it)] = exc
+        for it in items:
+            exc = outcome.get(id(it))
+            if exc is None:
+                counters.images_ok += 1
+                counters.patches += len(it[2])
+                progress(it[0], it[1], "ok")
+            else:
+                fail_image(it[0], it[1], exc)
+
     def run_batch(items):
         """items: (sid, iid, rowcols, feature_loc) in image order."""
+        if decode_pool is not None:
+            return run_batch_device(items)
         loaded = list(pool.map(lambda it: _capture(load_one, it), items))
         good = [(it, arr) for it, (arr, exc) in zip(items, loaded) if exc is None]
         outcome = {id(it): exc for it, (arr, exc) in zip(items, loaded) if exc is not None}
@@ -255,6 +319,8 @@ def build_feature_bucket(
     finally:
         if pool is not None:
             pool.shutdown(wait=True)
+        if decode_pool is not None:
+            decode_pool.close()
         if err_file:
             err_file.close()
         if prog:

@@ -125,3 +125,28 @@ def export_artifact(model: Any, output_dir, reference_features: Any, *, config=N
     torch.jit.save(frozen, str(model_pt))
     (output_dir / "model.json").write_text(json.dumps(manifest, indent=2))
     return model_pt, manifest, max_diff
+
+
+def write_head_artifact(output_dir, weights, biases, a, b, classes, *, config=None, task: str = TASK_NAME):
+    """``model.pt`` + ``model.json`` from explicit head parameters (Linear weights / biases, per-class Platt ``a`` / ``b``):
+    the same frozen TorchScript graph and manifest fields :func:`export_artifact` writes (``inference/export.py:54-57,71-92``
+    in the reference), without a calibrated estimator object to read them from.  Returns ``(model_pt, model_json)``."""
+    output_dir = Path(output_dir)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    ws = [torch.as_tensor(np.asarray(w), dtype=torch.float32) for w in weights]
+    bs = [torch.as_tensor(np.asarray(x), dtype=torch.float32) for x in biases]
+    head = PortableHead(ws, bs, torch.as_tensor(np.asarray(a), dtype=torch.float32), torch.as_tensor(np.asarray(b), dtype=torch.float32))
+    frozen = torch.jit.freeze(torch.jit.script(head.eval()))
+    manifest = {
+        "schema_version": SCHEMA_VERSION,
+        "task": task,
+        "classes": [c.item() if hasattr(c, "item") else c for c in classes],
+        "input_dim": int(ws[0].shape[1]),
+        "config": config if config is not None else {"patch_size": 224},
+        "trained_with": {"torch": torch.__version__, "sklearn": _version("scikit-learn"), "pyspacer": _version("pyspacer"),
+                         "trainer": "mermaid_classifier_b200"},
+    }
+    model_pt, model_json = output_dir / "model.pt", output_dir / "model.json"
+    torch.jit.save(frozen, str(model_pt))
+    model_json.write_text(json.dumps(manifest, indent=2))
+    return model_pt, model_json

@@ -1,0 +1,100 @@
+"""GPU tests of the device-side image decode: nvJPEG through the C ABI against PIL's load_image semantics,
+and the bucket driver running on device-decoded images."""
+import io
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from mermaid_classifier_b200 import drivers, synth
+from mermaid_classifier_b200.decode import DecodePool, JpegDecoder, load_image_device
+from mermaid_classifier_b200.extractor import EfficientNetExtractor
+from mermaid_classifier_b200.spacer_compat import DataLocation, ImageFeatures
+
+pytestmark = pytest.mark.gpu
+
+# nvJPEG's IDCT / colour conversion / chroma upsampling are not libjpeg-turbo's bit for bit, so parity with PIL is a
+# tolerance, not equality (measured on the noisy synthetic image, 4:4:4: half of the bytes identical, the rest off by one,
+# worst byte off by 4).  Stated bound against PIL's convert("RGB"): 4:4:4 streams every byte within 6 grey levels and a
+# mean absolute difference <= 0.75; 4:2:0 streams (libjpeg-turbo's fancy upsampling vs nvJPEG's interpolation) within 32
+# and mean <= 1.5.  Downstream, features of device-decoded images agree with host-decoded ones to cosine >= 0.9999.
+def _jpeg(arr, quality=92, subsampling=0):
+    buf = io.BytesIO()
+    Image.fromarray(arr).save(buf, format="JPEG", quality=quality, subsampling=subsampling)
+    return buf.getvalue()
+
+
+def _pil(data):
+    return np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+
+
+def test_jpeg_decode_matches_pil():
+    dec = JpegDecoder()
+    im = synth.synth_image(synth.DEFAULT_SEED, 3, 600, 840)
+    data = _jpeg(im, subsampling=0)   # 4:4:4
+    assert dec.info(data) == (600, 840, 3)
+    got = dec.decode(data).cpu().numpy()
+    want = _pil(data)
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert got.shape == want.shape == (600, 840, 3)
+    assert d.max() <= 6 and d.mean() <= 0.75, (d.max(), d.mean())
+    data420 = _jpeg(im, subsampling=2)
+    d2 = np.abs(dec.decode(data420).cpu().numpy().astype(np.int16) - _pil(data420).astype(np.int16))
+    assert d2.max() <= 32 and d2.mean() <= 1.5, (d2.max(), d2.mean())
+    # grayscale stream -> three equal channels, as PIL's convert("RGB")
+    gray = _jpeg(im[:, :, 0])
+    g = dec.decode(gray).cpu().numpy()
+    assert dec.info(gray)[2] == 1 and g.shape == (600, 840, 3)
+    assert np.array_equal(g[:, :, 0], g[:, :, 1]) and np.array_equal(g[:, :, 1], g[:, :, 2])
+    assert np.abs(g.astype(np.int16) - _pil(gray).astype(np.int16)).max() <= 6
+    with pytest.raises(ValueError):
+        dec.info(b"\\xff\\xd8 not a jpeg")
+    dec.close()
+
+
+def test_decode_pool_and_png_fallback():
+    pool = DecodePool(4)
+    ims = [synth.synth_image(7, i, 200 + 16 * i, 320) for i in range(6)]
+    blobs = [_jpeg(im) for im in ims[:5]]
+    png = io.BytesIO()
+    Image.fromarray(ims[5]).save(png, format="PNG")
+    blobs.append(png.getvalue())
+    blobs.append(b"garbage")
+    out = pool.decode_many(blobs)
+    torch.cuda.synchronize()
+    assert [e is None for _, e in out] == [True] * 6 + [False]
+    for (img, _), blob in zip(out[:5], blobs[:5]):
+        assert np.abs(img.cpu().numpy().astype(np.int16) - _pil(blob).astype(np.int16)).max() <= 6
+    assert np.array_equal(out[5][0].cpu().numpy(), ims[5])   # PNG: lossless through the PIL fallback
+    pool.close()
+
+
+def test_bucket_driver_with_device_decode(tmp_path, backbone_sd):
+    """build_feature_bucket(decode="device"): features of device-decoded JPEGs against the host-decoded run of the same
+    files (decoders differ by a few grey levels in a few pixels: features agree to cosine >= 0.9999)."""
+    src = tmp_path / "src"
+    (src / "s9" / "images").mkdir(parents=True)
+    sources = {"9": {}}
+    for i in range(5):
+        im = synth.synth_image(synth.DEFAULT_SEED, 60 + i, 320, 400)
+        (src / "s9" / "images" / f"{i}.jpg").write_bytes(_jpeg(im, quality=95))
+        sources["9"][str(i)] = drivers.prepare_points(*zip(*synth.synth_points(synth.DEFAULT_SEED, 60 + i, 320, 400, 9)))
+    sources["9"]["4"] = [(1, 2), (999, 3)]   # invalid point: recorded, the batch carries on
+    ext = EfficientNetExtractor(state_dict=backbone_sd, mode="fp32", max_batch=32)
+    try:
+        a = drivers.build_feature_bucket(sources, ext, source_root=src, target_root=tmp_path / "host", batch_images=3)
+        b = drivers.build_feature_bucket(sources, ext, source_root=src, target_root=tmp_path / "dev", batch_images=3,
+                                         decode="device", io_threads=3)
+    finally:
+        ext.close()
+    for c in (a, b):
+        assert (c.images_ok, c.images_failed) == (4, 1)
+    for i in range(4):
+        fa = ImageFeatures.load(DataLocation("filesystem", str(tmp_path / "host" / "s9" / "features" / f"i{i}.featurevector")))
+        fb = ImageFeatures.load(DataLocation("filesystem", str(tmp_path / "dev" / "s9" / "features" / f"i{i}.featurevector")))
+        A = np.stack([p.data for p in fa.point_features]).astype(np.float64)
+        B = np.stack([p.data for p in fb.point_features]).astype(np.float64)
+        cos = (A * B).sum(1) / (np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1))
+        assert [(p.row, p.col) for p in fa.point_features] == [(p.row, p.col) for p in fb.point_features]
+        assert cos.min() >= 0.9999, cos.min()

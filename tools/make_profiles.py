@@ -8,10 +8,17 @@ g = Path("gpurun_out")
 
 # 1. launch list -> per-launch rows of the first full sub-batch + per-family shares
 rows = [r for r in csv.reader(open(g / f"launches_{mode}.csv")) if len(r) > 10 and r[0].isdigit()]
-launches = [(int(r[0]), r[4].split("(")[0].replace("void ", ""), r[7], r[8], float(r[14]) / 1e3) for r in rows]
+def kname(full):
+    full = full.replace("void ", "")
+    i = full.find(">(")   # templated kernel: keep the template arguments, drop the parameter list
+    return full[: i + 1] if i >= 0 else full.split("(")[0]
+launches = [(int(r[0]), kname(r[4]), r[7], r[8], float(r[14]) / 1e3) for r in rows]
 def family(name):
-    for k in ("synth_image", "stem", "dw_tma", "dw_reg", "se_kernel", "pw_tc_kernel<float, (bool)0>", "pw_tc_kernel<float, (bool)1>",
-              "pw_tc_kernel<__nv_bfloat16, (bool)0>", "pw_tc_kernel<__nv_bfloat16, (bool)1>", "pw_tc", "avgpool", "pw_simt", "head_rows"):
+    # pw_tc_kernel<T, GATED, RELU, POOL>: ungated = expand / head layers, gated = project layers, pool = head conv + pool
+    for tag, label in (("float, 0, 0, 1>", "pw_tc(head conv + pool)"), ("bfloat16, 0, 0, 1>", "pw_tc(head conv + pool)"),
+                       (", 1, 0, 0>", "pw_tc(project, gated)"), (", 0, 0, 0>", "pw_tc(expand)"), (", 0, 1, 0>", "pw_tc(mlp head)")):
+        if "pw_tc_kernel" in name and tag in name: return label
+    for k in ("synth_image", "stem_tc", "stem", "mbconv_fused", "dw_tma", "dw_reg", "se_kernel", "pw_tc", "avgpool", "pw_simt", "head_rows"):
         if k in name: return k
     return "other(torch)"
 # one sub-batch = from the first stem launch to the launch before the second stem (or head_rows)
@@ -19,9 +26,9 @@ stems = [i for i, l in enumerate(launches) if "stem" in l[1]]
 lo = stems[0]; hi = stems[1] if len(stems) > 1 else len(launches)
 sub = launches[lo:hi]
 with open(out / f"{tag}_launches_{mode}.csv", "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none : one 500-patch sub-batch of `python bench.py --images 5 --batch 500 --steps 1 --mode %s` (cold-cache, serialised: compare shares)\n" % mode)
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none : one 500-patch sub-batch of `python bench.py --images 5 --batch 500 --steps 1 --no-cpu-baseline --no-sub --mode %s` (cold-cache, serialised: compare shares)\n" % mode)
     f.write("launch,kernel,block,grid,us\n")
-    for i, n, b, gr, us in sub: f.write(f"{i},{n},\"{b}\",\"{gr}\",{us:.1f}\n")
+    for i, n, b, gr, us in sub: f.write(f"{i},\"{n}\",\"{b}\",\"{gr}\",{us:.1f}\n")
 fam = collections.OrderedDict()
 for _, n, _, _, us in sub: fam[family(n)] = fam.get(family(n), 0.0) + us
 tot = sum(fam.values())
