@@ -111,8 +111,10 @@ int mlp_gemm(mc_mlp* h, bool a_mc, bool b_nc, const float* A, int lda, const flo
              int N, int K, int epi, const float* bias, const float* mask, int ldmask, float* colsum, cudaStream_t st) {
   const int tiles = cdiv(M, 64) * cdiv(N, 64);
   int splits = 1;
-  if (!a_mc && !b_nc && tiles < 64 && K >= 512 && ldc == N) {
-    splits = std::min(cdiv(K, 128), std::max(1, 160 / tiles));
+  // few tiles and a long reduction (forward layers and the delta back-propagation at mini-batch 200): split K so that
+  // ~150 CTAs work instead of 8-40; the partials are summed in slice order (deterministic) by the epilogue kernel
+  if (!a_mc && tiles < 64 && K >= 256 && ldc == N && colsum == nullptr) {
+    splits = std::min(cdiv(K, 64), std::max(1, 160 / tiles));
   }
   int kps = K;
   if (splits > 1) {
@@ -135,7 +137,7 @@ int mlp_gemm(mc_mlp* h, bool a_mc, bool b_nc, const float* A, int lda, const flo
   MC_CHECK_LAUNCH();
   h->launches++;
   if (splits > 1) {
-    mlp_splitk_epilogue_kernel<<<cdiv((int64_t)M * N / 4, 256), 256, 0, st>>>(h->d_part, splits, C, M, N, epi, bias);
+    mlp_splitk_epilogue_kernel<<<cdiv((int64_t)M * N / 4, 256), 256, 0, st>>>(h->d_part, splits, C, M, N, epi, bias, mask, ldmask);
     MC_CHECK_LAUNCH();
     h->launches++;
   }

@@ -49,8 +49,11 @@ mlp_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   float csum = 0.f;
   const bool do_colsum = A_MC && colsum != nullptr && blockIdx.y == 0;
 
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
-    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // global -> register loads of one k-tile (issued one tile ahead of the math: the loop is latency-bound otherwise, a
+  // 64 x 64 x 200 tile spent ~1 us per 16-deep k step waiting for L2)
+  auto load_tile = [&](int k0, float4& a4, float4& b4) {
+    a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (A_MC) {
       const int k = k0 + (tid >> 4), m = m0 + (tid & 15) * 4;
       if (k < kend && m < M) a4 = *reinterpret_cast<const float4*>(A + (int64_t)k * lda + m);
@@ -65,7 +68,11 @@ mlp_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
       const int n = n0 + (tid >> 2), k = k0 + (tid & 3) * 4;
       if (n < N && k < kend) b4 = *reinterpret_cast<const float4*>(B + (int64_t)n * ldb + k);
     }
-    __syncthreads();
+  };
+  float4 a4, b4;
+  load_tile(kbeg, a4, b4);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    __syncthreads();   // the previous tile's math is done with As / Bs
     if (A_MC) {
       *reinterpret_cast<float4*>(&As[tid >> 4][(tid & 15) * 4]) = a4;
     } else {
@@ -79,6 +86,7 @@ mlp_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
       Bs[kk + 0][r] = b4.x; Bs[kk + 1][r] = b4.y; Bs[kk + 2][r] = b4.z; Bs[kk + 3][r] = b4.w;
     }
     __syncthreads();
+    if (k0 + BK < kend) load_tile(k0 + BK, a4, b4);   // in flight during the math below
     if (do_colsum && tid < BM) {
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) csum += As[kk][tid];   // rows past kend were stored as zeros
@@ -131,7 +139,7 @@ mlp_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 
 // Sum the split-K partials in slice order (deterministic) and apply the epilogue.
 __global__ void mlp_splitk_epilogue_kernel(const float* __restrict__ part, int splits, float* __restrict__ C, int M, int N,
-                                           int epi, const float* __restrict__ bias) {
+                                           int epi, const float* __restrict__ bias, const float* __restrict__ mask, int ldmask) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)M * N / 4;
   if (t >= total) return;
@@ -147,6 +155,11 @@ __global__ void mlp_splitk_epilogue_kernel(const float* __restrict__ part, int s
     if (epi == MLP_EPI_BIAS_RELU) {
       s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
     }
+  } else if (epi == MLP_EPI_RELU_MASK) {
+    const int64_t m = (t * 4) / N;
+    const float4 mk = *reinterpret_cast<const float4*>(mask + m * ldmask + n);
+    s.x = mk.x > 0.f ? s.x : 0.f; s.y = mk.y > 0.f ? s.y : 0.f;
+    s.z = mk.z > 0.f ? s.z : 0.f; s.w = mk.w > 0.f ? s.w : 0.f;
   }
   *reinterpret_cast<float4*>(C + t * 4) = s;
 }
@@ -268,12 +281,25 @@ mlp_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict_
     s = p[i] * p[i];
   }
   block_ssq_store(s, ssq_next + blockIdx.x);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nrows > 0.f) {
-    float ssq = 0.f;
-    for (int b = 0; b < n_ssq; ++b) ssq += ssq_prev[b];
-    const double data = wsum != 0.f ? (double)stats[1] / (double)wsum : 0.0;
-    loss_acc[0] += (data + 0.5 * (double)alpha / (double)nrows * (double)ssq) * (double)nrows;
-    loss_acc[1] += (double)nrows;
+  if (blockIdx.x == 0 && nrows > 0.f) {
+    // sum(W^2) before this update: the per-block partials of the previous step, reduced by the whole block in a fixed
+    // order (a single thread walking ~3 400 partials was 70 of the kernel's 76 us)
+    __shared__ float red2[MLP_ADAM_THREADS];
+    float part = 0.f;
+    for (int b = threadIdx.x; b < n_ssq; b += MLP_ADAM_THREADS) part += ssq_prev[b];
+    __syncthreads();
+    red2[threadIdx.x] = part;
+    __syncthreads();
+    for (int o = MLP_ADAM_THREADS / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red2[threadIdx.x] += red2[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const float ssq = red2[0];
+      const double data = wsum != 0.f ? (double)stats[1] / (double)wsum : 0.0;
+      loss_acc[0] += (data + 0.5 * (double)alpha / (double)nrows * (double)ssq) * (double)nrows;
+      loss_acc[1] += (double)nrows;
+    }
   }
 }
 

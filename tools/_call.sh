@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_decode.py -x -q -m gpu > gpurun_out/c19_tests.log 2>&1; echo tests rc=$?; tail -12 gpurun_out/c19_tests.log | cut -c1-300
-bash tools/ncu_capture.sh fp32 > gpurun_out/c18_capture_fp32.log 2>&1; tail -12 gpurun_out/c18_capture_fp32.log
+timeout 900 python -m pytest tests/test_gpu_decode.py tests/test_gpu_callers.py tests/test_gpu_mlp.py tests/test_gpu_trainer.py -x -q -m gpu > gpurun_out/c22_tests.log 2>&1; echo tests rc=$?; tail -8 gpurun_out/c22_tests.log | cut -c1-300
