@@ -235,6 +235,27 @@ __device__ __forceinline__ float tanh_approx(float x) {
 
 }  // namespace ptx
 
+// four consecutive residual values as loaded from memory (kept packed while in flight)
+template <typename T>
+struct ResVec;
+template <>
+struct ResVec<float> {
+  typedef float4 type;
+  __device__ __forceinline__ static float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ static float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ static void unpack(const float4& v, float (&r)[4]) { r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
+};
+template <>
+struct ResVec<__nv_bfloat16> {
+  typedef uint2 type;
+  __device__ __forceinline__ static uint2 zero() { return make_uint2(0u, 0u); }
+  __device__ __forceinline__ static uint2 load(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ static void unpack(const uint2& v, float (&r)[4]) {
+    r[0] = __uint_as_float(v.x << 16); r[1] = __uint_as_float(v.x & 0xFFFF0000u);
+    r[2] = __uint_as_float(v.y << 16); r[3] = __uint_as_float(v.y & 0xFFFF0000u);
+  }
+};
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row (1024 B) swizzle atoms stacked
 // along M/N.  start address >> 4 | LBO(ignored)=1 | SBO = 1024 >> 4 | version 1 | SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -303,7 +324,9 @@ struct TcCfg<float> {
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_BUDGET = 227 * 1024;
 constexpr int TC_EPI_BYTES = 0;                                                  // the epilogue stores straight from registers
-constexpr int TC_FIXED_BYTES = 1024 /*align slack*/ + TC_EPI_BYTES + 2 * 1280 * 4 + 512;
+constexpr int TC_GATE_ROWS = 4;                                                   // patches a 128-row tile can span (7x7 maps: 49 rows each)
+constexpr int TC_GATE_BYTES = TC_MAX_STAGES * TC_GATE_ROWS * 128;                 // SE gate chunks of every stage (project layers)
+constexpr int TC_FIXED_BYTES = 1024 /*align slack*/ + TC_EPI_BYTES + TC_GATE_BYTES + 2 * 1280 * 4 + 512;
 
 // bytes of one pipeline stage for a layer with BN output columns per block (1024-aligned)
 template <typename T>
@@ -338,7 +361,7 @@ inline int tc_num_stages_res(int w_bytes) {
 template <typename T, bool GATED, bool RELU = false, bool POOL = false>
 __global__ void __launch_bounds__(tc_threads<GATED>(), 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-             const __grid_constant__ CUtensorMap tmWlo, const PwTcArgs p) {
+             const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmG, const PwTcArgs p) {
   using Cfg = TcCfg<T>;
   const int S = p.stages;
   const int W_BYTES = (p.BN * 128 + 1023) / 1024 * 1024;       // one W operand tile (1024-aligned)
@@ -353,8 +376,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* w_base = smem;                                      // resident weights (1024-aligned tiles), may be empty
   uint8_t* stage_base = smem + W_RES_BYTES;
   uint8_t* epi_base = stage_base + (size_t)S * STAGE_BYTES;
-  float* pool_s = (float*)epi_base;                            // POOL: [group][warp of the group][128 columns]
-  float* sc_s = (float*)(epi_base + TC_EPI_BYTES + (POOL ? TC_POOL_BYTES : 0));
+  uint8_t* gate_s = epi_base;                                  // GATED: [stage][4 patches][128 B] SE gate chunk of the stage's k-chunk
+  float* pool_s = (float*)(epi_base + TC_GATE_BYTES);          // POOL: [group][warp of the group][128 columns]
+  float* sc_s = (float*)(epi_base + TC_EPI_BYTES + TC_GATE_BYTES + (POOL ? TC_POOL_BYTES : 0));
   float* bi_s = sc_s + 1280;
   uint64_t* bars = (uint64_t*)(bi_s + 1280);
   uint64_t* full = bars;                          // [S]   TMA landed
@@ -447,6 +471,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ptx::mbar_expect_tx(&full[s], tx - (uint32_t)Cfg::A_BYTES + 2u * TC_POOL_HW * 128u);
             ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, (int)mt * 2 * TC_POOL_HW);
             ptx::tma_load_2d(st + 64 * 128, &tmA, &full[s], kc * Cfg::KC, ((int)mt * 2 + 1) * TC_POOL_HW);
+          } else if constexpr (GATED) {
+            // + the SE gate of this k-chunk for the (up to four) patches the tile's rows belong to
+            ptx::mbar_expect_tx(&full[s], tx + TC_GATE_ROWS * 128u);
+            ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, m0);
+            ptx::tma_load_2d(gate_s + s * (TC_GATE_ROWS * 128), &tmG, &full[s], kc * Cfg::KC, (int)((mt * (uint32_t)TC_BM) / (uint32_t)p.HW));
           } else {
             ptx::mbar_expect_tx(&full[s], tx);
             ptx::tma_load_2d(st, &tmA, &full[s], kc * Cfg::KC, m0);
@@ -550,90 +579,69 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr int EPCH = 16 / (int)sizeof(T);    // elements per 16-byte chunk
       int s = 0;
       uint32_t ph = 0;
-      // (tile, k-chunk) walked incrementally; `gp` / `gp_n` = gate row of this / the next step's tile row
-      const int n_items = items;
-      int it = blockIdx.x, kc = 0;
-      auto gate_row = [&](int item) -> const T* {
-        const int m = (int)((uint32_t)item / nblk) * TC_BM + r;
-        return (item < n_items && m < (int)p.M) ? (const T*)p.gate + (int64_t)(m / p.HW) * p.K : nullptr;
-      };
-      const T* gp = gate_row(it);
-      uint4 gn0 = make_uint4(0u, 0u, 0u, 0u), gn1 = gn0, gn2 = gn0, gn3 = gn0;   // gate chunks of the next step
-#define MC_GATE_FETCH(ROW, KCHUNK)                                                                        \
-  do {                                                                                                    \
-    const int k0_ = (KCHUNK) * Cfg::KC;                                                                   \
-    const int nch_ = min(8, (p.K - k0_) / EPCH);                                                          \
-    const uint4* src_ = reinterpret_cast<const uint4*>((ROW) + k0_ + j0 * EPCH);                          \
-    if ((ROW) != nullptr) {                                                                               \
-      if (j0 + 0 < nch_) gn0 = __ldg(src_ + 0);                                                           \
-      if (j0 + 1 < nch_) gn1 = __ldg(src_ + 1);                                                           \
-      if (j0 + 2 < nch_) gn2 = __ldg(src_ + 2);                                                           \
-      if (j0 + 3 < nch_) gn3 = __ldg(src_ + 3);                                                           \
-    }                                                                                                     \
-  } while (0)
-      MC_GATE_FETCH(gp, 0);
-      while (it < n_items) {
-        const bool gated = gp != nullptr;
-        const int k0 = kc * Cfg::KC;
-        const int nch = min(8, (p.K - k0) / EPCH);  // chunks that hold real data (the rest is TMA zero fill)
-        const uint4 gq[4] = {gn0, gn1, gn2, gn3};
-        // advance to the next step and start fetching its gate chunks before waiting for this step's data
-        int it_n = it, kc_n = kc + 1;
-        const T* gp_n = gp;
-        if (kc_n == p.k_chunks) {
-          kc_n = 0;
-          it_n = it + (int)gridDim.x;
-          gp_n = gate_row(it_n);
-        }
-        MC_GATE_FETCH(gp_n, kc_n);
-        ptx::mbar_wait(&full[s], ph);
-        const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
+      // The gate chunk of the stage's k-chunk arrives with the A tile (TMA box of four gate rows: the patches the tile's
+      // rows can belong to), so the transform reads it from shared memory: fetched from L2 by the threads themselves, one
+      // step ahead, its ~700-cycle round trip was not hidden behind a ~300-cycle step (ncu: transform warps busy 92 %, the
+      // MMA issuer starved, tensor pipe 41 % on b15.project).  All shared-memory loads of a step are issued before the first
+      // dependent instruction (the inline-asm accesses keep program order).
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const uint32_t mt = (uint32_t)it / nblk;
+        const uint32_t m = mt * TC_BM + (uint32_t)r;
+        const uint32_t prow = min((uint32_t)(TC_GATE_ROWS - 1), m / (uint32_t)p.HW - (mt * TC_BM) / (uint32_t)p.HW);   // rows past M: any patch (A is zero)
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const int k0 = kc * Cfg::KC;
+          const int nch = min(8, (p.K - k0) / EPCH);  // chunks that hold real data (the rest is TMA zero fill)
+          ptx::mbar_wait(&full[s], ph);
+          const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
+          const uint32_t g_u32 = ptx::smem_u32(gate_s + s * (TC_GATE_ROWS * 128)) + prow * 128u + (uint32_t)j0 * 16u;
+          uint4 raw[4], gq[4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = j0 + jj;
-          if (j < nch && !(p.exp_flags & 4)) {
-            const uint32_t phys = a_hi + (((uint32_t)j ^ xr) << 4);
-            uint4 raw = ptx::lds128(phys);
-            const uint4 gj = gq[jj];
-            if (Cfg::TF32) {
-              float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-              if (gated) {
-                v[0] *= __uint_as_float(gj.x); v[1] *= __uint_as_float(gj.y);
-                v[2] *= __uint_as_float(gj.z); v[3] *= __uint_as_float(gj.w);
-              }
-              uint4 hi, lo;
-              uint32_t* hp = &hi.x;
-              uint32_t* lp = &lo.x;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                hp[e] = __float_as_uint(v[e]) & 0xFFFFE000u;   // exact TF32 value
-                lp[e] = tf32_lo_bits(__float_as_uint(v[e]));     // remainder, rounded to TF32
-              }
-              if (gated) ptx::sts128(phys, hi);
-              ptx::sts128(phys + Cfg::A_BYTES, lo);
-            } else if (gated) {
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-              const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gj);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], gh[e]);
-              ptx::sts128(phys, raw);
+          for (int jj = 0; jj < 4; ++jj) {
+            raw[jj] = make_uint4(0u, 0u, 0u, 0u);
+            gq[jj] = raw[jj];
+            if (j0 + jj < nch && !(p.exp_flags & 4)) {
+              raw[jj] = ptx::lds128(a_hi + (((uint32_t)(j0 + jj) ^ xr) << 4));
+              gq[jj] = ptx::lds128(g_u32 + (uint32_t)jj * 16u);
             }
-          } else if (Cfg::TF32 && j >= nch) {
-            // zero-filled K tail: the lo copy must be zero too
-            ptx::sts128(a_hi + Cfg::A_BYTES + (((uint32_t)j ^ xr) << 4), make_uint4(0u, 0u, 0u, 0u));
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj;
+            const uint32_t phys = a_hi + (((uint32_t)j ^ xr) << 4);
+            if (j < nch && !(p.exp_flags & 4)) {
+              if (Cfg::TF32) {
+                float v[4] = {__uint_as_float(raw[jj].x) * __uint_as_float(gq[jj].x), __uint_as_float(raw[jj].y) * __uint_as_float(gq[jj].y),
+                              __uint_as_float(raw[jj].z) * __uint_as_float(gq[jj].z), __uint_as_float(raw[jj].w) * __uint_as_float(gq[jj].w)};
+                uint4 hi, lo;
+                uint32_t* hp = &hi.x;
+                uint32_t* lp = &lo.x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  hp[e] = __float_as_uint(v[e]) & 0xFFFFE000u;   // exact TF32 value
+                  lp[e] = tf32_lo_bits(__float_as_uint(v[e]));     // remainder, rounded to TF32
+                }
+                ptx::sts128(phys, hi);
+                ptx::sts128(phys + Cfg::A_BYTES, lo);
+              } else {
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw[jj]);
+                const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq[jj]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], gh[e]);
+                ptx::sts128(phys, raw[jj]);
+              }
+            } else if (Cfg::TF32 && j >= nch) {
+              // zero-filled K tail: the lo copy must be zero too
+              ptx::sts128(phys + Cfg::A_BYTES, make_uint4(0u, 0u, 0u, 0u));
+            }
+          }
+          ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+          ptx::mbar_arrive(&ready[s]);
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
           }
         }
-        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
-        ptx::mbar_arrive(&ready[s]);
-        if (++s == S) {
-          s = 0;
-          ph ^= 1;
-        }
-        it = it_n;
-        kc = kc_n;
-        gp = gp_n;
       }
-#undef MC_GATE_FETCH
     } else if constexpr (Cfg::TF32) {
       // ungated fp32: one thread per tile row; the raw fp32 tile stays in place as the hi operand
       // (kind::tf32 reads only the upper 19 bits), only the lo operand a - tf32(a) is written.
@@ -778,6 +786,25 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         continue;
       }
       for (int c0 = 0; c0 < ncols; c0 += 32) {
+        // residual (skip connection) values of this column group: all eight loads in flight BEFORE the accumulator is
+        // read.  Issued where they are consumed they sit between the lane exchanges and serialise -- eight exposed L2 / HBM
+        // round trips per group (ncu on b2.project: 41 % of the epilogue's time).
+        [[maybe_unused]] typename ResVec<T>::type rpre[2][2][2];
+        if constexpr (GATED) {
+          if (res_t != nullptr) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+              for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                  const int cb = odd ? 16 * pr + 8 + 2 * (q - 1) : 16 * pr + 2 * q;
+                  const int row = 16 * h2 + 8 * rh + lr;
+                  rpre[h2][pr][rh] = ResVec<T>::zero();
+                  if (row < rows_valid && c0 + cb < ncols) rpre[h2][pr][rh] = ResVec<T>::load(res_t + row * p.N + c0 + cb);
+                }
+          }
+        }
         // both 16-lane halves in flight before the single wait: the tcgen05.ld round trip is the longest
         // latency of the epilogue (serialising the halves cost 40 % on the expand layers)
         uint32_t v[2][16];
@@ -832,7 +859,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int off = row * p.N + c0 + cb;
                 if (res_t != nullptr) {
                   float r[4];
-                  load4<T>(res_t + off, r);
+                  if constexpr (GATED) ResVec<T>::unpack(rpre[h2][pr][rh], r);
+                  else load4<T>(res_t + off, r);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) y[e] += r[e];
                 }
@@ -895,6 +923,22 @@ inline int make_map(CUtensorMap* map, bool f32, const void* base, int64_t rows, 
   return MC_OK;
 }
 
+// SE gate map: dim0 = K (contiguous), dim1 = patches; box = 128 bytes of K x TC_GATE_ROWS patches; plain layout; OOB -> 0.
+inline int make_gate_map(CUtensorMap* map, bool f32, const void* base, int64_t rows, int K) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int es = f32 ? 4 : 2;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)K * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)TC_GATE_ROWS};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled (gate) failed with CUresult " + std::to_string((int)r));
+  return MC_OK;
+}
+
 struct PwTcLayer {
   bool present = false;
   int N = 0, K = 0, BN = 0, n_blocks = 0, k_chunks = 0, act = 0;
@@ -907,6 +951,9 @@ struct PwTcLayer {
   const void* a_ptr[2] = {nullptr, nullptr};
   int64_t a_rows[2] = {0, 0};
   CUtensorMap tmA[2];
+  // gated launches: map over the SE gate [patches][K] with a {128 bytes of K, 4 patches} box, no swizzle
+  const void* g_ptr = nullptr;
+  CUtensorMap tmG;
   // POOL launch (head conv): map with a 49-row box over the same buffer
   const void* apool_ptr = nullptr;
   CUtensorMap tmApool;
@@ -1086,19 +1133,25 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   const int64_t items = a.m_tiles * a.n_blocks;
   const int grid = (int)std::min<int64_t>(items, plan->num_sms);
   const bool gated = a.gate != nullptr;
+  if (gated && l.g_ptr != a.gate) {
+    int rc = make_gate_map(&l.tmG, f32, a.gate, plan->max_batch, l.K);
+    if (rc) return rc;
+    l.g_ptr = a.gate;
+  }
+  const CUtensorMap& tmG = gated ? l.tmG : l.tmW;   // ungated kernels never touch it
   if (plan->relu_variant) {   // MLP head (fp32, ungated)
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
-    pw_tc_kernel<float, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+    pw_tc_kernel<float, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   } else if (f32 && gated)
-    pw_tc_kernel<float, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+    pw_tc_kernel<float, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   else if (f32)
-    pw_tc_kernel<float, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+    pw_tc_kernel<float, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   else if (gated)
-    pw_tc_kernel<__nv_bfloat16, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+    pw_tc_kernel<__nv_bfloat16, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   else
-    pw_tc_kernel<__nv_bfloat16, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, a);
+    pw_tc_kernel<__nv_bfloat16, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   MC_CHECK_LAUNCH();
   if (a.dbg) {
     long long d[32];
@@ -1152,8 +1205,8 @@ inline int pw_tc_run_pool(PwTcPlan* plan, int id, const void* A, int nb, float* 
   a.m_tiles = (nb + 1) / 2;
   const int64_t items = a.m_tiles * a.n_blocks;
   const int grid = (int)std::min<int64_t>(items, plan->num_sms);
-  if (f32) pw_tc_kernel<float, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, a);
-  else pw_tc_kernel<__nv_bfloat16, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, a);
+  if (f32) pw_tc_kernel<float, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
+  else pw_tc_kernel<__nv_bfloat16, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
   MC_CHECK_LAUNCH();
   return MC_OK;
 }
