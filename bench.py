@@ -53,20 +53,30 @@ B0 = [  # (k, stride, expand, c_in, c_out, h_in)
 ]
 
 
+def fused_blocks() -> int:
+    """Bit mask of the MBConv blocks whose expand + depthwise run as ONE kernel (library default: b1; MC_FUSE_MASK)."""
+    return int(os.environ.get("MC_FUSE_MASK", "2"), 16)
+
+
 def layer_bytes(e: int) -> dict[int, tuple[str, float]]:
-    """layer id (mc_extractor_profile ids) -> (name, algorithmic bytes per patch)."""
+    """layer id (mc_extractor_profile ids) -> (name, algorithmic bytes per patch).  A fused block's single kernel is
+    timed under the depthwise id and carries the algorithmic bytes of BOTH layers (SURVEY section 8d's per-layer figures:
+    the traffic fusion removes is credited, ncu's dram__bytes shows what actually moves)."""
     out = {0: ("stem(crop+norm+conv3x3s2)", 224 * 224 * 3 + 112 * 112 * 32 * e)}
     for b, (k, s, ex, ci, co, h) in enumerate(B0):
         ho = (h + s - 1) // s
         cm = ci * ex
-        if ex != 1:
-            out[1 + 4 * b] = (f"b{b}.expand", h * h * (ci + cm) * e)
-        out[2 + 4 * b] = (f"b{b}.depthwise", (h * h + ho * ho) * cm * e)
+        if ex != 1 and (fused_blocks() >> b) & 1:
+            out[2 + 4 * b] = (f"b{b}.expand+depthwise(fused)", h * h * (ci + cm) * e + (h * h + ho * ho) * cm * e)
+        else:
+            if ex != 1:
+                out[1 + 4 * b] = (f"b{b}.expand", h * h * (ci + cm) * e)
+            out[2 + 4 * b] = (f"b{b}.depthwise", (h * h + ho * ho) * cm * e)
         out[3 + 4 * b] = (f"b{b}.se", cm * 4 * 2)
         skip = s == 1 and ci == co
         out[4 + 4 * b] = (f"b{b}.project", ho * ho * (cm + co * (2 if skip else 1)) * e)
-    out[65] = ("conv_head", 49 * (320 + 1280) * e)
-    out[66] = ("avgpool", 49 * 1280 * e + 1280 * 4)
+    # K7: the head conv pools in its epilogue (one kernel, timed under id 65); algorithmic bytes of both layers
+    out[65] = ("conv_head+avgpool(fused)", 49 * (320 + 1280) * e + 49 * 1280 * e + 1280 * 4)
     return out
 
 
@@ -125,20 +135,26 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-NCU_CAPTURE_OF_LAYER = {0: "stem", 6: "dw_b1", 18: "dw_b4", 5: "exp_b1", 12: "proj_b2", 65: "head_conv"}
+# layer id -> capture name in profiles/r02_kernels_<mode>.csv (tools/ncu_capture.sh)
+NCU_CAPTURE_OF_LAYER = {0: "stem", 6: "fused_b1", 2: "dw_b0", 18: "dw_b4", 38: "dw_b9", 9: "exp_b2", 12: "proj_b2", 64: "proj_b15",
+                        65: "head_pool"}
+PROFILE_TAG = "r02"
 
 
 def ncu_traffic(layer_id: int, mode: str, patches_per_launch: float):
-    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of the
-    same kernel (profiles/r01_summary_<mode>.json, 500 patches per launch), scaled to this run's launch
-    size.  None when that layer has no committed capture."""
-    f = ROOT / "profiles" / f"r01_summary_{mode}.json"
+    """(DRAM bytes per launch, source) of the dominant kernel, from the committed `ncu --set full` capture of the same
+    kernel (profiles/<tag>_summary_<mode>.json: dram__bytes_read.sum + dram__bytes_write.sum at 500 patches per launch),
+    scaled to this run's launch size.  (None, reason) when that layer has no committed capture: the number is never
+    measured inside a timed run (a run under ncu is not a bench run)."""
+    f = ROOT / "profiles" / f"{PROFILE_TAG}_summary_{mode}.json"
     name = NCU_CAPTURE_OF_LAYER.get(layer_id)
     if name is None or not f.exists():
-        return None
+        return None, "no committed ncu capture of this kernel"
     d = json.loads(f.read_text())
     mb = d.get("traffic_MB_per_launch", {}).get(name)
-    return None if mb is None else mb * 1e6 * patches_per_launch / d["patches_per_launch"]
+    if mb is None:
+        return None, "no committed ncu capture of this kernel"
+    return mb * 1e6 * patches_per_launch / d["patches_per_launch"], f"profiles/{f.name}:{name} (ncu --set full, {d['patches_per_launch']} patches per launch, scaled)"
 
 
 def measured_peaks() -> tuple[float, str]:
@@ -333,6 +349,7 @@ def run_b200(args, rank: int, world: int, local: int):
     achieved = dom_bytes * patches_per_launch / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     share = float(ms_all[dominant] / ms_all.sum()) if ms_all.sum() > 0 else 0.0
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = ncu_traffic(dominant, args.mode, patches_per_launch)
     table = sorted(((float(ms_all[i]), lbytes.get(i, (str(i), 0))[0]) for i in range(67) if ms_all[i] > 0), reverse=True)
     if args.profile_out:
         rows = ["layer_id,name,ms_per_step,launches,algorithmic_MB_per_patch,achieved_GBps,frac_of_hbm_peak,share_of_profiled_time"]
@@ -364,7 +381,7 @@ def run_b200(args, rank: int, world: int, local: int):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(dominant, args.mode, patches_per_launch),
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": dom_bytes * patches_per_launch, "peak_source": peak_src,
                      "algorithmic_bytes_per_patch": dom_bytes, "avg_launch_ms": dom_ms,
                      "patches_per_launch": patches_per_launch, "share_of_step": share,
