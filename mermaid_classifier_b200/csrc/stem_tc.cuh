@@ -102,8 +102,16 @@ stem_tc_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__
     struct RowGeo {
       const uint8_t* data;
       int64_t pitch;
+      const uint8_t* end;     // one past the last byte of the image
       int H, W, row0, x0;
       bool fast;
+    };
+    auto row_src = [&](const RowGeo& g, int r) {
+      return g.data + (int64_t)reflect_fast(g.row0 + r, g.H) * g.pitch + (int64_t)g.x0 * 3;
+    };
+    auto row_safe = [&](const RowGeo& g, const uint8_t* src) {
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15;
+      return a0 >= reinterpret_cast<uintptr_t>(g.data) && a0 + STEM_ROW_CHUNKS * 16 <= reinterpret_cast<uintptr_t>(g.end);
     };
     auto geo_of = [&](int it) {
       RowGeo g;
@@ -116,9 +124,11 @@ stem_tc_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__
       g.W = im.width;
       g.row0 = pt.row - 112 + 2 * STEM_BAND * band;   // image row of staged row 0 (before reflection)
       g.x0 = pt.col - 112;
-      // fast rows: the 224 patch columns are contiguous in the image, with 6 pixels of slack either side for the
-      // aligned 16-byte chunks that straddle the ends
-      g.fast = g.x0 >= 6 && g.x0 + 230 <= g.W;
+      // fast items: no reflection in x, the 224 patch columns of a row are 672 contiguous bytes of the image.  The aligned
+      // 16-byte chunks that cover them reach up to 15 bytes before and 31 bytes past the row segment: a row whose chunks would
+      // leave the image buffer (first / last image row) is gathered per pixel instead (row_safe)
+      g.fast = g.x0 >= 0 && g.x0 + 224 <= g.W;
+      g.end = g.data + (int64_t)(g.H - 1) * g.pitch + (int64_t)g.W * 3;
       return g;
     };
     // staged rows of an item: r = 0..32, patch row 32*band + r; patch row 224 is the SAME pad (never staged, never read)
@@ -131,9 +141,9 @@ stem_tc_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__
         const int r = idx / STEM_ROW_CHUNKS, c = idx - r * STEM_ROW_CHUNKS;
         pre[q] = make_uint4(0u, 0u, 0u, 0u);
         if (g.fast && r < nrows) {
-          const uint8_t* src = g.data + (int64_t)reflect_fast(g.row0 + r, g.H) * g.pitch + (int64_t)g.x0 * 3;
+          const uint8_t* src = row_src(g, r);
           const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15;
-          pre[q] = __ldg(reinterpret_cast<const uint4*>(a0) + c);
+          if (row_safe(g, src)) pre[q] = __ldg(reinterpret_cast<const uint4*>(a0) + c);
         }
       }
     };
@@ -144,12 +154,17 @@ stem_tc_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__
         for (int q = 0; q < STEM_PRE; ++q) {
           const int idx = tid + q * NB_THREADS;
           const int r = idx / STEM_ROW_CHUNKS, c = idx - r * STEM_ROW_CHUNKS;
-          if (r < nrows) *reinterpret_cast<uint4*>(rb + r * STEM_ROW_PITCH + c * 16) = pre[q];
+          if (r < nrows && row_safe(g, row_src(g, r))) *reinterpret_cast<uint4*>(rb + r * STEM_ROW_PITCH + c * 16) = pre[q];
         }
-        if (tid < nrows) {
-          const uint8_t* src = g.data + (int64_t)reflect_fast(g.row0 + tid, g.H) * g.pitch + (int64_t)g.x0 * 3;
-          roff_s[buf * 40 + tid] = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+        // rows whose aligned chunks would leave the image buffer: per-byte copy of the 672 bytes (one warp per such row)
+        for (int r = tid >> 5; r < nrows; r += NB_THREADS / 32) {
+          const uint8_t* src = row_src(g, r);
+          if (!row_safe(g, src)) {
+            const int o = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+            for (int b = tid & 31; b < 672; b += 32) rb[r * STEM_ROW_PITCH + o + b] = src[b];
+          }
         }
+        if (tid < nrows) roff_s[buf * 40 + tid] = (int)(reinterpret_cast<uintptr_t>(row_src(g, tid)) & 15);
       } else {
         // the window crosses the left / right image border: per-pixel reflect gather
         for (int idx = tid; idx < nrows * 224; idx += NB_THREADS) {
