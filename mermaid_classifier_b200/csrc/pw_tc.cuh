@@ -329,13 +329,19 @@ constexpr int TC_GATE_BYTES = TC_MAX_STAGES * TC_GATE_ROWS * 128;               
 constexpr int TC_FIXED_BYTES = 1024 /*align slack*/ + TC_EPI_BYTES + TC_GATE_BYTES + 2 * 1280 * 4 + 512;
 
 // bytes of one pipeline stage for a layer with BN output columns per block (1024-aligned)
+// The TF32 lo operand of A is produced by the transform warps, not by TMA: it lives in its own two-slot ring, so the TMA
+// ring holds one A tile (+ the W tiles) per stage and is a stage deeper for the same shared memory.  With hi + lo of A AND W in
+// every stage the late layers fitted three stages; their time per k-chunk follows (TMA latency + transform + MMA) / stages
+// (measured: removing the MMAs altogether only took b15.project from 0.242 to 0.163 ms), so depth is what they lack.
+template <typename T>
+constexpr int tc_lo_ring_bytes() { return TcCfg<T>::TF32 ? 2 * TcCfg<T>::A_BYTES : 0; }
 template <typename T>
 constexpr int tc_stage_bytes(int BN) {
-  return TcCfg<T>::NA * TcCfg<T>::A_BYTES + TcCfg<T>::NW * ((BN * 128 + 1023) / 1024 * 1024);
+  return TcCfg<T>::A_BYTES + TcCfg<T>::NW * ((BN * 128 + 1023) / 1024 * 1024);
 }
 template <typename T>
-inline int tc_num_stages(int BN) {
-  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES) / tc_stage_bytes<T>(BN);
+inline int tc_num_stages(int BN, int extra_fixed = 0) {
+  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES - extra_fixed - tc_lo_ring_bytes<T>()) / tc_stage_bytes<T>(BN);
   return s > TC_MAX_STAGES ? TC_MAX_STAGES : s;
 }
 // resident-weight layout: W region of n_blocks * k_chunks * NW tiles, stages carry the A operands only
@@ -346,7 +352,7 @@ inline int tc_w_res_bytes(int BN, int n_blocks, int k_chunks) {
 }
 template <typename T>
 inline int tc_num_stages_res(int w_bytes) {
-  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES - w_bytes) / (TcCfg<T>::NA * TcCfg<T>::A_BYTES);
+  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES - w_bytes - tc_lo_ring_bytes<T>()) / TcCfg<T>::A_BYTES;
   return s > TC_MAX_STAGES ? TC_MAX_STAGES : s;
 }
 
@@ -370,12 +376,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // front layers then depended on which L2 slices the weight allocation happened to hash to (4.8 vs 3.2 TB/s on b1.expand).
   const bool w_res = p.w_res != 0;
   const int W_RES_BYTES = w_res ? p.n_blocks * p.k_chunks * Cfg::NW * W_BYTES : 0;
-  const int STAGE_BYTES = Cfg::NA * Cfg::A_BYTES + (w_res ? 0 : Cfg::NW * W_BYTES);
+  const int STAGE_BYTES = Cfg::A_BYTES + (w_res ? 0 : Cfg::NW * W_BYTES);   // A (hi) tile [+ W hi, W lo tiles]
+  constexpr int LO_SLOTS = Cfg::TF32 ? 2 : 0;                                // ring of the TF32 lo operand of A
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* w_base = smem;                                      // resident weights (1024-aligned tiles), may be empty
   uint8_t* stage_base = smem + W_RES_BYTES;
-  uint8_t* epi_base = stage_base + (size_t)S * STAGE_BYTES;
+  uint8_t* lo_base = stage_base + (size_t)S * STAGE_BYTES;
+  uint8_t* epi_base = lo_base + LO_SLOTS * Cfg::A_BYTES;
   uint8_t* gate_s = epi_base;                                  // GATED: [stage][4 patches][128 B] SE gate chunk of the stage's k-chunk
   float* pool_s = (float*)(epi_base + TC_GATE_BYTES);          // POOL: [group][warp of the group][128 columns]
   float* sc_s = (float*)(epi_base + TC_EPI_BYTES + TC_GATE_BYTES + (POOL ? TC_POOL_BYTES : 0));
@@ -387,7 +395,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = bars + 3 * TC_MAX_STAGES;     // [4]   accumulator complete
   uint64_t* tempty = tfull + 4;                   // [4]   accumulator drained
   uint64_t* wbar = tempty + 4;                    // resident weights landed
-  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
+  uint64_t* lo_empty = wbar + 1;                  // [2]   MMAs reading the lo slot retired
+  uint32_t* tmem_slot = (uint32_t*)(lo_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // accumulator stages in TMEM: 4 x 128 columns when the block fits, else 2 x 256
@@ -426,6 +435,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::mbar_init(&empty[s], 1);
     }
     ptx::mbar_init(wbar, 1);
+    ptx::mbar_init(&lo_empty[0], 1);
+    ptx::mbar_init(&lo_empty[1], 1);
     for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&tfull[s], 1);
       ptx::mbar_init(&tempty[s], 128);
@@ -447,7 +458,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       const uint32_t w_tile_tx = (uint32_t)p.BN * 128u;   // bytes one W box delivers
-      const uint32_t tx = Cfg::A_BYTES + (w_res ? 0u : w_tile_tx * (Cfg::TF32 ? 2u : 1u));
+      const bool skip_wlo = (p.exp_flags & 64) != 0;   // timing experiment: do not fetch the W lo tile (results wrong by design)
+      const uint32_t tx = Cfg::A_BYTES + (w_res ? 0u : w_tile_tx * ((Cfg::TF32 && !skip_wlo) ? 2u : 1u));
       if (w_res) {
         ptx::mbar_expect_tx(wbar, w_tile_tx * (uint32_t)(p.n_blocks * p.k_chunks * Cfg::NW));
         for (int nb_ = 0; nb_ < p.n_blocks; ++nb_)
@@ -482,8 +494,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           if (!w_res) {
             if (Cfg::TF32) {
-              ptx::tma_load_2d(st + 2 * Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
-              ptx::tma_load_2d(st + 2 * Cfg::A_BYTES + W_BYTES, &tmWlo, &full[s], kc * Cfg::KC, n0);
+              ptx::tma_load_2d(st + Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
+              if (!skip_wlo) ptx::tma_load_2d(st + Cfg::A_BYTES + W_BYTES, &tmWlo, &full[s], kc * Cfg::KC, n0);
             } else {
               ptx::tma_load_2d(st + Cfg::A_BYTES, &tmW, &full[s], kc * Cfg::KC, n0);
             }
@@ -508,6 +520,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr uint32_t DESC_LBO = 1u << 16;
       const uint32_t stage_lo = ptx::smem_u32(stage_base) >> 4, w_lo_base = ptx::smem_u32(w_base) >> 4;
       const uint32_t stage_step = (uint32_t)STAGE_BYTES >> 4, w_step = (uint32_t)W_BYTES >> 4;
+      const uint32_t lo_ring_lo = ptx::smem_u32(lo_base) >> 4;
+      uint32_t cc = 0;   // k-chunk counter of this CTA: lo slot cc & 1
       int s = 0;
       uint32_t ph = 0;
       int li = 0;
@@ -525,13 +539,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         w_tempty += ptx::mbar_wait_timed(&tempty[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_cols);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++cc) {
           w_full += ptx::mbar_wait_timed(transform ? &ready[s] : &full[s], ph);
           ptx::tc_fence_after();
           // low descriptor words ((address >> 4) | LBO); every operand tile lives below 256 KB, so the 14-bit field never wraps
           const uint32_t a_lo = (stage_lo + (uint32_t)s * stage_step) | DESC_LBO;
+          [[maybe_unused]] const uint32_t l_lo = (lo_ring_lo + (cc & 1u) * (uint32_t)(Cfg::A_BYTES >> 4)) | DESC_LBO;   // TF32 lo operand of A
           const uint32_t w_lo = w_res ? ((w_lo_base + (uint32_t)((nb_i * p.k_chunks + kc) * Cfg::NW) * w_step) | DESC_LBO)
-                                      : a_lo + (uint32_t)((Cfg::NA * Cfg::A_BYTES) >> 4);
+                                      : a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
           const int krem = p.K - kc * Cfg::KC;
           const int ksteps = (p.exp_flags & 16) ? 0 : (min(krem, Cfg::KC) + Cfg::UK - 1) / Cfg::UK;
 #pragma unroll
@@ -540,7 +555,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const uint32_t acc = (kc | ks) != 0;
               const uint32_t ko = (uint32_t)ks * 2u;   // UK elements = 32 bytes = 2 descriptor units
               if (Cfg::TF32) {
-                const uint64_t ahi = DESC_HI64 | (a_lo + ko), alo = DESC_HI64 | (a_lo + (uint32_t)(Cfg::A_BYTES >> 4) + ko);
+                const uint64_t ahi = DESC_HI64 | (a_lo + ko), alo = DESC_HI64 | (l_lo + ko);
                 const uint64_t whi = DESC_HI64 | (w_lo + ko), wlo = DESC_HI64 | (w_lo + w_step + ko);
                 ptx::mma_ss<true>(d_tmem, alo, whi, idesc, acc);
                 ptx::mma_ss<true>(d_tmem, ahi, wlo, idesc, 1u);
@@ -551,6 +566,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           ptx::mma_commit(&empty[s]);
+          if (Cfg::TF32) ptx::mma_commit(&lo_empty[cc & 1u]);
           if (++s == S) {
             s = 0;
             ph ^= 1;
@@ -584,15 +600,18 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // step ahead, its ~700-cycle round trip was not hidden behind a ~300-cycle step (ncu: transform warps busy 92 %, the
       // MMA issuer starved, tensor pipe 41 % on b15.project).  All shared-memory loads of a step are issued before the first
       // dependent instruction (the inline-asm accesses keep program order).
+      uint32_t cc = 0;   // k-chunk counter of this CTA: lo slot cc & 1
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const uint32_t mt = (uint32_t)it / nblk;
         const uint32_t m = mt * TC_BM + (uint32_t)r;
         const uint32_t prow = min((uint32_t)(TC_GATE_ROWS - 1), m / (uint32_t)p.HW - (mt * TC_BM) / (uint32_t)p.HW);   // rows past M: any patch (A is zero)
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++cc) {
           const int k0 = kc * Cfg::KC;
           const int nch = min(8, (p.K - k0) / EPCH);  // chunks that hold real data (the rest is TMA zero fill)
           ptx::mbar_wait(&full[s], ph);
+          if (Cfg::TF32) ptx::mbar_wait(&lo_empty[cc & 1u], ((cc >> 1) & 1u) ^ 1u);   // the MMAs of two chunks ago are done with the slot
           const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
+          [[maybe_unused]] const uint32_t a_lo_slot = ptx::smem_u32(lo_base + (cc & 1u) * Cfg::A_BYTES) + row_off;
           const uint32_t g_u32 = ptx::smem_u32(gate_s + s * (TC_GATE_ROWS * 128)) + prow * 128u + (uint32_t)j0 * 16u;
           uint4 raw[4], gq[4];
 #pragma unroll
@@ -621,7 +640,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   lp[e] = tf32_lo_bits(__float_as_uint(v[e]));     // remainder, rounded to TF32
                 }
                 ptx::sts128(phys, hi);
-                ptx::sts128(phys + Cfg::A_BYTES, lo);
+                ptx::sts128(a_lo_slot + (((uint32_t)j ^ xr) << 4), lo);
               } else {
                 __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw[jj]);
                 const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq[jj]);
@@ -631,7 +650,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             } else if (Cfg::TF32 && j >= nch) {
               // zero-filled K tail: the lo copy must be zero too
-              ptx::sts128(phys + Cfg::A_BYTES, make_uint4(0u, 0u, 0u, 0u));
+              ptx::sts128(a_lo_slot + (((uint32_t)j ^ xr) << 4), make_uint4(0u, 0u, 0u, 0u));
             }
           }
           ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
@@ -650,25 +669,34 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t xr = (uint32_t)(r & 7);
       int s = 0;
       uint32_t ph = 0;
+      uint32_t cc = 0;   // k-chunk counter of this CTA: lo slot cc & 1
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++cc) {
           const int nch = min(8, (p.K - kc * Cfg::KC) / 4);
           ptx::mbar_wait(&full[s], ph);
+          ptx::mbar_wait(&lo_empty[cc & 1u], ((cc >> 1) & 1u) ^ 1u);   // the MMAs of two chunks ago are done with the slot
           const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
+          const uint32_t a_lo_slot = ptx::smem_u32(lo_base + (cc & 1u) * Cfg::A_BYTES) + row_off;
+          // all loads before the first dependent instruction (the inline-asm shared-memory accesses keep program order)
+          uint4 raw[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t phys = a_hi + (((uint32_t)j ^ xr) << 4);
+            raw[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < nch && !(p.exp_flags & 4)) raw[j] = ptx::lds128(a_hi + (((uint32_t)j ^ xr) << 4));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
             uint4 lo = make_uint4(0u, 0u, 0u, 0u);   // zero-filled K tail: the lo copy must be zero too
             if (j < nch && !(p.exp_flags & 4)) {
-              const uint4 raw = ptx::lds128(phys);
-              lo.x = tf32_lo_bits(raw.x);
-              lo.y = tf32_lo_bits(raw.y);
-              lo.z = tf32_lo_bits(raw.z);
-              lo.w = tf32_lo_bits(raw.w);
+              lo.x = tf32_lo_bits(raw[j].x);
+              lo.y = tf32_lo_bits(raw[j].y);
+              lo.z = tf32_lo_bits(raw[j].z);
+              lo.w = tf32_lo_bits(raw[j].w);
               if (p.exp_flags & 8)   // experiment: write the truncated hi operand explicitly instead of leaving the raw fp32 in place
-                ptx::sts128(phys, make_uint4(raw.x & 0xFFFFE000u, raw.y & 0xFFFFE000u, raw.z & 0xFFFFE000u, raw.w & 0xFFFFE000u));
+                ptx::sts128(a_hi + (((uint32_t)j ^ xr) << 4),
+                            make_uint4(raw[j].x & 0xFFFFE000u, raw[j].y & 0xFFFFE000u, raw[j].z & 0xFFFFE000u, raw[j].w & 0xFFFFE000u));
             }
-            ptx::sts128(phys + Cfg::A_BYTES, lo);
+            ptx::sts128(a_lo_slot + (((uint32_t)j ^ xr) << 4), lo);
           }
           ptx::fence_proxy_async();
           ptx::mbar_arrive(&ready[s]);
@@ -1000,6 +1028,15 @@ inline int pw_tc_add(PwTcPlan* plan, int id, const float* w_host, const float* d
   l.n_blocks = (N + l.BN - 1) / l.BN;
   const int kc = f32 ? TcCfg<float>::KC : TcCfg<__nv_bfloat16>::KC;
   l.k_chunks = (K + kc - 1) / kc;
+  // fp32 layers whose weights do not stay resident stream W hi + lo tiles through the TMA ring: cap the block width so that FOUR
+  // stages fit (ungated: 96 columns -> 40 KB stages; gated: 112 -> 44 KB).  Their k-chunk period is (TMA latency + transform +
+  // MMA) / stages, so the fourth stage is worth more than the wider block.
+  // Measured: project layers -5..7 %, the 14x14 expand layers -9 %; the head conv (1280 = 13.3 x 96: padded blocks) +6 %, so
+  // the cap only applies where 96 divides N.
+  if (f32 && tc_w_res_bytes<float>(l.BN, l.n_blocks, l.k_chunks) > TC_W_RES_MAX && (gated || N % 96 == 0)) {
+    l.BN = pick_bn(N, gated ? 112 : 96);
+    l.n_blocks = (N + l.BN - 1) / l.BN;
+  }
   const size_t n = (size_t)N * K;
   int rc;
   if (f32) {
@@ -1122,12 +1159,13 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   static const bool no_w_res = getenv("MC_TC_NO_WRES") != nullptr;   // experiment switch
   a.w_res = (!no_w_res && w_bytes <= TC_W_RES_MAX) ? 1 : 0;
   size_t smem;
+  const size_t lo_ring = f32 ? tc_lo_ring_bytes<float>() : 0;
   if (a.w_res) {
     a.stages = f32 ? tc_num_stages_res<float>(w_bytes) : tc_num_stages_res<__nv_bfloat16>(w_bytes);
-    smem = TC_FIXED_BYTES + (size_t)w_bytes + (size_t)a.stages * (f32 ? 2 : 1) * TC_BM * 128;
+    smem = TC_FIXED_BYTES + (size_t)w_bytes + lo_ring + (size_t)a.stages * TC_BM * 128;
   } else {
     a.stages = f32 ? tc_num_stages<float>(l.BN) : tc_num_stages<__nv_bfloat16>(l.BN);
-    smem = TC_FIXED_BYTES + (size_t)a.stages * (f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN));
+    smem = TC_FIXED_BYTES + lo_ring + (size_t)a.stages * (f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN));
   }
   a.m_tiles = (M + TC_BM - 1) / TC_BM;
   const int64_t items = a.m_tiles * a.n_blocks;
@@ -1188,7 +1226,7 @@ inline int pw_tc_run_pool(PwTcPlan* plan, int id, const void* A, int nb, float* 
   a.out = feats;
   a.M = (int64_t)nb * TC_POOL_HW;
   a.a_row_off = 0;
-  a.exp_flags = 0;
+  { const char* e_ = getenv("MC_TC_EXP"); a.exp_flags = e_ ? atoi(e_) : 0; }
   a.dbg = nullptr;
   a.N = l.N;
   a.K = l.K;
@@ -1200,8 +1238,8 @@ inline int pw_tc_run_pool(PwTcPlan* plan, int id, const void* A, int nb, float* 
   a.w_res = 0;
   a.pool_nb = nb;
   const int stage_bytes = f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN);
-  a.stages = std::min(TC_MAX_STAGES, (TC_SMEM_BUDGET - TC_FIXED_BYTES - TC_POOL_BYTES) / stage_bytes);
-  const size_t smem = TC_FIXED_BYTES + TC_POOL_BYTES + (size_t)a.stages * stage_bytes;
+  a.stages = f32 ? tc_num_stages<float>(l.BN, TC_POOL_BYTES) : tc_num_stages<__nv_bfloat16>(l.BN, TC_POOL_BYTES);
+  const size_t smem = TC_FIXED_BYTES + TC_POOL_BYTES + (f32 ? tc_lo_ring_bytes<float>() : 0) + (size_t)a.stages * stage_bytes;
   a.m_tiles = (nb + 1) / 2;
   const int64_t items = a.m_tiles * a.n_blocks;
   const int grid = (int)std::min<int64_t>(items, plan->num_sms);
