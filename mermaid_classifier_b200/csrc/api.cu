@@ -887,13 +887,19 @@ static int head_scores_impl(mc_head* h, const float* features_dev, int64_t n, do
     int warps = (int)std::min<int64_t>(8, (96 * 1024) / ((int64_t)K * 4));
     if (warps < 1) return fail(MC_ERR_UNSUPPORTED, "mc_head_scores: too many classes for the row kernel");
     const size_t smem = (size_t)warps * K * sizeof(float);
-    if (smem > 48 * 1024)
-      MC_CUDA(cudaFuncSetAttribute(head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_rows_kernel<<<cdiv(m, warps), warps * 32, smem, st>>>(
-        x, h->dims_p[L], K, h->d_a, h->d_pb, proba_dev ? proba_dev + s * K : nullptr,
-        labels_dev ? labels_dev + s : nullptr, topk, topk_idx_dev ? topk_idx_dev + s * topk : nullptr,
-        topk_val_dev ? topk_val_dev + s * topk : nullptr, m, y_dev ? y_dev + s : nullptr,
-        row_loss_dev ? row_loss_dev + s : nullptr);
+    // labels / top-k only on a calibrated head through the tensor-core chain: the FAST row kernel (head.cuh)
+    const bool fast_rows = use_tc && h->d_a != nullptr && proba_dev == nullptr && y_dev == nullptr && row_loss_dev == nullptr;
+    if (smem > 48 * 1024) {
+      MC_CUDA(cudaFuncSetAttribute(head_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MC_CUDA(cudaFuncSetAttribute(head_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+#define MC_HEAD_ROWS_ARGS                                                                                              \
+  x, h->dims_p[L], K, h->d_a, h->d_pb, proba_dev ? proba_dev + s * K : nullptr, labels_dev ? labels_dev + s : nullptr, topk,   \
+      topk_idx_dev ? topk_idx_dev + s * topk : nullptr, topk_val_dev ? topk_val_dev + s * topk : nullptr, m,                  \
+      y_dev ? y_dev + s : nullptr, row_loss_dev ? row_loss_dev + s : nullptr
+    if (fast_rows) head_rows_kernel<true><<<cdiv(m, warps), warps * 32, smem, st>>>(MC_HEAD_ROWS_ARGS);
+    else head_rows_kernel<false><<<cdiv(m, warps), warps * 32, smem, st>>>(MC_HEAD_ROWS_ARGS);
+#undef MC_HEAD_ROWS_ARGS
     MC_CHECK_LAUNCH();
     h->launches++;
   }

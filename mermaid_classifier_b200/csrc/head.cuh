@@ -47,6 +47,12 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
   }
 }
 
+// FAST (labels / top-k only, calibrated head, no probabilities or loss terms requested): the row normalisation c / sum(c)
+// and the overshoot clip are monotone, so the arg-max runs on the un-normalised c_k and only the k winners are normalised;
+// the softmax division becomes one reciprocal per row and the exponentials use the fast intrinsics.  This path already sits
+// behind the 3xTF32 tensor-core Linear chain (label agreement with the exact chain >= 99.9 % is what the tests hold it to);
+// predict_proba and the evaluation terms keep the exact arithmetic below (the reference's 1e-6 export gate).
+template <bool FAST>
 __global__ void head_rows_kernel(const float* __restrict__ logits, int ld, int K,
                                  const float* __restrict__ pa, const float* __restrict__ pb,
                                  double* __restrict__ proba, int32_t* __restrict__ labels, int topk,
@@ -69,13 +75,23 @@ __global__ void head_rows_kernel(const float* __restrict__ logits, int ld, int K
   mx = warp_max(mx);
   float sum = 0.f;
   for (int k = lane; k < K; k += 32) {
-    const float e = expf(s[k] - mx);
+    const float e = FAST ? __expf(s[k] - mx) : expf(s[k] - mx);
     s[k] = e;
     sum += e;
   }
   sum = warp_sum(sum);
 
-  if (pa != nullptr) {
+  float fast_csum = 1.f;
+  if constexpr (FAST) {
+    const float inv = 1.f / sum;
+    float csum = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float c = __fdividef(1.f, 1.f + __expf(fmaf(pa[k], s[k] * inv, pb[k])));
+      s[k] = c;
+      csum += c;
+    }
+    fast_csum = warp_sum(csum);
+  } else if (pa != nullptr) {
     // calibrated: c_k = sigmoid(-(a_k p_k + b_k)); proba = c / sum(c)  (uniform when sum == 0)
     float csum = 0.f;
     for (int k = lane; k < K; k += 32) {
@@ -133,7 +149,14 @@ __global__ void head_rows_kernel(const float* __restrict__ logits, int ld, int K
       if (r == 0 && labels) labels[row] = bi;
       if (topk > 0) {
         topk_idx[row * topk + r] = bi;
-        if (topk_val) topk_val[row * topk + r] = bv;
+        if (topk_val) {
+          float pv = bv;
+          if constexpr (FAST) {   // normalise the winner only (uniform 1/K when every c_k underflowed)
+            pv = fast_csum != 0.f ? bv / fast_csum : 1.f / (float)K;
+            if (pv > 1.f && pv <= 1.f + 1e-5f) pv = 1.f;
+          }
+          topk_val[row * topk + r] = pv;
+        }
       }
       if (bi < K) s[bi] = -INFINITY;
     }
