@@ -31,11 +31,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-  return v;
-}
 }  // namespace ptx
 
 constexpr int DW_MAX_STAGES = 8;
@@ -76,7 +71,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
   constexpr int NCOL = (TW - 1) * S + K;  // input columns per strip
   constexpr int ES = (int)sizeof(T);
   extern __shared__ uint8_t dw_smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)dw_smem_raw + 127) & ~(uintptr_t)127);
+  uint8_t* smem = dw_smem_raw + ((128u - (ptx::smem_u32(dw_smem_raw) & 127u)) & 127u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   const int CGT = a.cgt, PT = a.pt, CB = CGT * 4;
   const int n_cons = CGT * PT;
   uint8_t* ring = smem;                                            // [stages][row_bytes]
@@ -358,7 +353,7 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
   constexpr int NCOL = (TW - 1) * S + K;
   constexpr int ES = (int)sizeof(T);
   extern __shared__ uint8_t dw_smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)dw_smem_raw + 127) & ~(uintptr_t)127);
+  uint8_t* smem = dw_smem_raw + ((128u - (ptx::smem_u32(dw_smem_raw) & 127u)) & 127u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   constexpr int CGT = SH.cgt, PTC = SH.ptc, CB = SH.cb, NXC = SH.nxc, C = SH.C, HIN = SH.Hin, HOUT = SH.Hout, PAD = SH.pad;
   constexpr int RPB = SH.rows_per_band, STAGES = SH.stages, ROW_BYTES = SH.row_bytes, BOX_BYTES = SH.box_bytes;
   constexpr int n_cons = CGT * PTC;

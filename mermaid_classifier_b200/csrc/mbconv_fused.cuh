@@ -113,7 +113,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   static_assert(CB == 32 || CB == 48, "epilogue column passes");
 
   extern __shared__ uint8_t fused_smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)fused_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = fused_smem_raw + ((1024u - (ptx::smem_u32(fused_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* w_s = smem;                                   // [kchunk][hi, lo] W slice tiles
   uint8_t* a_s = w_s + SH.w_bytes;                       // [NH stages][kchunk] x tiles (TMA)
   uint8_t* lo_s = a_s + NH * A_STAGE;                    // [2 stages][kchunk] TF32 lo operand (fp32 mode)

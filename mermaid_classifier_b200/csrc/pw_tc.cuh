@@ -132,6 +132,25 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
         : "memory");
   }
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (128 rows = lanes, K 32-bit columns) is read from tensor memory, so an
+// MMA pulls only its B tile through the shared-memory pipe
+__device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: thread t of the warp writes lane (base + t), 16 consecutive 32-bit columns.  No wait inside.
+__device__ __forceinline__ void tmem_st32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Convergent-warp forms: the WHOLE warp executes these and one elected lane issues.  Under a divergent
 // `if (lane == 0)` ptxas cannot prove the uniform-register operands warp-uniform and wraps every tcgen05 instruction in an
 // elect / broadcast / branch waterfall (6 extra instructions each, all on the slow uniform datapath): measured ~150
@@ -219,6 +238,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -286,6 +310,8 @@ struct PwTcArgs {
   long long* dbg;     // MC_TC_DBG: per-role wait/total cycle counters of CTA 0 (null = off)
   int exp_flags;      // MC_TC_EXP timing experiments: 1 no activation, 2 no global stores, 4 no operand transform, 16 no MMA, 32 no tcgen05.ld
   int w_res;          // 1: the layer's whole weight (all n-blocks x k-chunks, hi+lo) stays resident in smem
+                      // 2: ONE n-block's weight (all k-chunks) stays resident: the grid is a multiple of n_blocks, so CTA c only
+                      //    ever sees n-block c % n_blocks (item it = c + j * grid -> n-block it % n_blocks)
   int a_row_off;      // first row of this launch inside the activation tensor map (chunked execution)
   int64_t m_tiles;
   int pool_nb;        // POOL instantiation: patches in this launch (a work item's 128-row tile = two 49-row patches)
@@ -340,8 +366,8 @@ constexpr int tc_stage_bytes(int BN) {
   return TcCfg<T>::A_BYTES + TcCfg<T>::NW * ((BN * 128 + 1023) / 1024 * 1024);
 }
 template <typename T>
-inline int tc_num_stages(int BN, int extra_fixed = 0) {
-  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES - extra_fixed - tc_lo_ring_bytes<T>()) / tc_stage_bytes<T>(BN);
+inline int tc_num_stages(int BN, int extra_fixed = 0, bool no_lo_ring = false) {
+  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES - extra_fixed - (no_lo_ring ? 0 : tc_lo_ring_bytes<T>())) / tc_stage_bytes<T>(BN);
   return s > TC_MAX_STAGES ? TC_MAX_STAGES : s;
 }
 // resident-weight layout: W region of n_blocks * k_chunks * NW tiles, stages carry the A operands only
@@ -351,8 +377,8 @@ inline int tc_w_res_bytes(int BN, int n_blocks, int k_chunks) {
   return n_blocks * k_chunks * TcCfg<T>::NW * ((BN * 128 + 1023) / 1024 * 1024);
 }
 template <typename T>
-inline int tc_num_stages_res(int w_bytes) {
-  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES - w_bytes - tc_lo_ring_bytes<T>()) / TcCfg<T>::A_BYTES;
+inline int tc_num_stages_res(int w_bytes, bool no_lo_ring = false) {
+  int s = (TC_SMEM_BUDGET - TC_FIXED_BYTES - w_bytes - (no_lo_ring ? 0 : tc_lo_ring_bytes<T>())) / TcCfg<T>::A_BYTES;
   return s > TC_MAX_STAGES ? TC_MAX_STAGES : s;
 }
 
@@ -364,7 +390,15 @@ inline int tc_num_stages_res(int w_bytes) {
 // boundary of the epilogue, the other rows of the tile are never read back).  The epilogue applies BN + swish, sums each
 // column over the patch's 49 rows in a fixed order (in-thread, lane shuffles, then the two warps of the patch through
 // shared memory) and writes mean features [patch][N] in fp32: the 49 x 1280 map per patch never exists in global memory.
-template <typename T, bool GATED, bool RELU = false, bool POOL = false>
+// TS (gated fp32 layers): the transform warps write the gated TF32 hi / lo operands of A into TENSOR MEMORY (tcgen05.st, a
+// thread = a tile row = a TMEM lane) instead of back into shared memory, and the MMAs take A from there.  With both
+// operands in shared memory the K >= 480 project layers were bound by the shared-memory pipe (128 B/clk per SM), not by the
+// tensor cores: per 128 x 96 x 8 MMA 4 KB of A + 3 KB of W operand reads, three MMAs per k-step, plus the TMA fills (40 KB
+// per k-chunk) and the transform's 16 KB of loads and 32 KB of stores -- ~115 smem-cycles per MMA against 49 tensor-cycles
+// (ncu: tensor pipe 41 % on b15.project; role timers: the issuer busy 75 %, no barrier waits).  A from TMEM removes the A
+// operand reads and the transform's stores: ~60 smem-cycles per MMA.  TMEM: accumulators in columns [0, 256) (two stages of
+// 128, or four of 64 when BN <= 64), A ring of four slots x (32 hi + 32 lo columns) in [256, 512).
+template <typename T, bool GATED, bool RELU = false, bool POOL = false, bool TS = false>
 __global__ void __launch_bounds__(tc_threads<GATED>(), 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmG, const PwTcArgs p) {
@@ -374,12 +408,18 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // Weight residency: when the whole layer weight fits, it is loaded ONCE per CTA and the ring carries activations only.
   // Re-fetching the same W tile for every work item made 148 CTAs hammer a handful of L2 lines: throughput of the
   // front layers then depended on which L2 slices the weight allocation happened to hash to (4.8 vs 3.2 TB/s on b1.expand).
+  // Past the front layers the whole weight no longer fits, and streaming W hi + lo tiles with every A tile made the expand
+  // layers L2 -> shared-memory fill-bound (b9.expand: 160 KB of fills per 128 x 96 output tile, 60 % of it weights; the chip's
+  // L2 delivers ~6300 B/clk in total).  Mode 2 pins each CTA to one n-block and keeps that block's weight resident.
   const bool w_res = p.w_res != 0;
-  const int W_RES_BYTES = w_res ? p.n_blocks * p.k_chunks * Cfg::NW * W_BYTES : 0;
+  const bool w_res_nb = p.w_res == 2;
+  const int W_RES_BYTES = w_res ? (w_res_nb ? 1 : p.n_blocks) * p.k_chunks * Cfg::NW * W_BYTES : 0;
   const int STAGE_BYTES = Cfg::A_BYTES + (w_res ? 0 : Cfg::NW * W_BYTES);   // A (hi) tile [+ W hi, W lo tiles]
-  constexpr int LO_SLOTS = Cfg::TF32 ? 2 : 0;                                // ring of the TF32 lo operand of A
+  static_assert(!TS || (GATED && Cfg::TF32), "TS is the gated fp32 form");
+  constexpr int LO_SLOTS = (Cfg::TF32 && !TS) ? 2 : 0;                       // ring of the TF32 lo operand of A (shared memory)
+  constexpr uint32_t TS_A_COL0 = 256, TS_SLOTS = 4, TS_SLOT_COLS = 64;       // TS: ring of the A operands in tensor memory
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* w_base = smem;                                      // resident weights (1024-aligned tiles), may be empty
   uint8_t* stage_base = smem + W_RES_BYTES;
   uint8_t* lo_base = stage_base + (size_t)S * STAGE_BYTES;
@@ -395,8 +435,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = bars + 3 * TC_MAX_STAGES;     // [4]   accumulator complete
   uint64_t* tempty = tfull + 4;                   // [4]   accumulator drained
   uint64_t* wbar = tempty + 4;                    // resident weights landed
-  uint64_t* lo_empty = wbar + 1;                  // [2]   MMAs reading the lo slot retired
-  uint32_t* tmem_slot = (uint32_t*)(lo_empty + 2);
+  uint64_t* lo_empty = wbar + 1;                  // [2]   MMAs reading the lo slot retired ([4] TS: the TMEM A slot)
+  uint32_t* tmem_slot = (uint32_t*)(lo_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // accumulator stages in TMEM: 4 x 128 columns when the block fits, else 2 x 256
@@ -414,8 +454,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // -> stage group + n_groups * (j % ACC_DEPTH), use j / ACC_DEPTH.  A stage is only ever waited on by its own group, which
   // sees every one of its phases (a parity wait is only meaningful for the current or the immediately preceding phase).
   constexpr int NAS = 4;
-  constexpr int ACC_DEPTH = NAS / n_groups;
-  constexpr int acc_cols = 128;
+  const int ACC_DEPTH = TS ? (p.BN <= 64 ? 2 : 1) : NAS / n_groups;
+  const int acc_cols = (TS && p.BN <= 64) ? 64 : 128;
   constexpr bool transform = Cfg::TF32 || GATED;
   // 32-bit work-item arithmetic throughout: a 64-bit divide by a run-time value is a ~100-instruction
   // subroutine, and every role used to pay several of them per item.
@@ -435,8 +475,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::mbar_init(&empty[s], 1);
     }
     ptx::mbar_init(wbar, 1);
-    ptx::mbar_init(&lo_empty[0], 1);
-    ptx::mbar_init(&lo_empty[1], 1);
+    for (int s = 0; s < 4; ++s) ptx::mbar_init(&lo_empty[s], 1);
     for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&tfull[s], 1);
       ptx::mbar_init(&tempty[s], 128);
@@ -461,10 +500,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool skip_wlo = (p.exp_flags & 64) != 0;   // timing experiment: do not fetch the W lo tile (results wrong by design)
       const uint32_t tx = Cfg::A_BYTES + (w_res ? 0u : w_tile_tx * ((Cfg::TF32 && !skip_wlo) ? 2u : 1u));
       if (w_res) {
-        ptx::mbar_expect_tx(wbar, w_tile_tx * (uint32_t)(p.n_blocks * p.k_chunks * Cfg::NW));
-        for (int nb_ = 0; nb_ < p.n_blocks; ++nb_)
+        const int nb_lo = w_res_nb ? (int)(blockIdx.x % nblk) : 0, nb_hi = w_res_nb ? nb_lo + 1 : p.n_blocks;
+        ptx::mbar_expect_tx(wbar, w_tile_tx * (uint32_t)((nb_hi - nb_lo) * p.k_chunks * Cfg::NW));
+        for (int nb_ = nb_lo; nb_ < nb_hi; ++nb_)
           for (int kc = 0; kc < p.k_chunks; ++kc) {
-            uint8_t* wt = w_base + (size_t)((nb_ * p.k_chunks + kc) * Cfg::NW) * W_BYTES;
+            uint8_t* wt = w_base + (size_t)(((nb_ - nb_lo) * p.k_chunks + kc) * Cfg::NW) * W_BYTES;
             ptx::tma_load_2d(wt, &tmW, wbar, kc * Cfg::KC, nb_ * p.BN);
             if (Cfg::TF32) ptx::tma_load_2d(wt + W_BYTES, &tmWlo, wbar, kc * Cfg::KC, nb_ * p.BN);
           }
@@ -535,7 +575,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int gj = li / n_groups;
         const int as = li % n_groups + n_groups * (gj % ACC_DEPTH);
         const uint32_t use = (uint32_t)(gj / ACC_DEPTH);
-        const int nb_i = (int)((uint32_t)it - ((uint32_t)it / nblk) * nblk);
+        const int nb_i = w_res_nb ? 0 : (int)((uint32_t)it - ((uint32_t)it / nblk) * nblk);   // index into the resident weights
         w_tempty += ptx::mbar_wait_timed(&tempty[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_cols);
@@ -554,7 +594,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (ks < ksteps) {
               const uint32_t acc = (kc | ks) != 0;
               const uint32_t ko = (uint32_t)ks * 2u;   // UK elements = 32 bytes = 2 descriptor units
-              if (Cfg::TF32) {
+              if constexpr (TS) {
+                const uint32_t a_tm = tmem_base + TS_A_COL0 + (cc & (TS_SLOTS - 1u)) * TS_SLOT_COLS + (uint32_t)ks * 8u;   // hi; lo 32 columns on
+                const uint64_t whi = DESC_HI64 | (w_lo + ko), wlo = DESC_HI64 | (w_lo + w_step + ko);
+                ptx::mma_ts_tf32(d_tmem, a_tm + 32u, whi, idesc, acc);
+                ptx::mma_ts_tf32(d_tmem, a_tm, wlo, idesc, 1u);
+                ptx::mma_ts_tf32(d_tmem, a_tm, whi, idesc, 1u);
+              } else if (Cfg::TF32) {
                 const uint64_t ahi = DESC_HI64 | (a_lo + ko), alo = DESC_HI64 | (l_lo + ko);
                 const uint64_t whi = DESC_HI64 | (w_lo + ko), wlo = DESC_HI64 | (w_lo + w_step + ko);
                 ptx::mma_ss<true>(d_tmem, alo, whi, idesc, acc);
@@ -566,7 +612,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           ptx::mma_commit(&empty[s]);
-          if (Cfg::TF32) ptx::mma_commit(&lo_empty[cc & 1u]);
+          if (TS) ptx::mma_commit(&lo_empty[cc & (TS_SLOTS - 1u)]);
+          else if (Cfg::TF32) ptx::mma_commit(&lo_empty[cc & 1u]);
           if (++s == S) {
             s = 0;
             ph ^= 1;
@@ -609,11 +656,46 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int k0 = kc * Cfg::KC;
           const int nch = min(8, (p.K - k0) / EPCH);  // chunks that hold real data (the rest is TMA zero fill)
           ptx::mbar_wait(&full[s], ph);
-          if (Cfg::TF32) ptx::mbar_wait(&lo_empty[cc & 1u], ((cc >> 1) & 1u) ^ 1u);   // the MMAs of two chunks ago are done with the slot
+          if (TS) ptx::mbar_wait(&lo_empty[cc & (TS_SLOTS - 1u)], ((cc >> 2) & 1u) ^ 1u);   // the MMAs of four chunks ago are done with the TMEM slot
+          else if (Cfg::TF32) ptx::mbar_wait(&lo_empty[cc & 1u], ((cc >> 1) & 1u) ^ 1u);   // the MMAs of two chunks ago are done with the slot
           const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
           [[maybe_unused]] const uint32_t a_lo_slot = ptx::smem_u32(lo_base + (cc & 1u) * Cfg::A_BYTES) + row_off;
           const uint32_t g_u32 = ptx::smem_u32(gate_s + s * (TC_GATE_ROWS * 128)) + prow * 128u + (uint32_t)j0 * 16u;
           uint4 raw[4], gq[4];
+          if constexpr (TS) {
+            // row r = TMEM lane r (warp w reaches lanes 32 (w % 4) ..): this thread's 16 gated values as TF32 hi and lo into
+            // columns 4 j0 .. 4 j0 + 15 of the slot's hi / lo blocks.  K tail: the TMA zero fill makes both zero.
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              raw[jj] = ptx::lds128(a_hi + (((uint32_t)(j0 + jj) ^ xr) << 4));
+              gq[jj] = ptx::lds128(g_u32 + (uint32_t)jj * 16u);
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint32_t* rp = &raw[jj].x;
+              const uint32_t* gp = &gq[jj].x;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t vb = __float_as_uint(__uint_as_float(rp[e]) * __uint_as_float(gp[e]));
+                hi[4 * jj + e] = vb & 0xFFFFE000u;
+                lo[4 * jj + e] = tf32_lo_bits(vb);
+              }
+            }
+            const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TS_A_COL0 + (cc & (TS_SLOTS - 1u)) * TS_SLOT_COLS +
+                                   (uint32_t)j0 * 4u;
+            ptx::tc_fence_after();
+            ptx::tmem_st32x32b_x16(t_row, hi);
+            ptx::tmem_st32x32b_x16(t_row + 32u, lo);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&ready[s]);
+            if (++s == S) {
+              s = 0;
+              ph ^= 1;
+            }
+            continue;
+          }
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             raw[jj] = make_uint4(0u, 0u, 0u, 0u);
@@ -813,6 +895,127 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         t_work += ptx::tc_clock() - t_item;
         continue;
       }
+      if constexpr (Cfg::TF32) {
+        // fp32: stores straight from the fragment layout.  A thread holds column PAIRS (8 bytes), a quad writes the 32 contiguous
+        // bytes of one sector of a row, eight rows per instruction -- the same sectors per instruction as the 16-byte form below,
+        // without its lane exchange (16 SHFL + 32 SEL per 32-column group).  N is a multiple of 4 (rows stay 8-byte aligned).  The body is branch-free apart from warp-uniform
+        // tests: with a (divergent-looking) bounds branch around each 4-element block ptxas fenced every block with BSSY / BSYNC
+        // and the EX2 -> ADD -> RCP -> MUL chains of the eight blocks ran one after the other (23 instructions per element,
+        // ncu: issue 63 %, the epilogue warps busy 80 % of the time on the front expand layers).
+        const bool do_act = p.act == 1 && !(p.exp_flags & 1);
+        const uint32_t sc_u32 = ptx::smem_u32(sc_s + n0 + 2 * q), bi_u32 = ptx::smem_u32(bi_s + n0 + 2 * q);
+        const int rowN = lr * p.N + 2 * q, rs8 = 8 * p.N;
+        float* __restrict__ orow = (float*)out_t + rowN;                       // + (16 h2 + 8 rh) * N + c0 + 8 i
+        const float* __restrict__ rrow = res_t != nullptr ? (const float*)res_t + rowN : nullptr;
+        bool rok[2][2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) rok[h2][rh] = 16 * h2 + 8 * rh + lr < rows_valid;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          // valid columns of this group: the conv widths are multiples of 8, the MLP head's of 4 -- a thread's column pair
+          // never straddles the end
+          bool cok[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cok[i] = c0 + 8 * i + 2 * q < ncols;
+          [[maybe_unused]] float2 rpre[2][2][4];
+          if constexpr (GATED) {
+            if (rrow != nullptr) {
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    rpre[h2][rh][i] = make_float2(0.f, 0.f);
+                    if (rok[h2][rh] && cok[i]) rpre[h2][rh][i] = *reinterpret_cast<const float2*>(rrow + (2 * h2 + rh) * rs8 + c0 + 8 * i);
+                  }
+            }
+          }
+          uint32_t v[2][16];
+          if (!(p.exp_flags & 32)) {
+            ptx::tmem_ld16x256b_x4(taddr + (uint32_t)c0, v[0]);
+            ptx::tmem_ld16x256b_x4(taddr + (16u << 16) + (uint32_t)c0, v[1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[0][e] = v[1][e] = 0u;
+          }
+          uint2 sc2[4], bi2[4];   // columns c0 + 8 i + 2 q + {0, 1} (entries past N are never stored)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            sc2[i] = ptx::lds64(sc_u32 + (uint32_t)(c0 + 8 * i) * 4u);
+            bi2[i] = ptx::lds64(bi_u32 + (uint32_t)(c0 + 8 * i) * 4u);
+          }
+          if (!(p.exp_flags & 32)) ptx::tmem_ld_wait();
+          float y[2][2][4][2];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                y[h2][rh][i][0] = fmaf(__uint_as_float(v[h2][4 * i + 2 * rh]), __uint_as_float(sc2[i].x), __uint_as_float(bi2[i].x));
+                y[h2][rh][i][1] = fmaf(__uint_as_float(v[h2][4 * i + 2 * rh + 1]), __uint_as_float(sc2[i].y), __uint_as_float(bi2[i].y));
+              }
+          if (do_act) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+              for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) y[h2][rh][i][e] = __fdividef(y[h2][rh][i][e], 1.f + __expf(-y[h2][rh][i][e]));
+          }
+          if (RELU) {
+            if (p.act == 2) {
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) y[h2][rh][i][e] = fmaxf(y[h2][rh][i][e], 0.f);
+            }
+          }
+          if constexpr (GATED) {
+            if (rrow != nullptr) {
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    y[h2][rh][i][0] += rpre[h2][rh][i].x;
+                    y[h2][rh][i][1] += rpre[h2][rh][i].y;
+                  }
+            }
+          } else if (rrow != nullptr) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+              for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (rok[h2][rh] && cok[i]) {
+                    const float2 r2 = *reinterpret_cast<const float2*>(rrow + (2 * h2 + rh) * rs8 + c0 + 8 * i);
+                    y[h2][rh][i][0] += r2.x;
+                    y[h2][rh][i][1] += r2.y;
+                  }
+          }
+          if (!(p.exp_flags & 2)) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+              for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (rok[h2][rh] && cok[i])
+                    *reinterpret_cast<float2*>(orow + (2 * h2 + rh) * rs8 + c0 + 8 * i) = make_float2(y[h2][rh][i][0], y[h2][rh][i][1]);
+          }
+        }
+      } else
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         // residual (skip connection) values of this column group: all eight loads in flight BEFORE the accumulator is
         // read.  Issued where they are consumed they sit between the lane exchanges and serialise -- eight exposed L2 / HBM
@@ -970,6 +1173,8 @@ inline int make_gate_map(CUtensorMap* map, bool f32, const void* base, int64_t r
 struct PwTcLayer {
   bool present = false;
   int N = 0, K = 0, BN = 0, n_blocks = 0, k_chunks = 0, act = 0;
+  int w_mode = 0;         // PwTcArgs::w_res: 0 streamed, 1 whole weight resident, 2 one n-block resident per CTA
+  bool ts = false;        // gated fp32: A operands through tensor memory (pw_tc_kernel TS instantiation)
   bool gated = false;
   void* d_w = nullptr;    // bf16 weights, or fp32 hi part
   void* d_wlo = nullptr;  // fp32 lo part
@@ -1036,6 +1241,45 @@ inline int pw_tc_add(PwTcPlan* plan, int id, const float* w_host, const float* d
   if (f32 && tc_w_res_bytes<float>(l.BN, l.n_blocks, l.k_chunks) > TC_W_RES_MAX && (gated || N % 96 == 0)) {
     l.BN = pick_bn(N, gated ? 112 : 96);
     l.n_blocks = (N + l.BN - 1) / l.BN;
+  }
+  // Weight residency.  Whole layer when it fits; else (expand-shaped layers: K small, N large) one n-block per CTA, with the
+  // widest block that still leaves FOUR activation stages (MC_TC_BN="<id>:<bn>,..." overrides the width, MC_TC_NO_WRES_NB
+  // disables the mode).
+  {
+    auto wbytes = [&](int bn, int nblocks) { return f32 ? tc_w_res_bytes<float>(bn, nblocks, l.k_chunks) : tc_w_res_bytes<__nv_bfloat16>(bn, nblocks, l.k_chunks); };
+    auto stages_res = [&](int wb) { return f32 ? tc_num_stages_res<float>(wb) : tc_num_stages_res<__nv_bfloat16>(wb); };
+    static const bool no_w_res = getenv("MC_TC_NO_WRES") != nullptr, no_nb = getenv("MC_TC_NO_WRES_NB") != nullptr;
+    l.w_mode = 0;
+    if (!no_w_res && wbytes(l.BN, l.n_blocks) <= TC_W_RES_MAX) {
+      l.w_mode = 1;
+    } else if (!no_w_res && !no_nb && !gated) {
+      int bn_forced = 0;
+      if (const char* e = getenv("MC_TC_BN")) {
+        for (const char* q = e; q && *q;) {
+          int lid = -1, bn = 0;
+          if (sscanf(q, "%d:%d", &lid, &bn) == 2 && lid == id) bn_forced = bn;
+          q = strchr(q, ',');
+          if (q) ++q;
+        }
+      }
+      const int bn_max = f32 ? TcCfg<float>::BN_MAX : TcCfg<__nv_bfloat16>::BN_MAX;
+      for (int cap = bn_forced ? bn_forced : bn_max; cap >= 64; cap -= 16) {
+        const int bn = pick_bn(N, cap), nblocks = (N + bn - 1) / bn;
+        if (nblocks > plan->num_sms) break;
+        if (stages_res(wbytes(bn, 1)) >= (bn_forced ? 2 : 4)) {
+          l.BN = bn;
+          l.n_blocks = nblocks;
+          l.w_mode = 2;
+          break;
+        }
+        if (bn_forced) break;
+      }
+    }
+  }
+  {
+    // MC_TC_TS_MASK=<hex>: gated fp32 layers (bit = plan layer id) that take A through tensor memory; default all of them
+    static const unsigned long long ts_mask = getenv("MC_TC_TS_MASK") ? strtoull(getenv("MC_TC_TS_MASK"), nullptr, 16) : ~0ull;
+    l.ts = f32 && gated && id < 64 && ((ts_mask >> id) & 1ull) != 0;
   }
   const size_t n = (size_t)N * K;
   int rc;
@@ -1155,21 +1399,25 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   a.n_blocks = l.n_blocks;
   a.k_chunks = l.k_chunks;
   a.act = l.act;
-  const int w_bytes = f32 ? tc_w_res_bytes<float>(l.BN, l.n_blocks, l.k_chunks) : tc_w_res_bytes<__nv_bfloat16>(l.BN, l.n_blocks, l.k_chunks);
-  static const bool no_w_res = getenv("MC_TC_NO_WRES") != nullptr;   // experiment switch
-  a.w_res = (!no_w_res && w_bytes <= TC_W_RES_MAX) ? 1 : 0;
-  size_t smem;
-  const size_t lo_ring = f32 ? tc_lo_ring_bytes<float>() : 0;
-  if (a.w_res) {
-    a.stages = f32 ? tc_num_stages_res<float>(w_bytes) : tc_num_stages_res<__nv_bfloat16>(w_bytes);
-    smem = TC_FIXED_BYTES + (size_t)w_bytes + lo_ring + (size_t)a.stages * TC_BM * 128;
-  } else {
-    a.stages = f32 ? tc_num_stages<float>(l.BN) : tc_num_stages<__nv_bfloat16>(l.BN);
-    smem = TC_FIXED_BYTES + lo_ring + (size_t)a.stages * (f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN));
-  }
   a.m_tiles = (M + TC_BM - 1) / TC_BM;
   const int64_t items = a.m_tiles * a.n_blocks;
-  const int grid = (int)std::min<int64_t>(items, plan->num_sms);
+  // mode 2 needs a grid that is a multiple of n_blocks (CTA c <-> n-block c % n_blocks); tiny launches stream instead
+  const int grid_nb = plan->num_sms / l.n_blocks * l.n_blocks;
+  a.w_res = l.w_mode;
+  if (a.w_res == 2 && items < grid_nb) a.w_res = 0;
+  const int w_bytes = f32 ? tc_w_res_bytes<float>(l.BN, a.w_res == 2 ? 1 : l.n_blocks, l.k_chunks)
+                          : tc_w_res_bytes<__nv_bfloat16>(l.BN, a.w_res == 2 ? 1 : l.n_blocks, l.k_chunks);
+  size_t smem;
+  const bool ts = l.ts && a.gate != nullptr && !plan->relu_variant;
+  const size_t lo_ring = (f32 && !ts) ? tc_lo_ring_bytes<float>() : 0;
+  if (a.w_res) {
+    a.stages = f32 ? tc_num_stages_res<float>(w_bytes, ts) : tc_num_stages_res<__nv_bfloat16>(w_bytes);
+    smem = TC_FIXED_BYTES + (size_t)w_bytes + lo_ring + (size_t)a.stages * TC_BM * 128;
+  } else {
+    a.stages = f32 ? tc_num_stages<float>(l.BN, 0, ts) : tc_num_stages<__nv_bfloat16>(l.BN);
+    smem = TC_FIXED_BYTES + lo_ring + (size_t)a.stages * (f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN));
+  }
+  const int grid = a.w_res == 2 ? grid_nb : (int)std::min<int64_t>(items, plan->num_sms);
   const bool gated = a.gate != nullptr;
   if (gated && l.g_ptr != a.gate) {
     int rc = make_gate_map(&l.tmG, f32, a.gate, plan->max_batch, l.K);
@@ -1182,6 +1430,11 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
     pw_tc_kernel<float, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+  } else if (f32 && gated && ts) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    if (first_use_on_device(attr_mask))
+      MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    pw_tc_kernel<float, true, false, false, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   } else if (f32 && gated)
     pw_tc_kernel<float, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   else if (f32)

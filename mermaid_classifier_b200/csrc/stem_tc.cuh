@@ -48,7 +48,7 @@ template <typename T>
 __global__ void __launch_bounds__(STEM_TC_THREADS, 1)
 stem_tc_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__ points, const StemTcArgs a) {
   extern __shared__ uint8_t stem_smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)stem_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = stem_smem_raw + ((1024u - (ptx::smem_u32(stem_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* w_s = smem;                                             // 3 parts x [32 rows x 128 B] (first 64 B of a row used)
   uint8_t* a_s = w_s + 3 * 4096;                                   // [4 stages][128 rows x 128 B] (first 64 B of a row used)
   uint8_t* rows_s = a_s + STEM_A_STAGES * TC_BM * 128;             // [2][33][720] staged source bytes

@@ -11,8 +11,9 @@
                                       capture, counters; images are sharded round-robin over ranks
 * :func:`stack_feature_files`      -- ``scripts/extract_reference_features.py:40-61`` (``(N, 1280) float32 .npy``)
 
-Storage is the filesystem / in-memory ``DataLocation`` of :mod:`spacer_compat` (S3 needs pyspacer + network and
-is out of scope); everything numerical runs in libmermaid_b200.
+Storage goes through the ``DataLocation`` / ``storage_factory`` seam of :mod:`spacer_compat`: a root is a directory, an
+``s3://bucket/prefix`` URI (boto3, as the reference's buckets) or ``memory://prefix``; everything numerical runs in
+libmermaid_b200.
 """
 
 from __future__ import annotations
@@ -38,6 +39,36 @@ from .spacer_compat import (
     load_image,
     storage_factory,
 )
+
+
+class StorageRoot:
+    """A bucket / directory root: ``loc(key)`` is the ``DataLocation`` of ``key`` under it.
+
+    ``/some/dir`` -> filesystem, ``s3://bucket/prefix`` -> S3 (the reference's layout, ``build_feature_bucket.py:530-544``),
+    ``memory://prefix`` -> the in-process store (tests)."""
+
+    def __init__(self, root: "str | Path | StorageRoot"):
+        if isinstance(root, StorageRoot):
+            self.storage_type, self.bucket, self.prefix = root.storage_type, root.bucket, root.prefix
+            return
+        text = str(root)
+        if text.startswith("s3://"):
+            bucket, _, prefix = text[5:].partition("/")
+            if not bucket:
+                raise ValueError(f"no bucket in {text!r}")
+            self.storage_type, self.bucket, self.prefix = "s3", bucket, prefix
+        elif text.startswith("memory://"):
+            self.storage_type, self.bucket, self.prefix = "memory", None, text[9:]
+        else:
+            self.storage_type, self.bucket, self.prefix = "filesystem", None, text
+        if self.prefix and not self.prefix.endswith("/"):
+            self.prefix += "/"
+
+    def loc(self, key: str) -> DataLocation:
+        return DataLocation(self.storage_type, self.prefix + key, self.bucket)
+
+    def storage(self):
+        return storage_factory(self.storage_type, self.bucket)
 
 
 def prepare_points(rows: Iterable[int], cols: Iterable[int]) -> list[tuple[int, int]]:
@@ -113,8 +144,8 @@ def build_feature_bucket(
     sources: Mapping[str, Mapping[str, Sequence[tuple[int, int]]]],
     extractor: Any,
     *,
-    source_root: str | Path,
-    target_root: str | Path,
+    source_root: "str | Path | StorageRoot",
+    target_root: "str | Path | StorageRoot",
     source_prefix: str = "",
     skip_existing: bool = True,
     dry_run: bool = False,
@@ -147,7 +178,7 @@ def build_feature_bucket(
     (:mod:`mermaid_classifier_b200.decode`, one nvJPEG decoder per pool thread): the decoded image never crosses PCIe and
     ``extractor.extract_device`` reads it where it lands."""
     counters = RunCounters()
-    source_root, target_root = Path(source_root), Path(target_root)
+    source_root, target_root = StorageRoot(source_root), StorageRoot(target_root)
     new_err = error_csv is not None and (not Path(error_csv).exists() or Path(error_csv).stat().st_size == 0)
     err_file = open(error_csv, "a", newline="") if error_csv else None
     err = csv.writer(err_file) if err_file else None
@@ -181,7 +212,7 @@ def build_feature_bucket(
 
     def load_one(item):
         sid, iid, rowcols, floc = item
-        loc = DataLocation("filesystem", str(source_root / image_key(source_prefix, sid, iid)))
+        loc = source_root.loc(image_key(source_prefix, sid, iid))
         img = load_image(loc)
         check_extract_inputs(img, rowcols, loc.key)
         return np.asarray(img)
@@ -189,8 +220,7 @@ def build_feature_bucket(
     def run_batch_device(items):
         """Device decode: file bytes -> nvJPEG -> extract_device -> features back -> threaded stores."""
         def read_bytes(it):
-            loc = DataLocation("filesystem", str(source_root / image_key(source_prefix, it[0], it[1])))
-            return storage_factory("filesystem").load(loc.key).getvalue()
+            return source_root.storage().load(source_root.loc(image_key(source_prefix, it[0], it[1])).key).getvalue()
 
         blobs = list(pool.map(lambda it: _capture(read_bytes, it), items))
         outcome = {id(it): exc for it, (_, exc) in zip(items, blobs) if exc is not None}
@@ -281,12 +311,12 @@ def build_feature_bucket(
             for k in images_for_rank(len(ids), rank, world):
                 iid = ids[k]
                 rowcols = list(grouped[iid])
-                floc = DataLocation("filesystem", str(target_root / feature_key(sid, iid)))
+                floc = target_root.loc(feature_key(sid, iid))
                 if not rowcols:
                     counters.images_skipped += 1
                     progress(sid, iid, "skipped", reason="no_rowcols")
                     continue
-                if skip_existing and storage_factory("filesystem").exists(floc.key):
+                if skip_existing and target_root.storage().exists(floc.key):
                     counters.images_skipped += 1
                     progress(sid, iid, "skipped", reason="exists")
                     continue
@@ -302,7 +332,7 @@ def build_feature_bucket(
                     continue
                 msg = ExtractFeaturesMsg(
                     job_token=f"s{sid}_i{iid}", extractor=extractor, rowcols=rowcols,
-                    image_loc=DataLocation("filesystem", str(source_root / image_key(source_prefix, sid, iid))),
+                    image_loc=source_root.loc(image_key(source_prefix, sid, iid)),
                     feature_loc=floc)
                 try:
                     extract_features(msg)

@@ -85,15 +85,83 @@ if not HAVE_SPACER:
         def delete(self, key: str) -> None:
             del self._blobs[key]
 
+    class _S3Storage:
+        """``DataLocation('s3', key, bucket_name)`` -- the bucket layout of ``scripts/build_feature_bucket.py:530-544`` (images
+        ``s{sid}/images/{iid}.jpg`` in, ``s{sid}/features/i{iid}.featurevector`` out).  boto3 is imported on first use; a
+        client can be injected (``_S3Storage.client_factory``) for tests and for callers that configure their own session."""
+
+        client_factory = None   # callable() -> boto3-style client
+
+        def __init__(self, bucket_name: str | None):
+            if not bucket_name:
+                raise ValueError("s3 storage needs a bucket_name")
+            self.bucket = bucket_name
+            self._client = None
+
+        @property
+        def client(self):
+            if self._client is None:
+                if type(self).client_factory is not None:
+                    self._client = type(self).client_factory()
+                else:
+                    try:
+                        import boto3
+                    except ImportError as e:   # pragma: no cover - boto3 is not in the build image
+                        raise RuntimeError("storage_type 's3' needs boto3 (or an injected _S3Storage.client_factory)") from e
+                    self._client = boto3.client("s3")
+            return self._client
+
+        def load(self, key: str) -> io.BytesIO:
+            return io.BytesIO(self.client.get_object(Bucket=self.bucket, Key=key)["Body"].read())
+
+        def store(self, key: str, stream: io.BytesIO) -> None:
+            self.client.put_object(Bucket=self.bucket, Key=key, Body=stream.getvalue())
+
+        def exists(self, key: str) -> bool:
+            try:
+                self.client.head_object(Bucket=self.bucket, Key=key)
+                return True
+            except Exception as e:   # botocore ClientError 404 / NoSuchKey; anything else is a real failure
+                code = str(getattr(e, "response", {}).get("Error", {}).get("Code", ""))
+                if code in ("404", "NoSuchKey", "NotFound") or isinstance(e, KeyError):
+                    return False
+                raise
+
+        def delete(self, key: str) -> None:
+            self.client.delete_object(Bucket=self.bucket, Key=key)
+
+    class _URLStorage:
+        """Read-only ``DataLocation('url', key)``."""
+
+        def load(self, key: str) -> io.BytesIO:
+            from urllib.request import urlopen
+
+            with urlopen(key) as r:   # noqa: S310 - the caller names the URL
+                return io.BytesIO(r.read())
+
+        def store(self, key: str, stream: io.BytesIO) -> None:
+            raise TypeError("url storage is read-only")
+
+        def exists(self, key: str) -> bool:
+            try:
+                self.load(key)
+                return True
+            except Exception:
+                return False
+
+        def delete(self, key: str) -> None:
+            raise TypeError("url storage is read-only")
+
     def storage_factory(storage_type: str, bucket_name: str | None = None):
         if storage_type == "filesystem":
             return _FileSystemStorage()
         if storage_type == "memory":
             return _MemoryStorage()
-        raise RuntimeError(
-            f"storage_type {storage_type!r} needs pyspacer (boto3 / network); only 'filesystem' and "
-            "'memory' are available in the stand-in"
-        )
+        if storage_type == "s3":
+            return _S3Storage(bucket_name)
+        if storage_type == "url":
+            return _URLStorage()
+        raise ValueError(f"unknown storage_type {storage_type!r}")
 
     def load_image(loc: "DataLocation"):
         from PIL import Image

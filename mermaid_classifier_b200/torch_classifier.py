@@ -52,6 +52,60 @@ class _MLPModule(nn.Module):
             nn.init.zeros_(lin.bias)
 
 
+def pack_reference_state(ws: list[np.ndarray], bs: list[np.ndarray], m_w, m_b, v_w, v_b, t: int, *, lr: float,
+                         betas: tuple[float, float], eps: float) -> tuple[dict[str, torch.Tensor], dict[str, Any]]:
+    """Device parameters and Adam moments -> the two pickle entries of the reference classifier.
+
+    ``_module_state`` is ``_MLPModule.state_dict()`` (keys ``linears.{i}.weight`` / ``.bias``) and
+    ``_optimizer_state`` is ``torch.optim.Adam.state_dict()`` over the parameters in module order
+    (reference ``torch_classifier.py:411-420``), so a pickle written here restores into the reference class
+    and the other way round."""
+    module_state: dict[str, torch.Tensor] = {}
+    params = []
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        module_state[f"linears.{i}.weight"] = torch.from_numpy(np.array(w, dtype=np.float32, copy=True))
+        module_state[f"linears.{i}.bias"] = torch.from_numpy(np.array(b, dtype=np.float32, copy=True))
+        params += [nn.Parameter(torch.empty(w.shape)), nn.Parameter(torch.empty(b.shape))]
+    # param_groups (hyper-parameters and torch-version-specific flags) come from a real Adam over same-shaped parameters
+    opt_state = torch.optim.Adam(params, lr=lr, betas=tuple(betas), eps=eps).state_dict()
+    if t > 0:
+        moments = [x for pair in zip(zip(m_w, v_w), zip(m_b, v_b)) for x in pair]   # (m, v) per parameter, module order
+        opt_state["state"] = {
+            j: {"step": torch.tensor(float(t)),
+                "exp_avg": torch.from_numpy(np.array(m, dtype=np.float32, copy=True)),
+                "exp_avg_sq": torch.from_numpy(np.array(v, dtype=np.float32, copy=True))}
+            for j, (m, v) in enumerate(moments)}
+    return module_state, opt_state
+
+
+def unpack_reference_state(module_state: dict[str, Any], optimizer_state: dict[str, Any] | None):
+    """Inverse of :func:`pack_reference_state`; also accepts the flat layout this class wrote in round 1."""
+    if "weights" in module_state:   # round-1 layout
+        ws, bs = list(module_state["weights"]), list(module_state["biases"])
+        if optimizer_state is None:
+            return ws, bs, None
+        return ws, bs, (optimizer_state["m_w"], optimizer_state["m_b"], optimizer_state["v_w"], optimizer_state["v_b"],
+                        int(optimizer_state["t"]))
+    n = len(module_state) // 2
+    to_np = lambda x: np.ascontiguousarray(x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x, dtype=np.float32)
+    ws = [to_np(module_state[f"linears.{i}.weight"]) for i in range(n)]
+    bs = [to_np(module_state[f"linears.{i}.bias"]) for i in range(n)]
+    if optimizer_state is None:
+        return ws, bs, None
+    st = optimizer_state.get("state", {})
+    if not st:   # optimizer created, no step taken yet
+        zeros = lambda xs: [np.zeros_like(x) for x in xs]
+        return ws, bs, (zeros(ws), zeros(bs), zeros(ws), zeros(bs), 0)
+    order = optimizer_state["param_groups"][0]["params"]
+    ent = [st[j] for j in order]
+    steps = {int(float(e["step"])) for e in ent}
+    if len(steps) != 1:
+        raise ValueError("Adam state with per-parameter step counts cannot be restored into the flat device optimizer")
+    m = [to_np(e["exp_avg"]) for e in ent]
+    v = [to_np(e["exp_avg_sq"]) for e in ent]
+    return ws, bs, (m[0::2], m[1::2], v[0::2], v[1::2], steps.pop())
+
+
 def split_steps(n_samples: int, batch_size: int, rank: int = 0, world: int = 1) -> tuple[np.ndarray, np.ndarray]:
     """Rows of the shuffled order this rank trains on, and the per-step offsets into them.
 
@@ -447,8 +501,9 @@ class TorchMLPClassifier:
             tcount = C.c_int64(0)
             arr = lambda xs: (C.c_void_p * n)(*[x.ctypes.data for x in xs])
             _lib.check(_lib.load().mc_mlp_get_adam(self._h, arr(mw), arr(mb_), arr(vw), arr(vb), C.byref(tcount)))
-            state["_module_state"] = {"weights": ws, "biases": bs}
-            state["_optimizer_state"] = {"m_w": mw, "m_b": mb_, "v_w": vw, "v_b": vb, "t": int(tcount.value)}
+            state["_module_state"], state["_optimizer_state"] = pack_reference_state(
+                ws, bs, mw, mb_, vw, vb, int(tcount.value), lr=self.learning_rate_init,
+                betas=(self.beta_1, self.beta_2), eps=self.epsilon)
         return state
 
     def __setstate__(self, state: dict[str, Any]) -> None:
@@ -457,10 +512,10 @@ class TorchMLPClassifier:
         self.__dict__.update(state)
         self.__dict__.setdefault("class_weight", None)
         if module_state is not None:
-            self._create_handle(module_state["weights"], module_state["biases"])
-            if opt is not None:
-                n = len(module_state["weights"])
-                arr = lambda xs: (C.c_void_p * n)(*[np.ascontiguousarray(x, dtype=np.float32).ctypes.data for x in xs])
-                keep = [[np.ascontiguousarray(x, dtype=np.float32) for x in opt[k]] for k in ("m_w", "m_b", "v_w", "v_b")]
+            ws, bs, adam = unpack_reference_state(module_state, opt)
+            self._create_handle(ws, bs)
+            if adam is not None:
+                n = len(ws)
+                keep = [[np.ascontiguousarray(x, dtype=np.float32) for x in xs] for xs in adam[:4]]
                 ptrs = [(C.c_void_p * n)(*[x.ctypes.data for x in ks]) for ks in keep]
-                _lib.check(_lib.load().mc_mlp_set_adam(self._h, *ptrs, int(opt["t"])))
+                _lib.check(_lib.load().mc_mlp_set_adam(self._h, *ptrs, int(adam[4])))

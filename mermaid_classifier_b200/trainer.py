@@ -167,6 +167,10 @@ class CalibratedClassifier:
     def __init__(self, estimator: TorchMLPClassifier, a: np.ndarray, b: np.ndarray):
         self.estimator = estimator
         self.classes_ = estimator.classes_
+        # K == 2: scikit-learn keeps ONE calibrator, fitted on the positive-class column (reference ``trainer.py:365-374``)
+        self.binary = len(self.classes_) == 2
+        if len(a) != (1 if self.binary else len(self.classes_)) or len(a) != len(b):
+            raise ValueError(f"{len(a)} calibrators for {len(self.classes_)} classes")
         self.calibrated_classifiers_ = [_CalibratedInner(
             estimator, [SigmoidCalibrator(float(x), float(z)) for x, z in zip(a, b)], estimator.classes_)]
         self._head: DeviceHead | None = None
@@ -177,6 +181,8 @@ class CalibratedClassifier:
         return np.asarray([c.a_ for c in cal]), np.asarray([c.b_ for c in cal])
 
     def head(self) -> DeviceHead:
+        if self.binary:   # same refusal as the reference's build_calibrated_head (inference/head.py:110-114)
+            raise ValueError("the calibrated head only supports the multiclass (K > 2) path; got K=2")
         if self._head is None:
             ws, bs = self.estimator._pull_params()
             a, b = self.platt
@@ -190,9 +196,18 @@ class CalibratedClassifier:
         return arr
 
     def predict_proba(self, X: Any) -> np.ndarray:
+        if self.binary:
+            # sklearn _CalibratedClassifier.predict_proba, n_classes == 2: the calibrator maps the positive column, the
+            # negative one is its complement (no renormalisation), then the (1, 1 + 1e-5] clip
+            p1 = self.calibrated_classifiers_[0].calibrators[0].predict(self.estimator.predict_proba(self._check(X))[:, 1])
+            proba = np.stack([1.0 - p1, p1], axis=1)
+            proba[(1.0 < proba) & (proba <= 1.0 + 1e-5)] = 1.0
+            return proba
         return self.head().scores_host(self._check(X), want_proba=True, want_labels=False)[0]
 
     def predict(self, X: Any) -> np.ndarray:
+        if self.binary:
+            return self.classes_[np.argmax(self.predict_proba(X), axis=1)]
         return self.classes_[self.head().scores_host(self._check(X), want_proba=False, want_labels=True)[1]]
 
     def __getstate__(self) -> dict[str, Any]:
@@ -440,8 +455,8 @@ class MermaidTrainer:
 
     def _calibrate_in_batches(self, clf: TorchMLPClassifier, ref_labels: Any) -> CalibratedClassifier:
         k = len(clf.classes_)
-        if k <= 2:
-            raise ValueError(f"device calibration covers the multiclass (K > 2) path the artifact supports; got K={k}")
+        if k < 2:
+            raise ValueError(f"calibration needs at least two classes; got K={k}")
         probs, ys = [], []
         for xd, yd in _chunks(ref_labels, self.batch_size, clf):
             probs.append(clf.predict_proba_device(xd.contiguous()))
@@ -449,6 +464,10 @@ class MermaidTrainer:
         proba = torch.cat(probs) if len(probs) > 1 else probs[0]
         y = (torch.cat(ys) if len(ys) > 1 else ys[0]).contiguous()
         proba, y = self._gather_rows(proba.contiguous()), self._gather_rows(y)
+        if k == 2:
+            # binary: one calibrator on the positive-class column (``preds[:, 1:]``, reference ``trainer.py:371-373``); as a
+            # one-column problem the positive rows are "class 0" and the negatives match no column
+            proba, y = proba[:, 1:].contiguous(), (1 - y).to(torch.int32).contiguous()
         a, b, _, passes = platt_fit_device(proba.contiguous(), y)
         logger.debug(f"Platt calibration: {k} classes, {proba.shape[0]} rows, {passes} matrix passes")
         return CalibratedClassifier(clf, a, b)
@@ -464,7 +483,7 @@ def evaluate_classifier(clf: Any, labels: Any, batch_size: int = 5000) -> tuple[
     ests: list[Any] = []
     scores: list[float] = []
     classes = np.asarray(clf.classes_)
-    if hasattr(labels, "device_batches") and hasattr(clf, "head"):  # labels and top scores picked on the device
+    if hasattr(labels, "device_batches") and hasattr(clf, "head") and not getattr(clf, "binary", False):  # labels and top scores picked on the device
         for xd, _ in labels.device_batches(batch_size, clf.classes_):
             out = clf.head().scores_device(xd.contiguous(), topk=1)
             ests.extend(classes[out["topk_idx"][:, 0].cpu().numpy()].tolist())

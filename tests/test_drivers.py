@@ -146,3 +146,63 @@ def test_bucket_driver_batched_path_matches_per_image_path(tmp_path):
         gx, gy = ImageFeatures.load(DataLocation("filesystem", str(x))), ImageFeatures.load(DataLocation("filesystem", str(y)))
         assert [(p.row, p.col) for p in gx.point_features] == [(p.row, p.col) for p in gy.point_features]
         assert np.array_equal(np.stack([p.data for p in gx.point_features]), np.stack([p.data for p in gy.point_features]))
+
+
+class _FakeS3:
+    """boto3-client-shaped dictionary: get_object / put_object / head_object / delete_object."""
+
+    def __init__(self):
+        self.objects = {}
+
+    def get_object(self, Bucket, Key):
+        import io
+        return {"Body": io.BytesIO(self.objects[(Bucket, Key)])}
+
+    def put_object(self, Bucket, Key, Body):
+        self.objects[(Bucket, Key)] = bytes(Body)
+
+    def head_object(self, Bucket, Key):
+        if (Bucket, Key) not in self.objects:
+            err = Exception("not found")
+            err.response = {"Error": {"Code": "404"}}
+            raise err
+        return {}
+
+    def delete_object(self, Bucket, Key):
+        del self.objects[(Bucket, Key)]
+
+
+def test_bucket_driver_over_s3_locations(monkeypatch):
+    """The reference's deployment reads images from and writes features to S3 buckets
+    (``scripts/build_feature_bucket.py:530-544``): same key layout through ``DataLocation('s3', key, bucket)``,
+    skip-existing by ``head_object``; the per-image and the batched path write identical objects."""
+    import io
+
+    from mermaid_classifier_b200 import spacer_compat
+
+    s3 = _FakeS3()
+    monkeypatch.setattr(spacer_compat._S3Storage, "client_factory", staticmethod(lambda: s3))
+    sources = {"5": {}}
+    for i in range(5):
+        buf = io.BytesIO()
+        Image.fromarray(np.full((40, 50, 3), 20 * i, np.uint8)).save(buf, format="JPEG")
+        s3.put_object("coralnet-src", f"pub/s5/images/{i}.jpg", buf.getvalue())
+        sources["5"][str(i)] = [(1, 2), (3, 4)]
+    c = drivers.build_feature_bucket(sources, FakeExtractor(), source_root="s3://coralnet-src", source_prefix="pub/",
+                                     target_root="s3://mermaid-features/run1")
+    assert c.images_ok == 5 and c.images_failed == 0
+    keys = sorted(k for b, k in s3.objects if b == "mermaid-features")
+    assert keys == [f"run1/s5/features/i{i}.featurevector" for i in range(5)]
+    f = ImageFeatures.load(DataLocation("s3", "run1/s5/features/i3.featurevector", "mermaid-features"))
+    assert [(p.row, p.col) for p in f.point_features] == [(1, 2), (3, 4)]
+    again = drivers.build_feature_bucket(sources, FakeExtractor(), source_root="s3://coralnet-src", source_prefix="pub/",
+                                         target_root="s3://mermaid-features/run1", skip_existing=True)
+    assert again.images_skipped == 5 and again.images_ok == 0
+    many = drivers.build_feature_bucket(sources, FakeBatchExtractor(), source_root="s3://coralnet-src", source_prefix="pub/",
+                                        target_root="s3://mermaid-features/run2", batch_images=3)
+    assert many.images_ok == 5
+    for i in range(5):
+        assert s3.objects[("mermaid-features", f"run2/s5/features/i{i}.featurevector")] == \
+            s3.objects[("mermaid-features", f"run1/s5/features/i{i}.featurevector")]
+    root = drivers.StorageRoot("memory://bucket")
+    assert root.loc("a/b").storage_type == "memory" and root.loc("a/b").key == "bucket/a/b"

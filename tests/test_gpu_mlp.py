@@ -126,6 +126,13 @@ def test_pickle_round_trip_resumes_identically():
     a.partial_fit(X, y, classes=list(range(6)))
     b = pickle.loads(pickle.dumps(a))
     assert b.n_iter_ == 1 and b.loss_curve_ == a.loss_curve_
+    # the pickle entries are the reference's: _MLPModule.state_dict() and torch.optim.Adam.state_dict()
+    state = a.__getstate__()
+    assert list(state["_module_state"]) == ["linears.0.weight", "linears.0.bias", "linears.1.weight", "linears.1.bias"]
+    params = [torch.nn.Parameter(torch.zeros_like(v)) for v in state["_module_state"].values()]
+    opt = torch.optim.Adam(params, lr=a.learning_rate_init)
+    opt.load_state_dict(state["_optimizer_state"])
+    assert int(opt.state[params[0]]["step"]) == a.n_steps_ and opt.state[params[0]]["exp_avg"].shape == (32, 64)
     a.partial_fit(X, y)
     b.partial_fit(X, y)
     assert a.loss_curve_[-1] == b.loss_curve_[-1]  # same kernels, same order: bit-identical

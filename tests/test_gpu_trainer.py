@@ -232,3 +232,38 @@ def test_full_size_evaluation_is_additive():
     hs, ls = head.evaluate_device(X[sub].contiguous(), y[sub].contiguous())
     assert ls == pytest.approx(float(otr.log_loss_terms(ysub, p).sum()), rel=1e-5)
     assert abs(hs - int((p.argmax(1) == ysub).sum())) <= 1
+
+
+def test_binary_calibration_single_calibrator():
+    """K = 2 (reference ``trainer.py:365-374``): one sigmoid calibrator fitted on the positive-class column; calibrated
+    probabilities are ``[1 - p, p]`` as scikit-learn's ``_CalibratedClassifier.predict_proba`` builds them."""
+    from mermaid_classifier_b200.torch_classifier import TorchMLPClassifier
+
+    rng = np.random.default_rng(5)
+    n, d = 3000, 16
+    y = rng.integers(0, 2, n)
+    X = (rng.standard_normal((n, d)) + 1.2 * (2 * y[:, None] - 1) * (np.arange(d) < 4)).astype(np.float32)
+    classes = np.asarray(["neg", "pos"])
+    clf = TorchMLPClassifier(hidden_layer_sizes=(8,), learning_rate_init=1e-2, random_state=0)
+    for _ in range(3):
+        clf.partial_fit(X[:2000], classes[y[:2000]], classes=classes)
+    trainer = MermaidTrainer(batch_size=700)
+    cal = trainer._calibrate_in_batches(clf, DeviceLabels(X[2000:], classes[y[2000:]]))
+    inner = cal.calibrated_classifiers_[0]
+    assert cal.binary and len(inner.calibrators) == 1 and list(cal.classes_) == ["neg", "pos"]
+    p1 = clf.predict_proba(X[2000:])[:, 1]
+    ra, rb = otr.sigmoid_calibration(p1, y[2000:])
+    t = otr.platt_targets(y[2000:])[0]
+    l_ref = otr.platt_objective(ra, rb, p1, t)[0]
+    l_dev, grad = otr.platt_objective(inner.calibrators[0].a_, inner.calibrators[0].b_, p1, t)
+    assert l_dev <= l_ref + 1e-9 * abs(l_ref) and np.abs(grad).max() < 1e-5
+    proba = cal.predict_proba(X[2000:])
+    want1 = 1.0 / (1.0 + np.exp(ra * p1 + rb))
+    assert proba.shape == (1000, 2) and np.abs(proba[:, 1] - want1).max() < 2e-3
+    assert np.abs(proba.sum(1) - 1.0).max() < 1e-12
+    assert (cal.predict(X[2000:]) == classes[np.argmax(proba, 1)]).all()
+    gts, ests, scores = __import__("mermaid_classifier_b200.trainer", fromlist=["evaluate_classifier"]).evaluate_classifier(
+        cal, DeviceLabels(X[2000:], classes[y[2000:]]), batch_size=400)
+    assert len(ests) == 1000 and np.mean(np.asarray(gts) == np.asarray(ests)) > 0.8 and max(scores) <= 1.0
+    with pytest.raises(ValueError):
+        cal.head()

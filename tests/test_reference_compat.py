@@ -74,3 +74,46 @@ def test_reference_head_builder_accepts_the_trainer_output(reference):
         assert torch.equal(ref_head(x), ours(x))
     assert [tuple(l.weight.shape) for l in ref_head.linears] == [tuple(l.weight.shape) for l in ours.linears]
     assert torch.equal(ref_head.a, ours.a) and torch.equal(ref_head.b, ours.b)
+
+
+def test_pickle_state_is_the_reference_layout(reference):
+    """``TorchMLPClassifier.__getstate__`` entries (reference ``torch_classifier.py:411-420``): the state a REFERENCE
+    classifier pickles converts to the flat device buffers and back without loss, and the converted state restores
+    into a fresh reference instance that predicts identically."""
+    sys.path.insert(0, str(REFERENCE))
+    try:
+        from mermaid_classifier.pyspacer.torch_classifier import TorchMLPClassifier as RefClf
+    finally:
+        sys.path.remove(str(REFERENCE))
+    from mermaid_classifier_b200.torch_classifier import pack_reference_state, unpack_reference_state
+
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((300, 20)).astype(np.float32)
+    y = np.asarray([f"c{i % 5}" for i in range(300)])
+    ref = RefClf(hidden_layer_sizes=(12, 8), learning_rate_init=1e-3, random_state=0)
+    ref.partial_fit(X, y, classes=np.unique(y))
+    ref.partial_fit(X, y)
+    state = ref.__getstate__()
+    ws, bs, adam = unpack_reference_state(state["_module_state"], state["_optimizer_state"])
+    assert [w.shape for w in ws] == [(12, 20), (8, 12), (5, 8)] and adam[4] == 4   # 2 x ceil(300 / 200) Adam steps
+    mod2, opt2 = pack_reference_state(ws, bs, *adam, lr=ref.learning_rate_init, betas=(ref.beta_1, ref.beta_2), eps=ref.epsilon)
+    assert list(mod2) == list(state["_module_state"])
+    for k in mod2:
+        assert torch.equal(mod2[k], state["_module_state"][k])
+    ref_opt = state["_optimizer_state"]
+    assert opt2["param_groups"] == ref_opt["param_groups"]
+    assert sorted(opt2["state"]) == sorted(ref_opt["state"])
+    for j in opt2["state"]:
+        for key in ("step", "exp_avg", "exp_avg_sq"):
+            assert torch.equal(torch.as_tensor(opt2["state"][j][key]).float(), torch.as_tensor(ref_opt["state"][j][key]).float())
+    state2 = dict(state, _module_state=mod2, _optimizer_state=opt2)
+    clone = RefClf.__new__(RefClf)
+    clone.__setstate__(state2)
+    assert np.array_equal(clone.predict_proba(X[:50]), ref.predict_proba(X[:50]))
+    clone.partial_fit(X, y)
+    ref.partial_fit(X, y)
+    assert np.array_equal(clone.predict_proba(X[:50]), ref.predict_proba(X[:50]))   # resumed training continues identically
+    # the round-1 flat layout still loads
+    ws1, bs1, adam1 = unpack_reference_state({"weights": ws, "biases": bs},
+                                             {"m_w": adam[0], "m_b": adam[1], "v_w": adam[2], "v_b": adam[3], "t": adam[4]})
+    assert adam1[4] == 4 and np.array_equal(ws1[0], ws[0])
