@@ -770,10 +770,12 @@ int mc_head_create(int32_t n_layers, const int32_t* dims, const float* const* we
     if (e == cudaSuccess) e = cudaMemcpy(h->d_a, pa, K * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_pb, pb, K * sizeof(float), cudaMemcpyHostToDevice);
   }
-  // activation chunk: bound the workspace to ~256 MB
-  int64_t per_row = h->dims_p[0];
+  // activation chunk: bound the workspace to ~1 GB (the caller's rows are read in place unless the width needs padding).
+  // At (200, 100, 500) that is 131 072 rows per chunk: with the 32 k-row chunks of round 1 the four launches of a chunk were
+  // four to five waves of work items each, and launch gaps + tails were most of the 165 us a chunk took.
+  int64_t per_row = h->dims_p[0] != h->dims[0] ? h->dims_p[0] : 0;
   for (int i = 1; i <= n_layers; ++i) per_row += h->dims_p[i];
-  h->chunk = std::max<int64_t>(1024, std::min<int64_t>(1 << 17, (int64_t)(256ll << 20) / (per_row * 4)));
+  h->chunk = std::max<int64_t>(1024, std::min<int64_t>(1 << 17, (int64_t)(1024ll << 20) / (per_row * 4)));
   for (int i = 1; i <= n_layers && e == cudaSuccess; ++i) {
     float* p = nullptr;
     e = cudaMalloc((void**)&p, h->chunk * h->dims_p[i] * sizeof(float));

@@ -450,16 +450,17 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
           }
           const int iy = iy0 + t;
           if (iy >= 0 && iy < HIN) {
+            // tap column outermost: consecutive FMAs go to all NL x TW accumulators in turn (each accumulator still takes its
+            // taps in the same order, so the sums are bit-identical to the row-major loop)
 #pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-              if ((r - ky + P * 4) % S == 0) {
-                const int slot = (((r - ky + P * 4) / S) % NL);
+            for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx)
+              for (int ky = 0; ky < K; ++ky)
+                if ((r - ky + P * 4) % S == 0) {
+                  const int slot = (((r - ky + P * 4) / S) % NL);
 #pragma unroll
                   for (int q = 0; q < TW; ++q) acc[slot][q] = __ffma2_rn(v[q * S + kx], w[ky * K + kx], acc[slot][q]);
-              }
-            }
+                }
           }
           if (active) ptx::mbar_arrive(&empty[s]);
           if (++s == STAGES) {

@@ -141,6 +141,14 @@ __device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same for 16-bit operands: two consecutive K elements per 32-bit TMEM column (K = 16 per MMA = 8 columns)
+__device__ __forceinline__ void mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // registers -> TMEM: thread t of the warp writes lane (base + t), 16 consecutive 32-bit columns.  No wait inside.
 __device__ __forceinline__ void tmem_st32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -415,9 +423,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const bool w_res_nb = p.w_res == 2;
   const int W_RES_BYTES = w_res ? (w_res_nb ? 1 : p.n_blocks) * p.k_chunks * Cfg::NW * W_BYTES : 0;
   const int STAGE_BYTES = Cfg::A_BYTES + (w_res ? 0 : Cfg::NW * W_BYTES);   // A (hi) tile [+ W hi, W lo tiles]
-  static_assert(!TS || (GATED && Cfg::TF32), "TS is the gated fp32 form");
+  static_assert(!TS || Cfg::TF32 || GATED, "TS: fp32 layers, and the gated bf16 ones (an ungated bf16 layer has no transform at all)");
   constexpr int LO_SLOTS = (Cfg::TF32 && !TS) ? 2 : 0;                       // ring of the TF32 lo operand of A (shared memory)
-  constexpr uint32_t TS_A_COL0 = 256, TS_SLOTS = 4, TS_SLOT_COLS = 64;       // TS: ring of the A operands in tensor memory
+  // TS: ring of the A operands in tensor memory.  Gated (two epilogue groups): accumulators in columns [0, 256), four slots
+  // in [256, 512).  Ungated (four groups, one 96-column accumulator each, BN <= 96): [0, 384), two slots in [384, 512).
+  constexpr uint32_t TS_A_COL0 = GATED ? 256 : 384, TS_SLOTS = GATED ? 4 : 2, TS_SLOT_COLS = 64;
+  constexpr uint32_t TS_SLOT_SHIFT = GATED ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* w_base = smem;                                      // resident weights (1024-aligned tiles), may be empty
@@ -454,8 +465,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // -> stage group + n_groups * (j % ACC_DEPTH), use j / ACC_DEPTH.  A stage is only ever waited on by its own group, which
   // sees every one of its phases (a parity wait is only meaningful for the current or the immediately preceding phase).
   constexpr int NAS = 4;
-  const int ACC_DEPTH = TS ? (p.BN <= 64 ? 2 : 1) : NAS / n_groups;
-  const int acc_cols = (TS && p.BN <= 64) ? 64 : 128;
+  const int ACC_DEPTH = TS ? ((GATED && p.BN <= 64) ? 2 : 1) : NAS / n_groups;
+  const int acc_cols = TS ? (GATED ? (p.BN <= 64 ? 64 : 128) : 96) : 128;
   constexpr bool transform = Cfg::TF32 || GATED;
   // 32-bit work-item arithmetic throughout: a 64-bit divide by a run-time value is a ~100-instruction
   // subroutine, and every role used to pay several of them per item.
@@ -594,7 +605,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (ks < ksteps) {
               const uint32_t acc = (kc | ks) != 0;
               const uint32_t ko = (uint32_t)ks * 2u;   // UK elements = 32 bytes = 2 descriptor units
-              if constexpr (TS) {
+              if constexpr (TS && !Cfg::TF32) {
+                const uint32_t a_tm = tmem_base + TS_A_COL0 + (cc & (TS_SLOTS - 1u)) * TS_SLOT_COLS + (uint32_t)ks * 8u;
+                ptx::mma_ts_f16(d_tmem, a_tm, DESC_HI64 | (w_lo + ko), idesc, acc);
+              } else if constexpr (TS) {
                 const uint32_t a_tm = tmem_base + TS_A_COL0 + (cc & (TS_SLOTS - 1u)) * TS_SLOT_COLS + (uint32_t)ks * 8u;   // hi; lo 32 columns on
                 const uint64_t whi = DESC_HI64 | (w_lo + ko), wlo = DESC_HI64 | (w_lo + w_step + ko);
                 ptx::mma_ts_tf32(d_tmem, a_tm + 32u, whi, idesc, acc);
@@ -656,13 +670,43 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int k0 = kc * Cfg::KC;
           const int nch = min(8, (p.K - k0) / EPCH);  // chunks that hold real data (the rest is TMA zero fill)
           ptx::mbar_wait(&full[s], ph);
-          if (TS) ptx::mbar_wait(&lo_empty[cc & (TS_SLOTS - 1u)], ((cc >> 2) & 1u) ^ 1u);   // the MMAs of four chunks ago are done with the TMEM slot
+          if (TS) ptx::mbar_wait(&lo_empty[cc & (TS_SLOTS - 1u)], ((cc >> TS_SLOT_SHIFT) & 1u) ^ 1u);   // the MMAs of four chunks ago are done with the TMEM slot
           else if (Cfg::TF32) ptx::mbar_wait(&lo_empty[cc & 1u], ((cc >> 1) & 1u) ^ 1u);   // the MMAs of two chunks ago are done with the slot
           const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
           [[maybe_unused]] const uint32_t a_lo_slot = ptx::smem_u32(lo_base + (cc & 1u) * Cfg::A_BYTES) + row_off;
           const uint32_t g_u32 = ptx::smem_u32(gate_s + s * (TC_GATE_ROWS * 128)) + prow * 128u + (uint32_t)j0 * 16u;
           uint4 raw[4], gq[4];
-          if constexpr (TS) {
+          if constexpr (TS && !Cfg::TF32) {
+            // bf16: the thread's four 16-byte chunks = 32 gated values = 16 TMEM columns (element pairs) of its lane
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              raw[jj] = ptx::lds128(a_hi + (((uint32_t)(j0 + jj) ^ xr) << 4));
+              gq[jj] = ptx::lds128(g_u32 + (uint32_t)jj * 16u);
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[jj]);
+              const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq[jj]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 m2 = __hmul2(h[e], gh[e]);
+                pk[4 * jj + e] = *reinterpret_cast<const uint32_t*>(&m2);
+              }
+            }
+            const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TS_A_COL0 + (cc & (TS_SLOTS - 1u)) * TS_SLOT_COLS +
+                                   (uint32_t)j0 * 4u;
+            ptx::tc_fence_after();
+            ptx::tmem_st32x32b_x16(t_row, pk);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&ready[s]);
+            if (++s == S) {
+              s = 0;
+              ph ^= 1;
+            }
+            continue;
+          } else if constexpr (TS) {
             // row r = TMEM lane r (warp w reaches lanes 32 (w % 4) ..): this thread's 16 gated values as TF32 hi and lo into
             // columns 4 j0 .. 4 j0 + 15 of the slot's hi / lo blocks.  K tail: the TMA zero fill makes both zero.
 #pragma unroll
@@ -758,6 +802,38 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ptx::mbar_wait(&full[s], ph);
           ptx::mbar_wait(&lo_empty[cc & 1u], ((cc >> 1) & 1u) ^ 1u);   // the MMAs of two chunks ago are done with the slot
           const uint32_t a_hi = ptx::smem_u32(stage_base + (size_t)s * STAGE_BYTES) + row_off;
+          if constexpr (TS) {
+            // row r = TMEM lane r: the row's 32 values as TF32 hi / lo into the slot's two 32-column blocks, 16 at a time
+            // (register budget).  The K tail is zero by the TMA fill.
+            const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TS_A_COL0 + (cc & 1u) * TS_SLOT_COLS;
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint4 raw4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) raw4[j] = ptx::lds128(a_hi + (((uint32_t)(4 * half + j) ^ xr) << 4));
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t* rp = &raw4[j].x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  hi[4 * j + e] = rp[e] & 0xFFFFE000u;
+                  lo[4 * j + e] = tf32_lo_bits(rp[e]);
+                }
+              }
+              ptx::tmem_st32x32b_x16(t_row + 16u * half, hi);
+              ptx::tmem_st32x32b_x16(t_row + 32u + 16u * half, lo);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&ready[s]);
+            if (++s == S) {
+              s = 0;
+              ph ^= 1;
+            }
+            continue;
+          }
           const uint32_t a_lo_slot = ptx::smem_u32(lo_base + (cc & 1u) * Cfg::A_BYTES) + row_off;
           // all loads before the first dependent instruction (the inline-asm shared-memory accesses keep program order)
           uint4 raw[8];
@@ -1229,7 +1305,21 @@ inline int pw_tc_add(PwTcPlan* plan, int id, const float* w_host, const float* d
   l.gated = gated;
   l.scale = d_scale;
   l.bias = d_bias;
-  l.BN = pick_bn(N, f32 ? TcCfg<float>::BN_MAX : TcCfg<__nv_bfloat16>::BN_MAX);
+  {
+    // MC_TC_TS_MASK=<hex>: fp32 layers (bit = plan layer id) that take A through tensor memory; default all of them
+    static const unsigned long long ts_mask = getenv("MC_TC_TS_MASK") ? strtoull(getenv("MC_TC_TS_MASK"), nullptr, 16) : ~0ull;
+    l.ts = (f32 || gated) && id < 64 && ((ts_mask >> id) & 1ull) != 0;
+    // measured (B200, per-layer CUDA events, same run): every gated layer gains (-6 % at K = 32 ... -26 % at K = 1152); ungated
+    // layers gain from K = 80 on (b6-8.expand -10 %, b9-11 -17 %, b12-15 -42 %) and lose 3 % below (one k-chunk or two: the
+    // tcgen05.st round trip is not amortised); the head conv (N = 1280) loses 7 % to the narrower blocks (14 x 96 for 10 x 128)
+    if (!gated && (K <= 64 || (N == 1280 && !plan->relu_variant))) l.ts = false;
+    // bf16 gated layers: -20..25 % on b11-b15.project (K >= 672, two n-blocks), +5..10 % on the single-block K = 480 / 672 ones
+    // (one accumulator per epilogue group instead of two), a wash on the front layers
+    if (!f32 && !(K >= 672 && N >= 192)) l.ts = false;
+  }
+  // ungated TS layers: four 96-column accumulators + the A ring share the 512 TMEM columns
+  const int bn_max = !f32 ? TcCfg<__nv_bfloat16>::BN_MAX : ((l.ts && !gated) ? 96 : TcCfg<float>::BN_MAX);
+  l.BN = pick_bn(N, bn_max);
   l.n_blocks = (N + l.BN - 1) / l.BN;
   const int kc = f32 ? TcCfg<float>::KC : TcCfg<__nv_bfloat16>::KC;
   l.k_chunks = (K + kc - 1) / kc;
@@ -1247,7 +1337,7 @@ inline int pw_tc_add(PwTcPlan* plan, int id, const float* w_host, const float* d
   // disables the mode).
   {
     auto wbytes = [&](int bn, int nblocks) { return f32 ? tc_w_res_bytes<float>(bn, nblocks, l.k_chunks) : tc_w_res_bytes<__nv_bfloat16>(bn, nblocks, l.k_chunks); };
-    auto stages_res = [&](int wb) { return f32 ? tc_num_stages_res<float>(wb) : tc_num_stages_res<__nv_bfloat16>(wb); };
+    auto stages_res = [&](int wb) { return f32 ? tc_num_stages_res<float>(wb, l.ts) : tc_num_stages_res<__nv_bfloat16>(wb); };
     static const bool no_w_res = getenv("MC_TC_NO_WRES") != nullptr, no_nb = getenv("MC_TC_NO_WRES_NB") != nullptr;
     l.w_mode = 0;
     if (!no_w_res && wbytes(l.BN, l.n_blocks) <= TC_W_RES_MAX) {
@@ -1262,7 +1352,6 @@ inline int pw_tc_add(PwTcPlan* plan, int id, const float* w_host, const float* d
           if (q) ++q;
         }
       }
-      const int bn_max = f32 ? TcCfg<float>::BN_MAX : TcCfg<__nv_bfloat16>::BN_MAX;
       for (int cap = bn_forced ? bn_forced : bn_max; cap >= 64; cap -= 16) {
         const int bn = pick_bn(N, cap), nblocks = (N + bn - 1) / bn;
         if (nblocks > plan->num_sms) break;
@@ -1275,11 +1364,6 @@ inline int pw_tc_add(PwTcPlan* plan, int id, const float* w_host, const float* d
         if (bn_forced) break;
       }
     }
-  }
-  {
-    // MC_TC_TS_MASK=<hex>: gated fp32 layers (bit = plan layer id) that take A through tensor memory; default all of them
-    static const unsigned long long ts_mask = getenv("MC_TC_TS_MASK") ? strtoull(getenv("MC_TC_TS_MASK"), nullptr, 16) : ~0ull;
-    l.ts = f32 && gated && id < 64 && ((ts_mask >> id) & 1ull) != 0;
   }
   const size_t n = (size_t)N * K;
   int rc;
@@ -1408,7 +1492,7 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
   const int w_bytes = f32 ? tc_w_res_bytes<float>(l.BN, a.w_res == 2 ? 1 : l.n_blocks, l.k_chunks)
                           : tc_w_res_bytes<__nv_bfloat16>(l.BN, a.w_res == 2 ? 1 : l.n_blocks, l.k_chunks);
   size_t smem;
-  const bool ts = l.ts && a.gate != nullptr && !plan->relu_variant;
+  const bool ts = l.ts && (a.gate != nullptr) == l.gated;
   const size_t lo_ring = (f32 && !ts) ? tc_lo_ring_bytes<float>() : 0;
   if (a.w_res) {
     a.stages = f32 ? tc_num_stages_res<float>(w_bytes, ts) : tc_num_stages_res<__nv_bfloat16>(w_bytes);
@@ -1425,16 +1509,31 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
     l.g_ptr = a.gate;
   }
   const CUtensorMap& tmG = gated ? l.tmG : l.tmW;   // ungated kernels never touch it
-  if (plan->relu_variant) {   // MLP head (fp32, ungated)
+  if (plan->relu_variant && ts) {   // MLP head (fp32, ungated)
+    static std::atomic<unsigned long long> attr_mask{0};
+    if (first_use_on_device(attr_mask))
+      MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    pw_tc_kernel<float, false, true, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+  } else if (plan->relu_variant) {
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
     pw_tc_kernel<float, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+  } else if (f32 && !gated && ts) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    if (first_use_on_device(attr_mask))
+      MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    pw_tc_kernel<float, false, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   } else if (f32 && gated && ts) {
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
     pw_tc_kernel<float, true, false, false, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+  } else if (!f32 && gated && ts) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    if (first_use_on_device(attr_mask))
+      MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    pw_tc_kernel<__nv_bfloat16, true, false, false, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   } else if (f32 && gated)
     pw_tc_kernel<float, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
   else if (f32)
@@ -1491,12 +1590,18 @@ inline int pw_tc_run_pool(PwTcPlan* plan, int id, const void* A, int nb, float* 
   a.w_res = 0;
   a.pool_nb = nb;
   const int stage_bytes = f32 ? tc_stage_bytes<float>(l.BN) : tc_stage_bytes<__nv_bfloat16>(l.BN);
-  a.stages = f32 ? tc_num_stages<float>(l.BN, TC_POOL_BYTES) : tc_num_stages<__nv_bfloat16>(l.BN, TC_POOL_BYTES);
-  const size_t smem = TC_FIXED_BYTES + TC_POOL_BYTES + (f32 ? tc_lo_ring_bytes<float>() : 0) + (size_t)a.stages * stage_bytes;
+  const bool ts = f32 && l.ts;
+  a.stages = f32 ? tc_num_stages<float>(l.BN, TC_POOL_BYTES, ts) : tc_num_stages<__nv_bfloat16>(l.BN, TC_POOL_BYTES);
+  const size_t smem = TC_FIXED_BYTES + TC_POOL_BYTES + ((f32 && !ts) ? tc_lo_ring_bytes<float>() : 0) + (size_t)a.stages * stage_bytes;
   a.m_tiles = (nb + 1) / 2;
   const int64_t items = a.m_tiles * a.n_blocks;
   const int grid = (int)std::min<int64_t>(items, plan->num_sms);
-  if (f32) pw_tc_kernel<float, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
+  if (ts) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    if (first_use_on_device(attr_mask))
+      MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
+    pw_tc_kernel<float, false, false, true, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
+  } else if (f32) pw_tc_kernel<float, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
   else pw_tc_kernel<__nv_bfloat16, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
   MC_CHECK_LAUNCH();
   return MC_OK;
