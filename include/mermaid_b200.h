@@ -87,6 +87,15 @@ int mc_check_extract_inputs(int32_t height, int32_t width, const int32_t* rowcol
 int mc_crop_patches(const mc_image* images_host, int32_t n_images, const mc_point* points_host,
                     int64_t n_points, uint8_t* patches_dev /* n x 224 x 224 x 3 */, void* stream);
 
+/* ---- A2': the patch-size != 224 path (model.json "config": {"patch_size": ...}, mermaid_classifier/pyspacer/inference/
+ *      export.py:77; north_star's "crop / bilinear-resize"): a crop_size x crop_size window around each point (same
+ *      reflect rule, centre offset crop_size / 2; even sizes) resized to 224 x 224 with bilinear interpolation in the
+ *      arithmetic of torch.nn.functional.interpolate(mode="bilinear", align_corners=False) and rounded half-to-even to
+ *      uint8.  crop_size == 224 is mc_crop_patches.  The patches then go through mc_extract_patches. ------------- */
+int mc_crop_resize_patches(const mc_image* images_host, int32_t n_images, const mc_point* points_host,
+                           int64_t n_points, int32_t crop_size, uint8_t* patches_dev /* n x 224 x 224 x 3 */,
+                           void* stream);
+
 /* ---- A3: torch_extractors.transformation() (scripts/build_feature_bucket.py:420-431):
  *      ToTensor + Normalize, HWC u8 -> CHW fp32.  Exposed for the parity gate only; the
  *      extraction path fuses it into the stem kernel. -------------------------------- */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mc_synth_image": (C.c_int, [_vp, _i32, _i32, _i64, _u32, _u32, _vp]),
     "mc_check_extract_inputs": (C.c_int, [_i32, _i32, _vp, _i64, _i64, _i64]),
     "mc_crop_patches": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    "mc_crop_resize_patches": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "mc_normalize_patches": (C.c_int, [_vp, _i64, _vp, _vp]),
     "mc_backbone_param_count": (_i64, []),
     "mc_extractor_create": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _pp]),

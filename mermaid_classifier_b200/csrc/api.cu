@@ -470,6 +470,32 @@ int mc_crop_patches(const mc_image* images, int32_t n_images, const mc_point* po
   return MC_OK;
 }
 
+int mc_crop_resize_patches(const mc_image* images, int32_t n_images, const mc_point* points, int64_t n, int32_t crop_size,
+                           uint8_t* patches_dev, void* stream) {
+  if (n == 0) return MC_OK;
+  if (!images || !points || !patches_dev || n_images < 1 || n < 0) return fail(MC_ERR_BAD_ARG, "mc_crop_resize_patches: null");
+  if (crop_size < 2 || crop_size > 4096 || (crop_size & 1))
+    return fail(MC_ERR_BAD_ARG, "mc_crop_resize_patches: crop_size must be an even number in [2, 4096]");
+  if (crop_size == 224) return mc_crop_patches(images, n_images, points, n, patches_dev, stream);
+  int rc;
+  if ((rc = check_images(images, n_images)) || (rc = check_points(images, n_images, points, n))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  mc_image* d_im = nullptr;
+  mc_point* d_pt = nullptr;
+  MC_CUDA(cudaMallocAsync((void**)&d_im, n_images * sizeof(mc_image), st));
+  MC_CUDA(cudaMallocAsync((void**)&d_pt, n * sizeof(mc_point), st));
+  MC_CUDA(cudaMemcpyAsync(d_im, images, n_images * sizeof(mc_image), cudaMemcpyHostToDevice, st));
+  MC_CUDA(cudaMemcpyAsync(d_pt, points, n * sizeof(mc_point), cudaMemcpyHostToDevice, st));
+  for (int64_t s = 0; s < n; s += 32768) {
+    const int nb = (int)std::min<int64_t>(32768, n - s);
+    crop_resize_kernel<<<dim3(28, nb), 224, 0, st>>>(d_im, d_pt + s, crop_size, patches_dev + s * 224 * 224 * 3);
+    MC_CHECK_LAUNCH();
+  }
+  MC_CUDA(cudaFreeAsync(d_im, st));
+  MC_CUDA(cudaFreeAsync(d_pt, st));
+  return MC_OK;
+}
+
 int mc_normalize_patches(const uint8_t* patches_dev, int64_t n, float* out_dev, void* stream) {
   if (n == 0) return MC_OK;
   if (!patches_dev || !out_dev || n < 0) return fail(MC_ERR_BAD_ARG, "mc_normalize_patches: null");

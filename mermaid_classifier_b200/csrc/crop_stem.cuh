@@ -202,4 +202,50 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const mc_image* __restrict
   }
 }
 
+// Crop a crop x crop window around each point (same reflect-padded window rule as crop_kernel, centre offset crop / 2) and
+// resize it to 224 x 224 with bilinear interpolation -- the patch-size != 224 path (model.json config.patch_size,
+// inference/export.py:77).  The arithmetic is torch.nn.functional.interpolate(mode="bilinear", align_corners=False,
+// antialias=False) on the float patch, reproduced to the bit: source index = fma(scale, i + 0.5, -0.5) clamped at 0, weights
+// l1 = index - floor(index), l0 = 1 - l1, value = fma(l0, a, l1 * b) along x and then along y (the contraction torch's CPU
+// kernel compiles to; checked against torch in tests/test_oracle_crop.py); the result is rounded half-to-even to uint8.
+// One CTA = one band of eight output rows of one patch, one thread = one output pixel (its four taps are byte gathers through
+// the read-only path: neighbouring threads read neighbouring pixels, and this is the side path -- 224-pixel patches take the
+// coalesced crop / the fused stem).
+__global__ void __launch_bounds__(224) crop_resize_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__ points,
+                                                          int crop, uint8_t* __restrict__ out) {
+  constexpr int ROWS = 8;
+  const int64_t k = blockIdx.y;
+  const mc_point pt = points[k];
+  const mc_image im = images[pt.image];
+  const int half = crop / 2;
+  const int j = threadIdx.x;                       // output column
+  const float scale = (float)crop / 224.f;
+  // x taps of this thread
+  const float rx = fmaxf(__fmaf_rn(scale, (float)j + 0.5f, -0.5f), 0.f);
+  const int x0c = min((int)rx, crop - 1);
+  const float lx1 = fminf(fmaxf(rx - (float)x0c, 0.f), 1.f), lx0 = 1.f - lx1;
+  const int x1c = min(x0c + 1, crop - 1);
+  const int xa = reflect_idx(pt.col - half + x0c, im.width) * 3, xb = reflect_idx(pt.col - half + x1c, im.width) * 3;
+#pragma unroll 2
+  for (int r = 0; r < ROWS; ++r) {
+    const int i = blockIdx.x * ROWS + r;
+    const float ry = fmaxf(__fmaf_rn(scale, (float)i + 0.5f, -0.5f), 0.f);
+    const int y0c = min((int)ry, crop - 1);
+    const float ly1 = fminf(fmaxf(ry - (float)y0c, 0.f), 1.f), ly0 = 1.f - ly1;
+    const int y1c = min(y0c + 1, crop - 1);
+    const uint8_t* row0 = im.data + (int64_t)reflect_idx(pt.row - half + y0c, im.height) * im.row_pitch;
+    const uint8_t* row1 = im.data + (int64_t)reflect_idx(pt.row - half + y1c, im.height) * im.row_pitch;
+    uint8_t* dst = out + ((k * 224 + i) * 224 + j) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = (float)__ldg(row0 + xa + c), b = (float)__ldg(row0 + xb + c);
+      const float d = (float)__ldg(row1 + xa + c), e = (float)__ldg(row1 + xb + c);
+      const float t0 = __fmaf_rn(lx0, a, __fmul_rn(lx1, b));
+      const float t1 = __fmaf_rn(lx0, d, __fmul_rn(lx1, e));
+      const float v = __fmaf_rn(ly0, t0, __fmul_rn(ly1, t1));
+      dst[c] = (uint8_t)min(max(__float2int_rn(v), 0), 255);
+    }
+  }
+}
+
 }  // namespace mc

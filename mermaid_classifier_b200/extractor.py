@@ -28,6 +28,7 @@ from . import _lib, weights as _weights
 from .spacer_compat import (
     ExtractFeaturesReturnMsg,
     ImageFeatures,
+    check_extract_inputs,
     image_features_from_array,
     storage_factory,
 )
@@ -64,6 +65,7 @@ class EfficientNetExtractor:
         mode: str = "fp32",
         max_batch: int = 256,
         state_dict: dict | None = None,
+        crop_size: int = _lib.CROP_SIZE,
     ):
         if state_dict is None and (not data_locations or "weights" not in data_locations):
             raise ValueError("data_locations must contain a 'weights' DataLocation")
@@ -72,6 +74,11 @@ class EfficientNetExtractor:
         self.data_locations = dict(data_locations or {})
         self.data_hashes = dict(data_hashes or {})
         self.mode = mode
+        # window cropped around each point; != 224 (model.json config.patch_size, inference/export.py:77) adds the bilinear
+        # resize to the network's 224 x 224 input (mc_crop_resize_patches)
+        self.crop_size = int(crop_size)
+        if self.crop_size < 2 or self.crop_size % 2:
+            raise ValueError(f"crop_size must be a positive even number; got {crop_size!r}")
         self.max_batch = int(max_batch)
         self._batch_size = int(batch_size) if batch_size else None
         self._device_arg = device
@@ -162,6 +169,12 @@ class EfficientNetExtractor:
         rc = np.ascontiguousarray(np.asarray(rowcols, dtype=np.int32).reshape(-1, 2))
         out = np.empty((rc.shape[0], self.feature_dim), dtype=np.float32)
         torch = _lib.require_cuda()
+        if self.crop_size != self.CROP_SIZE:
+            check_extract_inputs(arr, [tuple(x) for x in rc.tolist()], "")
+            with torch.cuda.device(self._device_index):
+                dev = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+                pts = np.concatenate([np.zeros((rc.shape[0], 1), np.int32), rc], axis=1)
+                return self.extract_device([dev], pts).cpu().numpy()
         with torch.cuda.device(self._device_index):
             _lib.check(_lib.load().mc_extract_image_host(
                 h, arr.ctypes.data, arr.shape[0], arr.shape[1], arr.strides[0], rc.ctypes.data, rc.shape[0],
@@ -183,6 +196,15 @@ class EfficientNetExtractor:
         torch = _lib.require_cuda()
         if len(images) != len(rowcols_list):
             raise ValueError("images and rowcols_list differ in length")
+        if self.crop_size != self.CROP_SIZE:
+            # resize path: image by image through crop + bilinear resize + the pre-cropped-patch call
+            parts = [self.extract_array(im.numpy() if hasattr(im, "data_ptr") else im, rc)
+                     for im, rc in zip(images, rowcols_list) if len(rc)]
+            feats = np.concatenate(parts) if parts else np.zeros((0, self.feature_dim), dtype=np.float32)
+            labels = None
+            if head is not None and feats.shape[0]:
+                labels = head.scores_host(feats, want_proba=False, want_labels=True)[1].astype(np.int32)
+            return (feats if want_features else None), labels
         keep = []   # keep the arrays alive for the duration of the call
         tab = (_lib.McImage * max(len(images), 1))()
         pts = []
@@ -271,6 +293,13 @@ class EfficientNetExtractor:
         with torch.cuda.device(self._device_index):
             if out is None:
                 out = torch.empty((pts.shape[0], self.feature_dim), dtype=torch.float32, device="cuda")
+            if self.crop_size != self.CROP_SIZE:   # crop + bilinear resize, then the pre-cropped-patch path, a sub-batch at a time
+                for s in range(0, pts.shape[0], self.max_batch):
+                    sub = pts[s:s + self.max_batch]
+                    patches = crop_resize_patches_device(images, sub, self.crop_size)
+                    _lib.check(_lib.load().mc_extract_patches(h, patches.data_ptr(), sub.shape[0], out[s:].data_ptr(),
+                                                              _lib.stream_ptr()))
+                return out
             _lib.check(_lib.load().mc_extract_points(h, C.addressof(tab), len(images), pts.ctypes.data, pts.shape[0],
                                                      out.data_ptr(), _lib.stream_ptr()))
         return out
@@ -293,6 +322,20 @@ def crop_patches_device(images: Sequence[Any], points: np.ndarray):
     out = torch.empty((pts.shape[0], 224, 224, 3), dtype=torch.uint8, device="cuda")
     _lib.check(_lib.load().mc_crop_patches(C.addressof(tab), len(images), pts.ctypes.data, pts.shape[0], out.data_ptr(),
                                            _lib.stream_ptr()))
+    return out
+
+
+def crop_resize_patches_device(images: Sequence[Any], points: np.ndarray, crop_size: int):
+    """``crop_size`` window around each point, bilinear-resized to 224 x 224 on the device (``mc_crop_resize_patches``):
+    returns a CUDA ``(n, 224, 224, 3) uint8`` tensor; ``crop_size == 224`` is the plain crop."""
+    torch = _lib.require_cuda()
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.int32).reshape(-1, 3))
+    tab = (_lib.McImage * len(images))()
+    for i, t in enumerate(images):
+        tab[i] = _lib.McImage(t.data_ptr(), t.shape[0], t.shape[1], t.stride(0))
+    out = torch.empty((pts.shape[0], 224, 224, 3), dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.load().mc_crop_resize_patches(C.addressof(tab), len(images), pts.ctypes.data, pts.shape[0], int(crop_size),
+                                                  out.data_ptr(), _lib.stream_ptr()))
     return out
 
 

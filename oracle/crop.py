@@ -70,6 +70,50 @@ def crop_patches(im: np.ndarray, rowcols, crop_size: int = CROP_SIZE) -> np.ndar
     return out
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add: the float64 product of two float32 values is exact, so one rounding remains."""
+    return (np.asarray(a, np.float32).astype(np.float64) * np.asarray(b, np.float32).astype(np.float64)
+            + np.asarray(c, np.float32).astype(np.float64)).astype(np.float32)
+
+
+def bilinear_taps(in_size: int, out_size: int):
+    """Taps of ``torch.nn.functional.interpolate(mode="bilinear", align_corners=False, antialias=False)`` along one axis:
+    ``(i0, i1, l0, l1)`` with source index ``fma(scale, i + 0.5, -0.5)`` clamped at 0 (torch's CPU kernel contracts the
+    multiply-add), ``l1`` its fraction, ``l0 = 1 - l1``."""
+    scale = np.float32(in_size) / np.float32(out_size)
+    i = np.arange(out_size, dtype=np.float32) + np.float32(0.5)
+    real = np.maximum(_fma32(np.full_like(i, scale), i, np.full_like(i, -0.5)), np.float32(0))
+    i0 = np.minimum(real.astype(np.int64), in_size - 1)
+    l1 = np.clip((real - i0.astype(np.float32)).astype(np.float32), 0, 1).astype(np.float32)
+    return i0, np.minimum(i0 + 1, in_size - 1), (np.float32(1) - l1).astype(np.float32), l1
+
+
+def resize_patches_bilinear(patches_u8: np.ndarray, out_size: int = CROP_SIZE) -> np.ndarray:
+    """``(n, P, P, C) uint8 -> (n, out, out, C) uint8``: torch's float bilinear resize, bit for bit (x pass then y pass, each
+    ``fma(l0, a, l1 * b)``), rounded half-to-even.  Pinned to torch itself by ``tests/test_oracle_crop.py``."""
+    x = np.asarray(patches_u8).astype(np.float32)
+    P = x.shape[1]
+    i0, i1, l0, l1 = bilinear_taps(P, out_size)
+    def along_x(rows):
+        a, b = rows[:, :, i0, :], rows[:, :, i1, :]
+        w0 = np.broadcast_to(l0[None, None, :, None], a.shape)
+        w1 = np.broadcast_to(l1[None, None, :, None], a.shape)
+        return _fma32(w0, a, (w1 * b).astype(np.float32))
+    t0, t1 = along_x(x[:, i0]), along_x(x[:, i1])
+    w0 = np.broadcast_to(l0[None, :, None, None], t0.shape)
+    w1 = np.broadcast_to(l1[None, :, None, None], t0.shape)
+    v = _fma32(w0, t0, (w1 * t1).astype(np.float32))
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def crop_resize_patches(im: np.ndarray, rowcols, crop_size: int, out_size: int = CROP_SIZE) -> np.ndarray:
+    """The patch-size != 224 path: ``crop_size`` window (even sizes; centre offset ``crop_size // 2``) -> bilinear -> ``out_size``."""
+    if crop_size % 2:
+        raise ValueError("crop_size must be even (the window centre rule of crop_patches is only pinned for even sizes)")
+    p = crop_patches(im, rowcols, crop_size)
+    return p if crop_size == out_size else resize_patches_bilinear(p, out_size)
+
+
 def normalize_patches(patches_u8: np.ndarray) -> np.ndarray:
     """torchvision ``ToTensor`` + ``Normalize(IMAGENET_MEAN, IMAGENET_STD)``:
     ``y[c,i,j] = (u8[i,j,c] / 255 - mean[c]) / std[c]`` in float32, HWC -> CHW.

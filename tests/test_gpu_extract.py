@@ -8,6 +8,7 @@ from mermaid_classifier_b200 import _lib, synth
 from mermaid_classifier_b200.extractor import (
     EfficientNetExtractor,
     crop_patches_device,
+    crop_resize_patches_device,
     normalize_patches_device,
     synth_image_device,
 )
@@ -88,6 +89,46 @@ def test_crop_multi_image_and_pitch():
         want.append(ocrop.crop_patches(im, rc))
     got = crop_patches_device(dev, np.array(pts, dtype=np.int32)).cpu().numpy()
     assert np.array_equal(got, np.concatenate(want))
+
+
+@pytest.mark.parametrize("crop", [448, 300, 112, 64])
+def test_crop_resize_bit_exact(crop):
+    """Patch size != 224: reflect-padded ``crop`` window -> bilinear -> 224 x 224 uint8, bit-exact against the oracle (which
+    is torch's ``interpolate`` bit for bit, tests/test_oracle_crop.py); windows larger than the image reflect repeatedly."""
+    for H, W in ((600, 800), (100, 37)):
+        im = synth.synth_image(4, crop, H, W)
+        pts = synth.synth_points(4, crop, H, W, 10, corners=True)
+        want = ocrop.crop_resize_patches(im, pts, crop)
+        p3 = np.array([(0, r, c) for r, c in pts], dtype=np.int32)
+        got = crop_resize_patches_device([torch.from_numpy(im).cuda()], p3, crop).cpu().numpy()
+        assert got.shape == want.shape == (len(pts), 224, 224, 3)
+        assert np.array_equal(got, want)
+    same = crop_resize_patches_device([torch.from_numpy(im).cuda()], p3, 224).cpu().numpy()
+    assert np.array_equal(same, ocrop.crop_patches(im, pts))
+    with pytest.raises(ValueError):
+        crop_resize_patches_device([torch.from_numpy(im).cuda()], p3, 225)
+
+
+def test_resize_path_features_match_oracle(backbone_sd):
+    """An extractor with ``crop_size=448`` (the 2x-context variant): crop + resize + network against the oracle's crop,
+    resize and fp32 forward at the fp32 bound; ``extract_many`` and ``__call__`` take the same path."""
+    H, W, crop = 700, 900, 448
+    im = synth.synth_image(6, 2, H, W)
+    rcs = synth.synth_points(6, 2, H, W, 9, corners=True)
+    ext = EfficientNetExtractor(state_dict=backbone_sd, mode="fp32", max_batch=4, crop_size=crop)
+    try:
+        got = ext.extract_array(im, rcs)
+        many, _ = ext.extract_many([im, im], [rcs, rcs[:3]])
+        feats, _msg = ext(im, rcs)
+    finally:
+        ext.close()
+    patches = ocrop.crop_resize_patches(im, rcs, crop)
+    want = oeff.extract_features_batched(backbone_sd, torch.from_numpy(ocrop.normalize_patches(patches)), 10).numpy()
+    assert np.abs(got - want).max() <= FP32_MAX_ABS and cosines(got, want).min() >= FP32_MIN_COS
+    assert np.array_equal(many[: len(rcs)], got) and np.array_equal(many[len(rcs):], got[:3])
+    assert np.array_equal(np.asarray([pf.data for pf in feats.point_features], np.float32), got)
+    with pytest.raises(ValueError):
+        EfficientNetExtractor(state_dict=backbone_sd, crop_size=225)
 
 
 def test_normalize_bit_exact():
