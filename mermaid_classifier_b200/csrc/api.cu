@@ -228,9 +228,8 @@ int launch_dw(mc_extractor* h, const BlockCfg& b, int n_off, T* out, int nb, cud
   h->launches++;
   {
     ProfScope ps(h, 3 + 4 * bidx, st);
-    se_kernel<<<nb, 256, (C + b.c_se) * sizeof(float), st>>>(h->d_pool, nparts, 1.f / (float)(b.h_out * b.h_out),
-                                                            P + b.w_se1, P + b.b_se1, P + b.w_se2, P + b.b_se2,
-                                                            h->d_gate, h->d_gate_h, C, b.c_se);
+    se_launch(h->d_pool, nparts, 1.f / (float)(b.h_out * b.h_out), P + b.w_se1, P + b.b_se1, P + b.w_se2, P + b.b_se2,
+              h->d_gate, h->d_gate_h, C, b.c_se, nb, st);
   }
   MC_CHECK_LAUNCH();
   h->launches++;
@@ -325,9 +324,8 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
         h->launches++;
         {
           ProfScope ps(h, 3 + 4 * (int)bi, st);
-          se_kernel<<<nb, 256, (b.c_mid + b.c_se) * sizeof(float), st>>>(
-              h->d_pool, fused_shape_of(fl.shape, (int)sizeof(T)).nbands, 1.f / (float)(b.h_out * b.h_out), P + b.w_se1,
-              P + b.b_se1, P + b.w_se2, P + b.b_se2, h->d_gate, h->d_gate_h, b.c_mid, b.c_se);
+          se_launch(h->d_pool, fused_shape_of(fl.shape, (int)sizeof(T)).nbands, 1.f / (float)(b.h_out * b.h_out), P + b.w_se1,
+                    P + b.b_se1, P + b.w_se2, P + b.b_se2, h->d_gate, h->d_gate_h, b.c_mid, b.c_se, nb, st);
         }
         MC_CHECK_LAUNCH();
         h->launches++;

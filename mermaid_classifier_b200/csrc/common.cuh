@@ -34,6 +34,26 @@ inline int fail(int code, const std::string& msg) {
 // backbone activations: fast intrinsics by name (the library is NOT built with --use_fast_math)
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// Experiment (MC_SWISH_NR=1, off): swish of a pair with ONE MUFU op per value -- e = 2^(-x log2 e) on the XU, the reciprocal of
+// 1 + e on the FMA pipe (integer seed, three Newton steps r <- r (2 - d r) as packed FFMA2 / FMUL2: 5 % -> 2.5e-3 -> 6.6e-6
+// -> 1.2e-7 relative error).  Measured on B200 in the GEMM epilogue: expand layers 4-11 % SLOWER, although the XU pipe is
+// the busiest unit of that epilogue (ncu 46-57 %) -- the extra nine FMA-pipe instructions per pair cost more issue slots
+// than the MUFU.RCP they replace frees.  The exponent is clamped at 2^60 so that 1 + e stays finite.
+#ifndef MC_SWISH_NR
+#define MC_SWISH_NR 0
+#endif
+__device__ __forceinline__ float2 silu2_nr(float2 x) {
+  float ex, ey;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fminf(x.x * -1.4426950408889634f, 60.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(fminf(x.y * -1.4426950408889634f, 60.f)));
+  const float2 d = make_float2(1.f + ex, 1.f + ey);
+  const float2 nd = make_float2(-d.x, -d.y);
+  float2 r = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(d.x)), __int_as_float(0x7EF311C7 - __float_as_int(d.y)));
+  const float2 two = make_float2(2.f, 2.f);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) r = __fmul2_rn(r, __ffma2_rn(nd, r, two));
+  return __fmul2_rn(x, r);
+}
 // swish of bn = acc * scale + bias in the activation mode of T.
 //   fp32 mode: exact form, 2 MUFU ops (ex2, rcp).
 //   bf16 mode: x * sigmoid(x) = h + h * tanh(h) with h = x / 2 and ONE MUFU op (tanh.approx, rel. error 2^-11,

@@ -1039,9 +1039,16 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i) {
+#if MC_SWISH_NR
+                  const float2 sw = silu2_nr(make_float2(y[h2][rh][i][0], y[h2][rh][i][1]));
+                  y[h2][rh][i][0] = sw.x;
+                  y[h2][rh][i][1] = sw.y;
+#else
 #pragma unroll
                   for (int e = 0; e < 2; ++e) y[h2][rh][i][e] = __fdividef(y[h2][rh][i][e], 1.f + __expf(-y[h2][rh][i][e]));
+#endif
+                }
           }
           if (RELU) {
             if (p.act == 2) {

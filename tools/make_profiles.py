@@ -14,11 +14,16 @@ def kname(full):
     return full[: i + 1] if i >= 0 else full.split("(")[0]
 launches = [(int(r[0]), kname(r[4]), r[7], r[8], float(r[14]) / 1e3) for r in rows]
 def family(name):
-    # pw_tc_kernel<T, GATED, RELU, POOL>: ungated = expand / head layers, gated = project layers, pool = head conv + pool
-    for tag, label in (("float, 0, 0, 1>", "pw_tc(head conv + pool)"), ("bfloat16, 0, 0, 1>", "pw_tc(head conv + pool)"),
-                       (", 1, 0, 0>", "pw_tc(project, gated)"), (", 0, 0, 0>", "pw_tc(expand)"), (", 0, 1, 0>", "pw_tc(mlp head)")):
-        if "pw_tc_kernel" in name and tag in name: return label
-    for k in ("synth_image", "stem_tc", "stem", "mbconv_fused", "dw_tma", "dw_reg", "se_kernel", "pw_tc", "avgpool", "pw_simt", "head_rows"):
+    # pw_tc_kernel<T, GATED, RELU, POOL, TS>: ungated = expand / head layers, gated = project layers, pool = head conv + pool;
+    # TS = A operands through tensor memory
+    if "pw_tc_kernel" in name:
+        args = [a.strip() for a in name[name.find("<") + 1: name.rfind(">")].split(",")]
+        args += ["0"] * (5 - len(args))
+        ts = " TS" if args[4] in ("1", "true") else ""
+        if args[3] in ("1", "true"): return "pw_tc(head conv + pool)" + ts
+        if args[2] in ("1", "true"): return "pw_tc(mlp head)" + ts
+        return ("pw_tc(project, gated)" if args[1] in ("1", "true") else "pw_tc(expand)") + ts
+    for k in ("synth_image", "stem_tc", "stem", "mbconv_fused", "dw_tma", "dw_reg", "se_kernel", "avgpool", "pw_simt", "head_rows"):
         if k in name: return k
     return "other(torch)"
 # one sub-batch = from the first stem launch to the launch before the second stem (or head_rows)

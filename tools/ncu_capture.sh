@@ -3,7 +3,7 @@
 # per family.  Reports are summarised ON the GPU box (tools/ncu_table.py) and deleted: gpurun_out/ is capped at 64 MiB.
 MODE=${1:-fp32}; shift
 # round 2: b1.expand + b1.depthwise are one kernel (mbconv_fused), the stem runs on the tensor cores, the head conv pools in its epilogue
-CAPS=${@:-"stem:stem_tc_kernel:0 fused_b1:mbconv_fused_kernel:0 dw_b0:dw_tma_kernel:0 dw_b4:dw_reg_kernel:2 dw_b9:dw_reg_kernel:7 exp_b2:pw_tc_kernel:2 proj_b2:pw_tc_kernel:3 proj_b15:pw_tc_kernel:29 head_pool:pw_tc_kernel:30"}
+CAPS=${@:-"stem:stem_tc_kernel:0 fused_b1:mbconv_fused_kernel:0 dw_b0:dw_tma_kernel:0 dw_b4:dw_reg_kernel:2 dw_b9:dw_reg_kernel:7 exp_b2:pw_tc_kernel:2 exp_b9:pw_tc_kernel:16 exp_b12:pw_tc_kernel:22 proj_b2:pw_tc_kernel:3 proj_b12:pw_tc_kernel:23 proj_b15:pw_tc_kernel:29 head_pool:pw_tc_kernel:30"}
 CMD="python bench.py --images 5 --batch 500 --steps 1 --no-cpu-baseline --no-sub --mode $MODE"
 timeout 120 $CMD > gpurun_out/plain_$MODE.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$MODE.log; exit 1; }
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$MODE.csv $CMD > gpurun_out/ncu_l.log 2>&1
