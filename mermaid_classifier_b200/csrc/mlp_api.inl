@@ -74,8 +74,10 @@ struct mc_mlp {
   int n_blocks = 0, ssq_cur = 0;
   double* d_loss = nullptr;
   std::vector<float*> d_act, d_delta;  // [L] each: outputs of layer i / gradient w.r.t. them
-  float* d_part = nullptr;
-  int64_t cap_part = 0;
+  float* d_part[2] = {nullptr, nullptr};   // split-K partials; slot 1 = the second GEMM of a paired launch
+  int64_t cap_part[2] = {0, 0};
+  int* d_tickets = nullptr;   // split-K tile tickets, n_tickets per slot (zero between launches)
+  int n_tickets = 0;
   float2* d_rowstat = nullptr;
   int cap_rows = 0;
   float* d_xs = nullptr;
@@ -107,40 +109,55 @@ int mlp_ensure_rows(mc_mlp* h, int rows) {
 }
 
 // C = A * B with the layout flags of mlp_gemm_kernel; split-K when the tile grid would leave most SMs idle.
-int mlp_gemm(mc_mlp* h, bool a_mc, bool b_nc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M,
-             int N, int K, int epi, const float* bias, const float* mask, int ldmask, float* colsum, cudaStream_t st) {
+int mlp_gemm_plan(mc_mlp* h, MlpGemmP* p, bool a_mc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M,
+                  int N, int K, int epi, const float* bias, const float* mask, int ldmask, float* colsum, int slot = 0) {
   const int tiles = cdiv(M, 64) * cdiv(N, 64);
   int splits = 1;
   // few tiles and a long reduction (forward layers and the delta back-propagation at mini-batch 200): split K so that
-  // ~150 CTAs work instead of 8-40; the partials are summed in slice order (deterministic) by the epilogue kernel
-  if (!a_mc && tiles < 64 && K >= 256 && ldc == N && colsum == nullptr) {
-    splits = std::min(cdiv(K, 64), std::max(1, 160 / tiles));
+  // ~300 CTAs (two per SM) work instead of 8-40; the partials are summed in slice order (deterministic) by the last slice
+  // Measured: splitting further (640 CTAs, and the weight-gradient GEMMs over the 200 mini-batch rows as well) is SLOWER
+  // (6.9 k -> 6.5 k Adam steps/s): these GEMMs are bound by the shared-memory traffic of the 4x4 micro-tile (128 KB per
+  // 64 x 64 x 16 step) plus ~5 us of launch / prologue each, not by their serial k-steps, and every extra slice adds a
+  // partial tile of traffic.  MC_MLP_SPLIT_CTAS overrides the CTA target.
+  static const int split_ctas = getenv("MC_MLP_SPLIT_CTAS") ? atoi(getenv("MC_MLP_SPLIT_CTAS")) : 296;
+  if (!a_mc && tiles < 64 && tiles <= h->n_tickets && K >= 256) {
+    splits = std::min(cdiv(K, 64), std::max(1, split_ctas / tiles));
   }
   int kps = K;
   if (splits > 1) {
     kps = cdiv(cdiv(K, splits), 16) * 16;
     splits = cdiv(K, kps);
   }
-  dim3 grid(cdiv(M, 64), cdiv(N, 64), splits);
-  float* out = C;
   if (splits > 1) {
-    int rc = grow(&h->d_part, &h->cap_part, (int64_t)splits * M * N);
+    if (tiles > h->n_tickets) return fail(MC_ERR_UNSUPPORTED, "mlp_gemm: more output tiles than split-K tickets");
+    int rc = grow(&h->d_part[slot], &h->cap_part[slot], (int64_t)splits * M * N + (int64_t)splits * M);
     if (rc) return rc;
-    out = h->d_part;
   }
-#define MLP_GEMM_ARGS A, lda, B, ldb, out, splits > 1 ? N : ldc, M, N, K, kps, epi, bias, mask, ldmask, colsum
-  if (!a_mc && !b_nc) mlp_gemm_kernel<false, false><<<grid, 256, 0, st>>>(MLP_GEMM_ARGS);
-  else if (a_mc && b_nc) mlp_gemm_kernel<true, true><<<grid, 256, 0, st>>>(MLP_GEMM_ARGS);
-  else if (!a_mc && b_nc) mlp_gemm_kernel<false, true><<<grid, 256, 0, st>>>(MLP_GEMM_ARGS);
+  *p = MlpGemmP{A, lda, B, ldb, C, ldc, h->d_part[slot], h->d_tickets + slot * h->n_tickets, M, N, K, kps, splits, epi, bias, mask, ldmask, colsum,
+                cdiv(M, 64), cdiv(N, 64)};
+  return MC_OK;
+}
+
+int mlp_gemm(mc_mlp* h, bool a_mc, bool b_nc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M,
+             int N, int K, int epi, const float* bias, const float* mask, int ldmask, float* colsum, cudaStream_t st) {
+  MlpGemmP p;
+  int rc = mlp_gemm_plan(h, &p, a_mc, A, lda, B, ldb, C, ldc, M, N, K, epi, bias, mask, ldmask, colsum);
+  if (rc) return rc;
+  dim3 grid(p.gx, p.gy, p.splits);
+  if (!a_mc && !b_nc) mlp_gemm_kernel<false, false><<<grid, 256, 0, st>>>(p);
+  else if (a_mc && b_nc) mlp_gemm_kernel<true, true><<<grid, 256, 0, st>>>(p);
+  else if (!a_mc && b_nc) mlp_gemm_kernel<false, true><<<grid, 256, 0, st>>>(p);
   else return fail(MC_ERR_UNSUPPORTED, "mlp_gemm: layout combination");
-#undef MLP_GEMM_ARGS
   MC_CHECK_LAUNCH();
   h->launches++;
-  if (splits > 1) {
-    mlp_splitk_epilogue_kernel<<<cdiv((int64_t)M * N / 4, 256), 256, 0, st>>>(h->d_part, splits, C, M, N, epi, bias, mask, ldmask);
-    MC_CHECK_LAUNCH();
-    h->launches++;
-  }
+  return MC_OK;
+}
+
+// dW (A_MC, B_NC, bias gradient) and dX (B_NC, ReLU mask, split-K) of one layer in ONE launch
+int mlp_gemm_pair(mc_mlp* h, const MlpGemmP& dw, const MlpGemmP& dx, cudaStream_t st) {
+  mlp_gemm_pair_kernel<<<dw.gx * dw.gy * dw.splits + dx.gx * dx.gy * dx.splits, 256, 0, st>>>(dw, dx);
+  MC_CHECK_LAUNCH();
+  h->launches++;
   return MC_OK;
 }
 
@@ -262,6 +279,9 @@ int mc_mlp_create(int32_t n_layers, const int32_t* dims, const float* const* wei
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_ssq[0], h->n_blocks * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_ssq[1], h->n_blocks * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_loss, 2 * sizeof(double));
+  h->n_tickets = 256;  // split-K only runs on grids of at most this many tiles
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_tickets, (2 * h->n_tickets + 1) * sizeof(int));   // + the CE kernel's
+  if (e == cudaSuccess) e = cudaMemset(h->d_tickets, 0, (2 * h->n_tickets + 1) * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_p, flat.data(), off * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(h->d_m, 0, off * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(h->d_v, 0, off * sizeof(float));
@@ -289,7 +309,7 @@ int mc_mlp_destroy(mc_mlp* h) {
   for (float* p : h->d_act) if (p) cudaFree(p);
   for (float* p : h->d_delta) if (p) cudaFree(p);
   void* ptrs[] = {h->d_p, h->d_m, h->d_v, h->d_g, h->d_cw, h->d_ssq[0], h->d_ssq[1], h->d_loss,
-                  h->d_part, h->d_rowstat, h->d_xs, h->d_ys};
+                  h->d_part[0], h->d_part[1], h->d_rowstat, h->d_xs, h->d_ys, h->d_tickets};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return MC_OK;
@@ -340,22 +360,27 @@ int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, cons
       }
       // loss + un-normalised output delta + statistics
       mlp_ce_kernel<<<cdiv(rows, 8), 256, 0, st>>>(h->d_act[L - 1], Kp, K, ys + step_offsets[s], h->d_cw, h->d_delta[L - 1],
-                                                  h->d_rowstat, rows);
+                                                  h->d_rowstat, rows, h->d_g + h->n_flat, h->d_tickets + 2 * h->n_tickets);
       MC_CHECK_LAUNCH();
-      mlp_stats_kernel<<<1, 256, 0, st>>>(h->d_rowstat, rows, h->d_g + h->n_flat);
-      MC_CHECK_LAUNCH();
-      h->launches += 2;
+      h->launches++;
       // backward
       for (int i = L - 1; i >= 0; --i) {
         const int Ki = h->dims_p[i], Ni = h->dims_p[i + 1];
         const float* lin = i == 0 ? x : h->d_act[i - 1];
-        if ((rc = mlp_gemm(h, true, true, h->d_delta[i], Ni, lin, Ki, h->d_g + h->segs.w_off[i], Ki, Ni, Ki, rows,
-                           MLP_EPI_NONE, nullptr, nullptr, 0, h->d_g + h->segs.b_off[i], st)))
-          return rc;
-        if (i > 0 &&
-            (rc = mlp_gemm(h, false, true, h->d_delta[i], Ni, h->d_p + h->segs.w_off[i], Ki, h->d_delta[i - 1], Ki, rows, Ki,
-                           Ni, MLP_EPI_RELU_MASK, nullptr, h->d_act[i - 1], Ki, nullptr, st)))
-          return rc;
+        if (i == 0) {
+          if ((rc = mlp_gemm(h, true, true, h->d_delta[i], Ni, lin, Ki, h->d_g + h->segs.w_off[i], Ki, Ni, Ki, rows,
+                             MLP_EPI_NONE, nullptr, nullptr, 0, h->d_g + h->segs.b_off[i], st)))
+            return rc;
+        } else {
+          // dW_i and the delta of the layer below both read delta_i and nothing of each other: one launch
+          MlpGemmP dw, dx;
+          if ((rc = mlp_gemm_plan(h, &dw, true, h->d_delta[i], Ni, lin, Ki, h->d_g + h->segs.w_off[i], Ki, Ni, Ki, rows,
+                                  MLP_EPI_NONE, nullptr, nullptr, 0, h->d_g + h->segs.b_off[i])) ||
+              (rc = mlp_gemm_plan(h, &dx, false, h->d_delta[i], Ni, h->d_p + h->segs.w_off[i], Ki, h->d_delta[i - 1], Ki, rows,
+                                  Ki, Ni, MLP_EPI_RELU_MASK, nullptr, h->d_act[i - 1], Ki, nullptr, 1)) ||
+              (rc = mlp_gemm_pair(h, dw, dx, st)))
+            return rc;
+        }
       }
     } else {
       MC_CUDA(cudaMemsetAsync(h->d_g, 0, (h->n_flat + 4) * sizeof(float), st));

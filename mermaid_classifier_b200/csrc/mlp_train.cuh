@@ -26,20 +26,36 @@ enum { MLP_EPI_NONE = 0, MLP_EPI_BIAS_RELU = 1, MLP_EPI_BIAS = 2, MLP_EPI_RELU_M
 //   A_MC == false: A[m * lda + k]   (k contiguous)      A_MC == true: A[k * lda + m]
 //   B_NC == false: B[n * ldb + k]   (k contiguous)      B_NC == true: B[k * ldb + n]
 // Contiguous dimensions must be multiples of 4 (16-byte vector loads); the other one is free.
-// gridDim.z > 1 = split-K: slice z accumulates k in [z*k_per_split, (z+1)*k_per_split) and stores
-// the raw partial to C + z * M * ldc (the epilogue then runs in mlp_splitk_epilogue_kernel).
-// colsum (A_MC only): CTAs with blockIdx.y == 0 also write colsum[m] = sum_k A(m,k)  (bias gradient).
+// splits > 1 = split-K: slice z accumulates k in [z*k_per_split, (z+1)*k_per_split) and stores its raw partial to
+// part + z * M * N; the LAST slice of a tile to finish (a ticket per tile) sums the partials in slice order -- the same
+// fixed order whichever CTA happens to be last, so the result is deterministic -- and applies the epilogue.  (Round 1 ran
+// that reduction as a second launch per GEMM: seven ~4 us launches per Adam step.)
+// colsum (A_MC only): CTAs with by == 0 also write colsum[m] = sum_k A(m,k)  (bias gradient).
+struct MlpGemmP {
+  const float* A; int lda;
+  const float* B; int ldb;
+  float* C; int ldc;
+  float* part;            // split-K partials [splits][M][N], then [splits][M] partial column sums
+  int* tickets;           // one per output tile, zero between launches
+  int M, N, K, k_per_split, splits, epi;
+  const float* bias;
+  const float* mask; int ldmask;
+  float* colsum;
+  int gx, gy;             // tile grid
+};
+
 template <bool A_MC, bool B_NC>
-__global__ void __launch_bounds__(256)
-mlp_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                int M, int N, int K, int k_per_split, int epi, const float* __restrict__ bias,
-                const float* __restrict__ mask, int ldmask, float* __restrict__ colsum) {
+__device__ __forceinline__ void mlp_gemm_body(const MlpGemmP& p, const int bx, const int by, const int bz) {
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ int s_ticket;
+  const float* __restrict__ A = p.A;
+  const float* __restrict__ B = p.B;
+  const int lda = p.lda, ldb = p.ldb, M = p.M, N = p.N, K = p.K;
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+  const int m0 = bx * BM, n0 = by * BN;
+  const int kbeg = bz * p.k_per_split, kend = min(K, kbeg + p.k_per_split);
   const int ty = tid >> 4, tx = tid & 15;
   float acc[4][4];
 #pragma unroll
@@ -47,7 +63,7 @@ mlp_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float csum = 0.f;
-  const bool do_colsum = A_MC && colsum != nullptr && blockIdx.y == 0;
+  const bool do_colsum = A_MC && p.colsum != nullptr && by == 0;
 
   // global -> register loads of one k-tile (issued one tile ahead of the math: the loop is latency-bound otherwise, a
   // 64 x 64 x 200 tile spent ~1 us per 16-deep k step waiting for L2)
@@ -103,76 +119,112 @@ mlp_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
     }
   }
-  if (do_colsum && tid < BM && m0 + tid < M) colsum[m0 + tid] = csum;
-  const int n = n0 + tx * 4;
-  if (n >= N) return;
-  const bool split = gridDim.z > 1;
-  float* Cz = C + (split ? (int64_t)blockIdx.z * M * ldc : 0);
-  float bi[4] = {0.f, 0.f, 0.f, 0.f};
-  if (!split && (epi == MLP_EPI_BIAS_RELU || epi == MLP_EPI_BIAS)) {
-    const float4 t = *reinterpret_cast<const float4*>(bias + n);
-    bi[0] = t.x; bi[1] = t.y; bi[2] = t.z; bi[3] = t.w;
+  const int64_t MN = (int64_t)M * N;
+  if (do_colsum && tid < BM && m0 + tid < M) {
+    if (p.splits > 1) p.part[(int64_t)p.splits * MN + (int64_t)bz * M + m0 + tid] = csum;   // partial column sums after the tile partials
+    else p.colsum[m0 + tid] = csum;
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = acc[i][j];
-    if (!split) {
+  const int n = n0 + tx * 4;
+  const bool col_ok = n < N;
+  const bool split = p.splits > 1;
+  const int epi = p.epi;
+  auto epilogue_store = [&](int m, float (&v)[4]) {
+    if (epi == MLP_EPI_BIAS_RELU || epi == MLP_EPI_BIAS) {
+      const float4 t = *reinterpret_cast<const float4*>(p.bias + n);
+      v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
       if (epi == MLP_EPI_BIAS_RELU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j] + bi[j], 0.f);
-      } else if (epi == MLP_EPI_BIAS) {
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+    } else if (epi == MLP_EPI_RELU_MASK) {
+      const float4 mk = *reinterpret_cast<const float4*>(p.mask + (int64_t)m * p.ldmask + n);
+      v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
+      v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+    }
+    *reinterpret_cast<float4*>(p.C + (int64_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+  };
+  if (!split) {
+    if (col_ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] += bi[j];
-      } else if (epi == MLP_EPI_RELU_MASK) {
-        const float4 mk = *reinterpret_cast<const float4*>(mask + (int64_t)m * ldmask + n);
-        v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
-        v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m < M) {
+          float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+          epilogue_store(m, v);
+        }
       }
     }
-    *reinterpret_cast<float4*>(Cz + (int64_t)m * ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+    return;
   }
+  // split-K: raw partial of this slice, then the last slice of the tile reduces
+  if (col_ok) {
+    float* Cz = p.part + (int64_t)bz * MN;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m < M) *reinterpret_cast<float4*>(Cz + (int64_t)m * N + n) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(&p.tickets[by * p.gx + bx], 1);
+  __syncthreads();
+  if (s_ticket != p.splits - 1) return;
+  __threadfence();
+  if (col_ok) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m < M) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int z = 0; z < p.splits; ++z) {   // slice order: the sum does not depend on which slice finished last
+          const float4 q = __ldcg(reinterpret_cast<const float4*>(p.part + (int64_t)z * MN + (int64_t)m * N + n));
+          v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+        }
+        epilogue_store(m, v);
+      }
+    }
+  }
+  if (do_colsum && tid < BM && m0 + tid < M) {
+    float cs = 0.f;
+    for (int z = 0; z < p.splits; ++z) cs += __ldcg(p.part + (int64_t)p.splits * MN + (int64_t)z * M + m0 + tid);
+    p.colsum[m0 + tid] = cs;
+  }
+  if (tid == 0) p.tickets[by * p.gx + bx] = 0;   // ready for the next launch on this stream
 }
 
-// Sum the split-K partials in slice order (deterministic) and apply the epilogue.
-__global__ void mlp_splitk_epilogue_kernel(const float* __restrict__ part, int splits, float* __restrict__ C, int M, int N,
-                                           int epi, const float* __restrict__ bias, const float* __restrict__ mask, int ldmask) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)M * N / 4;
-  if (t >= total) return;
-  const int n = (int)((t * 4) % N);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < splits; ++z) {
-    const float4 p = *reinterpret_cast<const float4*>(part + (int64_t)z * M * N + t * 4);
-    s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+template <bool A_MC, bool B_NC>
+__global__ void __launch_bounds__(256) mlp_gemm_kernel(const MlpGemmP p) {
+  mlp_gemm_body<A_MC, B_NC>(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// The two GEMMs that consume one layer's delta -- dW_i = delta_i^T . input_i (+ bias gradient) and
+// dX = delta_i . W_i (ReLU mask, split-K) -- are independent: one launch, the CTAs of both side by side.
+__global__ void __launch_bounds__(256) mlp_gemm_pair_kernel(const MlpGemmP p0, const MlpGemmP p1) {
+  int b = blockIdx.x;
+  const int n0 = p0.gx * p0.gy * p0.splits;
+  if (b < n0) {
+    mlp_gemm_body<true, true>(p0, b % p0.gx, (b / p0.gx) % p0.gy, b / (p0.gx * p0.gy));
+  } else {
+    b -= n0;
+    mlp_gemm_body<false, true>(p1, b % p1.gx, (b / p1.gx) % p1.gy, b / (p1.gx * p1.gy));
   }
-  if (epi == MLP_EPI_BIAS_RELU || epi == MLP_EPI_BIAS) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + n);
-    s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
-    if (epi == MLP_EPI_BIAS_RELU) {
-      s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
-    }
-  } else if (epi == MLP_EPI_RELU_MASK) {
-    const int64_t m = (t * 4) / N;
-    const float4 mk = *reinterpret_cast<const float4*>(mask + m * ldmask + n);
-    s.x = mk.x > 0.f ? s.x : 0.f; s.y = mk.y > 0.f ? s.y : 0.f;
-    s.z = mk.z > 0.f ? s.z : 0.f; s.w = mk.w > 0.f ? s.w : 0.f;
-  }
-  *reinterpret_cast<float4*>(C + t * 4) = s;
 }
 
 // One warp per mini-batch row: log-softmax over the K real classes, un-normalised delta
 //   delta[r][k] = w_r * (softmax_k - [k == y_r])     (padded columns K..Kp-1 = 0)
 //   row_stat[r] = (w_r, w_r * -log p[y_r])
-__global__ void mlp_ce_kernel(const float* __restrict__ logits, int Kp, int K, const int32_t* __restrict__ y,
-                              const float* __restrict__ class_w, float* __restrict__ delta,
-                              float2* __restrict__ row_stat, int rows) {
+// The last CTA to finish (ticket) then reduces the row statistics in a fixed order into the 4 statistics floats of the
+// gradient buffer (round 1: a second, single-CTA launch).
+__device__ __forceinline__ void mlp_stats_reduce(const float2* __restrict__ row_stat, int rows, float* __restrict__ stats);
+
+__global__ void __launch_bounds__(256)
+mlp_ce_kernel(const float* __restrict__ logits, int Kp, int K, const int32_t* __restrict__ y,
+              const float* __restrict__ class_w, float* __restrict__ delta,
+              float2* __restrict__ row_stat, int rows, float* __restrict__ stats, int* __restrict__ ticket) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (r >= rows) return;
+  if (r < rows) {
   const float* x = logits + (int64_t)r * Kp;
   float mx = -INFINITY;
   for (int k = lane; k < K; k += 32) mx = fmaxf(mx, x[k]);
@@ -190,14 +242,24 @@ __global__ void mlp_ce_kernel(const float* __restrict__ logits, int Kp, int K, c
     d[k] = v;
   }
   if (lane == 0) row_stat[r] = make_float2(w, w * (lse - x[yr]));
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  mlp_stats_reduce(row_stat, rows, stats);
+  if (threadIdx.x == 0) *ticket = 0;
 }
 
-// Fixed-order reduction of the row statistics into the 4 statistics floats of the gradient buffer.
-__global__ void mlp_stats_kernel(const float2* __restrict__ row_stat, int rows, float* __restrict__ stats) {
+// Fixed-order reduction of the row statistics (256 threads): thread t sums rows t, t + 256, ..., then a tree over the threads.
+__device__ __forceinline__ void mlp_stats_reduce(const float2* __restrict__ row_stat, int rows, float* __restrict__ stats) {
   __shared__ float sw[256], sl[256];
   float w = 0.f, l = 0.f;
   for (int r = threadIdx.x; r < rows; r += 256) {
-    const float2 s = row_stat[r];
+    const float2 s = __ldcg(row_stat + r);
     w += s.x;
     l += s.y;
   }
