@@ -76,6 +76,7 @@ struct mc_mlp {
   std::vector<float*> d_act, d_delta;  // [L] each: outputs of layer i / gradient w.r.t. them
   float* d_part[2] = {nullptr, nullptr};   // split-K partials; slot 1 = the second GEMM of a paired launch
   int64_t cap_part[2] = {0, 0};
+  bool rl_attr_set = false;   // dynamic shared-memory attribute of mlp_rowlocal_kernel set on this handle's device
   int* d_tickets = nullptr;   // split-K tile tickets, n_tickets per slot (zero between launches)
   int n_tickets = 0;
   float2* d_rowstat = nullptr;
@@ -348,7 +349,70 @@ int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, cons
   for (int s = 0; s < n_steps; ++s) {
     const int rows = (int)(step_offsets[s + 1] - step_offsets[s]);
     const float* x = xs + step_offsets[s] * Dp;
-    if (rows > 0) {
+    // Experiment, off by default (MC_MLP_ROWLOCAL=1; MC_MLP_RL_R = rows per CTA): first-layer GEMM -> ONE launch for layers
+    // 1..L-1, the loss and every delta (mlp_rowlocal_kernel) -> one launch for all weight gradients: 4 launches per step
+    // instead of 10.  Measured at (500,300,100) / 500 classes / mini-batch 200: 6.0 k Adam steps/s (R = 2) against 7.1 k for
+    // the GEMM chain -- every CTA streams all 1.84 MB of the layer 1..L-1 weights from L2 (forward + backward), 184 MB per
+    // step at R = 2, and without the row-tiling of a GEMM that stream, not the launch count, is the bound.
+    static const bool no_rl = getenv("MC_MLP_ROWLOCAL") == nullptr;
+    static const int rl_r = getenv("MC_MLP_RL_R") ? atoi(getenv("MC_MLP_RL_R")) : 2;
+    int rl_width = 0, rl_maxw = 0;
+    for (int i = 1; i <= L; ++i) {
+      rl_width += h->dims_p[i];
+      rl_maxw = std::max(rl_maxw, h->dims_p[i]);
+    }
+    const size_t rl_smem = (size_t)rl_r * (rl_width + 2 * rl_maxw) * sizeof(float);
+    const bool use_rl = !no_rl && L >= 2 && L <= MLP_RL_MAX_LAYERS && rows > 0 && rows <= 4096 && rl_smem <= 200 * 1024 &&
+                        (rl_r == 2 || rl_r == 4 || rl_r == 8);
+    if (use_rl) {
+      const int N0 = h->dims_p[1];
+      if ((rc = mlp_gemm(h, false, false, x, Dp, h->d_p + h->segs.w_off[0], Dp, h->d_act[0], N0, rows, N0, Dp, MLP_EPI_BIAS_RELU,
+                         h->d_p + h->segs.b_off[0], nullptr, 0, nullptr, st)))
+        return rc;
+      MlpRowLocalP rp{};
+      rp.L = L; rp.K = K; rp.rows = rows;
+      for (int i = 0; i <= L; ++i) rp.dims_p[i] = h->dims_p[i];
+      for (int i = 0; i < L; ++i) {
+        rp.w_off[i] = h->segs.w_off[i];
+        rp.b_off[i] = h->segs.b_off[i];
+        rp.act[i] = h->d_act[i];
+        rp.delta[i] = h->d_delta[i];
+      }
+      rp.params = h->d_p;
+      rp.act0 = h->d_act[0];
+      rp.y = ys + step_offsets[s];
+      rp.class_w = h->d_cw;
+      rp.row_stat = h->d_rowstat;
+      rp.stats = h->d_g + h->n_flat;
+      rp.ticket = h->d_tickets + 2 * h->n_tickets;
+      if (!h->rl_attr_set) {
+        MC_CUDA(cudaFuncSetAttribute(mlp_rowlocal_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MC_CUDA(cudaFuncSetAttribute(mlp_rowlocal_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MC_CUDA(cudaFuncSetAttribute(mlp_rowlocal_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        h->rl_attr_set = true;
+      }
+      if (rl_r == 2) mlp_rowlocal_kernel<2><<<cdiv(rows, 2), 512, rl_smem, st>>>(rp);
+      else if (rl_r == 4) mlp_rowlocal_kernel<4><<<cdiv(rows, 4), 512, rl_smem, st>>>(rp);
+      else mlp_rowlocal_kernel<8><<<cdiv(rows, 8), 512, rl_smem, st>>>(rp);
+      MC_CHECK_LAUNCH();
+      h->launches++;
+      MlpGemmMulti mp{};
+      mp.n = L;
+      int first = 0;
+      for (int i = 0; i < L; ++i) {
+        const int Ki = h->dims_p[i], Ni = h->dims_p[i + 1];
+        const float* lin = i == 0 ? x : h->d_act[i - 1];
+        if ((rc = mlp_gemm_plan(h, &mp.p[i], true, h->d_delta[i], Ni, lin, Ki, h->d_g + h->segs.w_off[i], Ki, Ni, Ki, rows,
+                                MLP_EPI_NONE, nullptr, nullptr, 0, h->d_g + h->segs.b_off[i])))
+          return rc;
+        mp.first[i] = first;
+        first += mp.p[i].gx * mp.p[i].gy * mp.p[i].splits;
+      }
+      mp.first[L] = first;
+      mlp_gemm_multi_kernel<<<first, 256, 0, st>>>(mp);
+      MC_CHECK_LAUNCH();
+      h->launches++;
+    } else if (rows > 0) {
       // forward
       const float* in = x;
       for (int i = 0; i < L; ++i) {

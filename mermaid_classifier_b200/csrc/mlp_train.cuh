@@ -254,7 +254,34 @@ mlp_ce_kernel(const float* __restrict__ logits, int Kp, int K, const int32_t* __
   if (threadIdx.x == 0) *ticket = 0;
 }
 
-// Fixed-order reduction of the row statistics (256 threads): thread t sums rows t, t + 256, ..., then a tree over the threads.
+// Fixed-order reduction of the row statistics by the first 256 threads of the CTA: thread t sums rows t, t + 256, ..., then a
+// tree over the threads.  (Callers with more than 256 threads pass only those through; the barriers inside are named so
+// that the other warps need not take part.)
+__device__ __forceinline__ void mlp_stats_reduce_n(const float2* __restrict__ row_stat, int rows, float* __restrict__ stats, int nthreads) {
+  __shared__ float sw[256], sl[256];
+  float w = 0.f, l = 0.f;
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    const float2 s = __ldcg(row_stat + r);
+    w += s.x;
+    l += s.y;
+  }
+  sw[threadIdx.x] = w;
+  sl[threadIdx.x] = l;
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sw[threadIdx.x] += sw[threadIdx.x + o];
+      sl[threadIdx.x] += sl[threadIdx.x + o];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    stats[0] = sw[0];
+    stats[1] = sl[0];
+    stats[2] = (float)rows;
+    stats[3] = 0.f;
+  }
+}
 __device__ __forceinline__ void mlp_stats_reduce(const float2* __restrict__ row_stat, int rows, float* __restrict__ stats) {
   __shared__ float sw[256], sl[256];
   float w = 0.f, l = 0.f;
@@ -279,6 +306,202 @@ __device__ __forceinline__ void mlp_stats_reduce(const float2* __restrict__ row_
     stats[2] = (float)rows;
     stats[3] = 0.f;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-local middle of the step.  At mini-batch 200 everything between the first layer's GEMM and the weight-gradient
+// GEMMs is a chain of small dependent products per ROW: layers 1..L-1 forward, softmax / cross-entropy, and the deltas
+// back down to layer 0.  As GEMM launches that chain was 4 + 3 launches of 6-17 us each (grids of 8-60 CTAs, latency- and
+// launch-bound); here one CTA carries R rows through the whole chain with the activations in shared memory and the
+// weights streamed from L2, and writes what the weight-gradient GEMMs need (activations 1..L-2, every delta) plus the
+// row statistics.  Forward: a warp per output neuron, lanes split the reduction (coalesced weight rows).  Backward: a
+// thread per input neuron, loop over the outputs (coalesced again, no reduction).
+constexpr int MLP_RL_MAX_LAYERS = 8;
+struct MlpRowLocalP {
+  int L, K, rows;
+  int dims_p[MLP_RL_MAX_LAYERS + 1];
+  int64_t w_off[MLP_RL_MAX_LAYERS], b_off[MLP_RL_MAX_LAYERS];
+  const float* params;
+  const float* act0;                  // [rows][dims_p[1]]: layer 0 output (bias + ReLU applied)
+  float* act[MLP_RL_MAX_LAYERS];      // act[i], i = 1..L-2: written (input of the weight gradient of layer i + 1)
+  float* delta[MLP_RL_MAX_LAYERS];    // delta[i], i = 0..L-1: written
+  const int32_t* y;
+  const float* class_w;
+  float2* row_stat;
+  float* stats;
+  int* ticket;
+};
+
+template <int R>
+__global__ void __launch_bounds__(512) mlp_rowlocal_kernel(const MlpRowLocalP p) {
+  extern __shared__ float rl_smem[];
+  // h[i] = activations of layer i (i = 0..L-1, the last one = logits), then two delta buffers of the widest layer
+  float* h[MLP_RL_MAX_LAYERS];
+  int maxw = 0;
+  {
+    float* q = rl_smem;
+    for (int i = 0; i < p.L; ++i) {
+      h[i] = q;
+      q += R * p.dims_p[i + 1];
+      maxw = max(maxw, p.dims_p[i + 1]);
+    }
+    h[p.L] = q;   // (unused slot keeps the indexing below simple)
+  }
+  float* dbuf[2] = {h[p.L], h[p.L] + R * maxw};
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int r0 = blockIdx.x * R;
+  const int nr = min(R, p.rows - r0);
+
+  // layer-0 activations of this CTA's rows
+  {
+    const int w0 = p.dims_p[1];
+    for (int t = tid; t < R * w0; t += blockDim.x) {
+      const int r = t / w0, k = t - r * w0;
+      h[0][t] = r < nr ? p.act0[(int64_t)(r0 + r) * w0 + k] : 0.f;
+    }
+  }
+  __syncthreads();
+  // forward, layers 1 .. L-1
+  for (int i = 1; i < p.L; ++i) {
+    const int Ki = p.dims_p[i], Ni = p.dims_p[i + 1];
+    const float* __restrict__ W = p.params + p.w_off[i];
+    const float* __restrict__ bias = p.params + p.b_off[i];
+    const float* hin = h[i - 1];
+    float* hout = h[i];
+    const bool relu = i < p.L - 1;
+    // NB output neurons per warp at a time: NB independent weight rows in flight per lane (the loop is bound by the L2
+    // latency of the weight stream, one row at a time left the SM's ~64 B/clk L2 port mostly idle)
+    constexpr int NB = 4;
+    for (int n0 = warp * NB; n0 < Ni; n0 += nwarps * NB) {
+      float acc[NB][R];
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
+#pragma unroll 2
+      for (int k = lane; k < Ki; k += 32) {
+        float w[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) w[j] = n0 + j < Ni ? W[(int64_t)(n0 + j) * Ki + k] : 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float hv = hin[r * Ki + k];
+#pragma unroll
+          for (int j = 0; j < NB; ++j) acc[j][r] = fmaf(w[j], hv, acc[j][r]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int n = n0 + j;
+        if (n < Ni) {   // warp-uniform
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[j][r] = warp_sum(acc[j][r]);
+          const float b = bias[n];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float v = acc[j][r] + b;
+            if (relu) v = fmaxf(v, 0.f);
+            if (lane == r) {
+              hout[r * Ni + n] = v;
+              if (relu && r < nr) p.act[i][(int64_t)(r0 + r) * Ni + n] = v;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // softmax / cross-entropy of the rows: warp r handles row r (as mlp_ce_kernel)
+  {
+    const int Kp = p.dims_p[p.L], K = p.K;
+    float* d = dbuf[0];
+    for (int r = warp; r < R; r += nwarps) {
+      const float* x = h[p.L - 1] + r * Kp;
+      if (r < nr) {
+        float mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, x[k]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int k = lane; k < K; k += 32) sum += expf(x[k] - mx);
+        sum = warp_sum(sum);
+        const float lse = mx + logf(sum);
+        const int yr = p.y[r0 + r];
+        const float w = p.class_w ? p.class_w[yr] : 1.f;
+        float* dg = p.delta[p.L - 1] + (int64_t)(r0 + r) * Kp;
+        for (int k = lane; k < Kp; k += 32) {
+          float v = 0.f;
+          if (k < K) v = w * (expf(x[k] - lse) - (k == yr ? 1.f : 0.f));
+          d[r * Kp + k] = v;
+          dg[k] = v;
+        }
+        if (lane == 0) p.row_stat[r0 + r] = make_float2(w, w * (lse - x[yr]));
+      } else {
+        for (int k = lane; k < Kp; k += 32) d[r * Kp + k] = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  // deltas down to layer 0: delta[i-1][r][k] = (act[i-1][r][k] > 0) * sum_n delta[i][r][n] W_i[n][k]
+  for (int i = p.L - 1; i >= 1; --i) {
+    const int Ki = p.dims_p[i], Ni = p.dims_p[i + 1];
+    const float* __restrict__ W = p.params + p.w_off[i];
+    const float* din = dbuf[(p.L - 1 - i) & 1];
+    float* dout = dbuf[(p.L - i) & 1];
+    const float* hmask = h[i - 1];
+    for (int k = tid; k < Ki; k += blockDim.x) {
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      // 16 weight loads in flight per thread (Ni is a multiple of 4; the tail runs one by one)
+      int n = 0;
+      for (; n + 16 <= Ni; n += 16) {
+        float w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = W[(int64_t)(n + j) * Ki + k];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fmaf(din[r * Ni + n + j], w[j], acc[r]);
+      }
+      for (; n < Ni; ++n) {
+        const float w = W[(int64_t)n * Ki + k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fmaf(din[r * Ni + n], w, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float v = hmask[r * Ki + k] > 0.f ? acc[r] : 0.f;
+        dout[r * Ki + k] = v;
+        if (r < nr) p.delta[i - 1][(int64_t)(r0 + r) * Ki + k] = v;
+      }
+    }
+    __syncthreads();
+  }
+  // the last CTA reduces the row statistics (fixed order)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(p.ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 256) mlp_stats_reduce_n(p.row_stat, p.rows, p.stats, 256);
+  if (tid == 0) *p.ticket = 0;
+}
+
+// the weight-gradient GEMMs of ALL layers in one launch (they only depend on the deltas and activations written above)
+constexpr int MLP_MULTI_MAX = MLP_RL_MAX_LAYERS;
+struct MlpGemmMulti {
+  int n;
+  int first[MLP_MULTI_MAX + 1];   // first CTA of each problem
+  MlpGemmP p[MLP_MULTI_MAX];
+};
+__global__ void __launch_bounds__(256) mlp_gemm_multi_kernel(const MlpGemmMulti mp) {
+  int q = 0;
+  while (q + 1 < mp.n && (int)blockIdx.x >= mp.first[q + 1]) ++q;
+  const MlpGemmP& p = mp.p[q];
+  const int b = blockIdx.x - mp.first[q];
+  mlp_gemm_body<true, true>(p, b % p.gx, (b / p.gx) % p.gy, b / (p.gx * p.gy));
 }
 
 struct MlpSegs {
