@@ -164,3 +164,34 @@ def test_errors_and_sklearn_protocol():
         TorchMLPClassifier(class_weight={0: 1.0}).partial_fit(X, y, classes=[0, 1, 2])
     f = TorchMLPClassifier(hidden_layer_sizes=(16,), random_state=0, max_iter=5).fit(X, y)
     assert 1 <= f.n_iter_ <= 5 and len(f.loss_curve_) == f.n_iter_
+
+
+def test_rowlocal_experiment_path_matches_default():
+    """The opt-in row-local middle of the Adam step (``MC_MLP_ROWLOCAL=1``, read once per process -> a subprocess) walks
+    the same trajectory as the default GEMM chain up to fp32 summation order, class weights and ragged tail included."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import json, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from mermaid_classifier_b200.torch_classifier import TorchMLPClassifier\n"
+        "rng = np.random.RandomState(5); c = rng.randn(7, 48) * 3.0; y = rng.randint(0, 7, size=930)\n"
+        "X = (c[y] + rng.randn(930, 48) * 1.3).astype(np.float32)\n"
+        "cw = {k: 0.5 + 0.25 * k for k in range(7)}\n"
+        "clf = TorchMLPClassifier(hidden_layer_sizes=(24, 16, 12), learning_rate_init=1e-3, random_state=0, class_weight=cw)\n"
+        "for _ in range(3): clf.partial_fit(X, y, classes=list(range(7)))\n"
+        "print(json.dumps({'loss': clf.loss_curve_, 'p': clf.predict_proba(X[:20]).tolist()}))\n"
+    ) % str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    outs = []
+    for flag in (None, "1"):
+        env = {k: v for k, v in os.environ.items() if k != "MC_MLP_ROWLOCAL"}
+        if flag:
+            env["MC_MLP_ROWLOCAL"] = flag
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    np.testing.assert_allclose(outs[1]["loss"], outs[0]["loss"], rtol=2e-5)
+    np.testing.assert_allclose(np.asarray(outs[1]["p"]), np.asarray(outs[0]["p"]), atol=2e-5)
