@@ -101,6 +101,8 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
     ptx::prefetch_tmap(&tmIn);
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();   // the input map (and the output buffer's previous readers) belong to earlier kernels
 
   const bool producer = tid >= (int)blockDim.x - 32;
   float psum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -384,6 +386,8 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
     ptx::prefetch_tmap(&tmIn);
   }
   __syncthreads();
+  pdl_trigger();
+  if (tid >= cons_threads) pdl_wait();   // the producer waits here; the consumers load their weights (constants) first
 
   if (tid >= cons_threads) {
     // ================================ TMA producer ================================
@@ -427,6 +431,7 @@ dw_reg_kernel(const __grid_constant__ CUtensorMap tmIn, const DwRegArgs a) {
   int s = 0;
   uint32_t ph = 0;
   int pbuf = 0;
+  pdl_wait();
   for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
     T* out_n = (T*)a.out + ((int64_t)n * HOUT * HOUT + ox0) * C + c;
     float2 acc[NL][TW];
@@ -615,7 +620,7 @@ inline int dw_tma_launch(DwLayer& l, const CUtensorMap& tm, const DwArgs& a, int
     static std::atomic<unsigned long long> attr_mask{0};                                                              \
     if (first_use_on_device(attr_mask))                                                                               \
       MC_CUDA(cudaFuncSetAttribute(dw_tma_kernel<T, KK, SS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); \
-    dw_tma_kernel<T, KK, SS, TT><<<grid, block, l.smem, st>>>(tm, a);                                                 \
+    MC_CUDA(launch_pdl(PDL_DW, dw_tma_kernel<T, KK, SS, TT>, grid, block, l.smem, st, tm, a));                               \
     MC_CHECK_LAUNCH();                                                                                                \
     return MC_OK;                                                                                                     \
   }
@@ -633,7 +638,7 @@ inline int dw_reg_launch_shape(DwLayer& l, const CUtensorMap& tm, const DwRegArg
   static std::atomic<unsigned long long> attr_mask{0};
   if (first_use_on_device(attr_mask))
     MC_CUDA(cudaFuncSetAttribute(dw_reg_kernel<T, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-  dw_reg_kernel<T, SHAPE><<<grid, block, l.smem, st>>>(tm, a);
+  MC_CUDA(launch_pdl(PDL_DWREG, dw_reg_kernel<T, SHAPE>, grid, block, l.smem, st, tm, a));
   MC_CHECK_LAUNCH();
   return MC_OK;
 }

@@ -21,6 +21,8 @@ se_kernel(const float* __restrict__ pool_partial, int nbands, float inv_hw, cons
   const int64_t n0 = (int64_t)blockIdx.x * P;
   const int np = (int)min((int64_t)P, (int64_t)nb - n0);   // patches of this CTA (the last one may hold fewer)
   const int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();   // the pool partials come from the depthwise kernel right before
   for (int c = tid; c < C; c += 256) {
 #pragma unroll
     for (int q = 0; q < P; ++q) {
@@ -78,9 +80,9 @@ inline void se_launch(const float* pool_partial, int nbands, float inv_hw, const
   // kernel is bound by the latency of its dependent loops at ~7 resident CTAs per SM, not by the L2 re-reads
   const int P = env_p ? env_p : 1;
   const size_t smem = (size_t)P * (C + Cse) * sizeof(float);
-  if (P >= 4) se_kernel<4><<<cdiv(nb, 4), 256, smem, st>>>(pool_partial, nbands, inv_hw, w1, b1, w2, b2, gate, gate_h, C, Cse, nb);
-  else if (P == 2) se_kernel<2><<<cdiv(nb, 2), 256, smem, st>>>(pool_partial, nbands, inv_hw, w1, b1, w2, b2, gate, gate_h, C, Cse, nb);
-  else se_kernel<1><<<nb, 256, smem, st>>>(pool_partial, nbands, inv_hw, w1, b1, w2, b2, gate, gate_h, C, Cse, nb);
+  if (P >= 4) launch_pdl(PDL_SE, se_kernel<4>, dim3(cdiv(nb, 4)), dim3(256), smem, st, pool_partial, nbands, inv_hw, w1, b1, w2, b2, gate, gate_h, C, Cse, nb);
+  else if (P == 2) launch_pdl(PDL_SE, se_kernel<2>, dim3(cdiv(nb, 2)), dim3(256), smem, st, pool_partial, nbands, inv_hw, w1, b1, w2, b2, gate, gate_h, C, Cse, nb);
+  else launch_pdl(PDL_SE, se_kernel<1>, dim3(nb), dim3(256), smem, st, pool_partial, nbands, inv_hw, w1, b1, w2, b2, gate, gate_h, C, Cse, nb);
 }
 
 // Global average pool of the head conv output: feats[n][c] = mean_p x[n][p][c] (fp32 out).

@@ -179,6 +179,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch (common.cuh): the producer loads the weight slice (constants) before it waits
+  pdl_trigger();
+  if (warp != WARP_TMA) pdl_wait();
 
   if (warp == WARP_TMA) {
     // ================================ TMA producer ================================
@@ -188,6 +191,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         ptx::tma_load_2d(w_s + (size_t)(kc * NOP) * W_TILE, &tmW, w_bar, kc * KC, cb0);
         if (F32) ptx::tma_load_2d(w_s + (size_t)(kc * NOP + 1) * W_TILE, &tmWlo, w_bar, kc * KC, cb0);
       }
+      pdl_wait();
       int hs = 0;
       uint32_t hph = 0;
       for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
@@ -576,7 +580,7 @@ inline int fused_launch_shape(FusedLayer& l, int slot, const FusedArgs& a, cudaS
       MC_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<T, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh.smem));
     const int per_patch = sh.cz * sh.nbands;
     const int gz = std::max(1, std::min(a.nb, 3000 / per_patch));
-    mbconv_fused_kernel<T, SHAPE><<<dim3(sh.cz, sh.nbands, gz), FUSED_THREADS, sh.smem, st>>>(l.tmX[slot], l.tmW, l.tmWlo, a);
+    MC_CUDA(launch_pdl(PDL_FUSED, mbconv_fused_kernel<T, SHAPE>, dim3(sh.cz, sh.nbands, gz), dim3(FUSED_THREADS), sh.smem, st, l.tmX[slot], l.tmW, l.tmWlo, a));
     MC_CHECK_LAUNCH();
     return MC_OK;
   }

@@ -501,6 +501,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above is independent of the previous kernel.  The producer still loads the
+  // resident weights (constants) before it waits; every other role waits here.
+  pdl_trigger();
+  if (warp != WARP_TMA) pdl_wait();
 
   if (warp == WARP_TMA) {
     // ================================ TMA producer ================================
@@ -520,6 +524,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (Cfg::TF32) ptx::tma_load_2d(wt + W_BYTES, &tmWlo, wbar, kc * Cfg::KC, nb_ * p.BN);
           }
       }
+      pdl_wait();   // activations, gate: written by the previous kernels
       long long w_empty = 0;
       const long long t_begin = ptx::tc_clock();
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -1520,35 +1525,35 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
-    pw_tc_kernel<float, false, true, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<float, false, true, false, true>, dim3(grid), dim3(tc_threads<false>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   } else if (plan->relu_variant) {
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
-    pw_tc_kernel<float, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<float, false, true>, dim3(grid), dim3(tc_threads<false>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   } else if (f32 && !gated && ts) {
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
-    pw_tc_kernel<float, false, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<float, false, false, false, true>, dim3(grid), dim3(tc_threads<false>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   } else if (f32 && gated && ts) {
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
-    pw_tc_kernel<float, true, false, false, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<float, true, false, false, true>, dim3(grid), dim3(tc_threads<true>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   } else if (!f32 && gated && ts) {
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<__nv_bfloat16, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
-    pw_tc_kernel<__nv_bfloat16, true, false, false, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<__nv_bfloat16, true, false, false, true>, dim3(grid), dim3(tc_threads<true>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   } else if (f32 && gated)
-    pw_tc_kernel<float, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<float, true>, dim3(grid), dim3(tc_threads<true>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   else if (f32)
-    pw_tc_kernel<float, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<float, false>, dim3(grid), dim3(tc_threads<false>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   else if (gated)
-    pw_tc_kernel<__nv_bfloat16, true><<<grid, tc_threads<true>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<__nv_bfloat16, true>, dim3(grid), dim3(tc_threads<true>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   else
-    pw_tc_kernel<__nv_bfloat16, false><<<grid, tc_threads<false>(), smem, st>>>(l.tmA[slot], l.tmW, l.tmWlo, tmG, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<__nv_bfloat16, false>, dim3(grid), dim3(tc_threads<false>()), smem, st, l.tmA[slot], l.tmW, l.tmWlo, tmG, a));
   MC_CHECK_LAUNCH();
   if (a.dbg) {
     long long d[32];
@@ -1607,9 +1612,9 @@ inline int pw_tc_run_pool(PwTcPlan* plan, int id, const void* A, int nb, float* 
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(pw_tc_kernel<float, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET));
-    pw_tc_kernel<float, false, false, true, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
-  } else if (f32) pw_tc_kernel<float, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
-  else pw_tc_kernel<__nv_bfloat16, false, false, true><<<grid, tc_threads<false>(), smem, st>>>(l.tmApool, l.tmW, l.tmWlo, l.tmW, a);
+    MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<float, false, false, true, true>, dim3(grid), dim3(tc_threads<false>()), smem, st, l.tmApool, l.tmW, l.tmWlo, l.tmW, a));
+  } else if (f32) MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<float, false, false, true>, dim3(grid), dim3(tc_threads<false>()), smem, st, l.tmApool, l.tmW, l.tmWlo, l.tmW, a));
+  else MC_CUDA(launch_pdl(PDL_GEMM, pw_tc_kernel<__nv_bfloat16, false, false, true>, dim3(grid), dim3(tc_threads<false>()), smem, st, l.tmApool, l.tmW, l.tmWlo, l.tmW, a));
   MC_CHECK_LAUNCH();
   return MC_OK;
 }

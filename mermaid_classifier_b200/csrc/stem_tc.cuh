@@ -93,6 +93,8 @@ stem_tc_kernel(const mc_image* __restrict__ images, const mc_point* __restrict__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();   // programmatic dependent launch (common.cuh): weights, scale and bias above are constants
+  pdl_wait();      // the output buffer may still be read by the previous sub-batch's kernels
 
   if (warp < STEM_BUILD_WARPS) {
     // ================================== builders ====================================
@@ -428,7 +430,7 @@ inline int stem_tc_launch(const StemTcPlan& p, const mc_image* d_images, const m
   a.out = out;
   a.nb = nb;
   const int items = nb * (112 / STEM_BAND);
-  stem_tc_kernel<T><<<std::min(items, p.num_sms), STEM_TC_THREADS, STEM_SMEM, st>>>(d_images, d_points, a);
+  MC_CUDA(launch_pdl(PDL_STEM, stem_tc_kernel<T>, dim3(std::min(items, p.num_sms)), dim3(STEM_TC_THREADS), STEM_SMEM, st, d_images, d_points, a));
   MC_CHECK_LAUNCH();
   return MC_OK;
 }
