@@ -212,7 +212,10 @@ inline bool first_use_on_device(std::atomic<unsigned long long>& mask) {
 // with the GEMM / SE / stem / fused families; the MLP training step gets 3x SLOWER (2.3 k for 6.7 k Adam steps/s: ten 5-25 us
 // kernels per step, the attributed launches cost more host time than the step has).  And with dw_reg_kernel enabled the
 // bit-reproducibility test (the same patches in reversed order, test_full_size_sub_batch_properties) FAILS, every time,
-// although every access of that kernel sits behind its wait -- unexplained, so nothing is enabled by default.
+// although every access of that kernel sits behind its wait.  Narrowed down: it only fails when the predecessor GEMM runs with
+// the per-n-block weight residency, i.e. on a grid of 144-147 CTAs that leaves SMs idle, so that the depthwise CTAs are
+// resident (and waiting) from the start of the GEMM instead of from its tail; waiting in every thread, __threadfence and
+// fence.proxy.async after the wait change nothing.  Unexplained, so nothing is enabled by default.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
