@@ -53,9 +53,10 @@ B0 = [  # (k, stride, expand, c_in, c_out, h_in)
 ]
 
 
-def fused_blocks() -> int:
-    """Bit mask of the MBConv blocks whose expand + depthwise run as ONE kernel (library default: b1; MC_FUSE_MASK)."""
-    return int(os.environ.get("MC_FUSE_MASK", "2"), 16)
+def fused_blocks(e: int) -> int:
+    """Bit mask of the MBConv blocks whose expand + depthwise run as ONE kernel: the library's defaults (csrc/api.cu
+    MC_FUSE_DEFAULT_FP32 = b1-b3 in fp32 mode, MC_FUSE_DEFAULT = b1 in bf16 mode) unless MC_FUSE_MASK overrides them."""
+    return int(os.environ.get("MC_FUSE_MASK", "e" if e == 4 else "2"), 16)
 
 
 def layer_bytes(e: int) -> dict[int, tuple[str, float]]:
@@ -66,7 +67,7 @@ def layer_bytes(e: int) -> dict[int, tuple[str, float]]:
     for b, (k, s, ex, ci, co, h) in enumerate(B0):
         ho = (h + s - 1) // s
         cm = ci * ex
-        if ex != 1 and (fused_blocks() >> b) & 1:
+        if ex != 1 and (fused_blocks(e) >> b) & 1:
             out[2 + 4 * b] = (f"b{b}.expand+depthwise(fused)", h * h * (ci + cm) * e + (h * h + ho * ho) * cm * e)
         else:
             if ex != 1:
@@ -136,8 +137,8 @@ class ClockSampler:
 
 
 # layer id -> capture name in profiles/r02_kernels_<mode>.csv (tools/ncu_capture.sh)
-NCU_CAPTURE_OF_LAYER = {0: "stem", 6: "fused_b1", 2: "dw_b0", 18: "dw_b4", 38: "dw_b9", 9: "exp_b2", 12: "proj_b2", 64: "proj_b15",
-                        65: "head_pool"}
+NCU_CAPTURE_OF_LAYER = {0: "stem", 6: "fused_b1", 10: "fused_b2", 2: "dw_b0", 18: "dw_b4", 38: "dw_b9", 17: "exp_b4", 37: "exp_b9",
+                        12: "proj_b2", 52: "proj_b12", 64: "proj_b15", 65: "head_pool"}
 PROFILE_TAG = "r02"
 
 

@@ -27,6 +27,13 @@ using namespace mc;
 #define MC_FUSE_DEFAULT 0x2u   // blocks fused by default (bit b = block b): b1 (measured -28 % fp32 / -33 % bf16 against expand + depthwise);
                                // b2 / b3 measure equal or slower fused (stride-1 consumers are the bound), b4 does not fit in fp32
 #endif
+#ifndef MC_FUSE_DEFAULT_FP32
+// fp32 mode runs into the board's power cap (~1 kW, SM clock 1.72-1.75 GHz): with b2 and b3 fused as well the step moves
+// 4.2 MB less per patch through HBM, the clock settles at 1.81-1.86 GHz and the whole step is 1.3-1.5 % faster (76.4 ->
+// 77.5 k patches/s, interleaved runs on one box) although the two fused kernels are no faster than the pairs they replace.
+// bf16 mode is not power-capped (1.965 GHz either way) and keeps b1 only.
+#define MC_FUSE_DEFAULT_FP32 0xEu
+#endif
 
 namespace {
 
@@ -577,7 +584,7 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
   if (const char* env = getenv("MC_TC_MASK")) tc_mask = strtoull(env, nullptr, 16);
   // MC_FUSE_MASK (hex, bit b = block b): which MBConv blocks run expand + depthwise as one kernel (mbconv_fused.cuh)
   h->no_pool_fusion = getenv("MC_NO_POOL_FUSION") != nullptr;
-  h->fuse_mask = MC_FUSE_DEFAULT;
+  h->fuse_mask = mode == MC_MODE_FP32 ? MC_FUSE_DEFAULT_FP32 : MC_FUSE_DEFAULT;
   if (const char* env = getenv("MC_FUSE_MASK")) h->fuse_mask = (unsigned)strtoul(env, nullptr, 16);
   if ((rc = pw_tc_build(&h->tc, h->net, params, h->d_params, mode, max_batch, device, (unsigned)(tc_mask & 0xffffffffu),
                         (unsigned)(tc_mask >> 32)))) {
