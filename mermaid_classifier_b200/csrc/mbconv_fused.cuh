@@ -76,7 +76,17 @@ __host__ __device__ constexpr FusedShape fused_make_shape(int K, int S, int Cin,
   // x tiles: a ring of NH stages filled by TMA (deep enough to cover the L2 / HBM latency), plus -- fp32 mode -- two
   // stages of the TF32 lo operand written by the transform warps
   d.nh = d.kchunks == 1 ? 4 : 3;
-  d.smem = 1024 + d.w_bytes + (d.nh + (es == 4 ? 2 : 0)) * d.a_stage_bytes + d.stages * d.row_bytes + (2 * d.pt + 1) * d.CB * 4 + 512;
+  const int other = 1024 + d.w_bytes + (d.nh + (es == 4 ? 2 : 0)) * d.a_stage_bytes + (2 * d.pt + 1) * d.CB * 4 + 512;
+#ifdef MC_FUSED_DEEP_RING
+  // experiment (-DMC_FUSED_DEEP_RING): as many ring rows as fit.  Measured: b1 / b3 unchanged, b2 8 % SLOWER (12 rows for 6):
+  // ring depth is not what the fused kernels wait for
+  {
+    int fit = (227 * 1024 - other) / d.row_bytes;
+    if (fit > FUSED_MAX_STAGES) fit = FUSED_MAX_STAGES;
+    if (fit > d.stages) d.stages = fit;
+  }
+#endif
+  d.smem = other + d.stages * d.row_bytes;
   return d;
 }
 
