@@ -1016,6 +1016,7 @@ int64_t mc_head_launches(const mc_head* h) { return h ? h->launches : 0; }
 }  // extern "C"
 
 #include "host_pipe.inl"
+#include "jpeg_exact.inl"
 #include "jpeg_api.inl"
 #include "mlp_api.inl"
 #include "calib_api.inl"

@@ -64,6 +64,7 @@ struct mc_jpeg {
   int device = 0;
   nvjpegHandle_t handle = nullptr;
   nvjpegJpegState_t state = nullptr;
+  JpxScratch jpx;   // mc_jpeg_decode_exact
 };
 
 extern "C" {
@@ -98,6 +99,7 @@ int mc_jpeg_destroy(mc_jpeg* d) {
     if (d->state) api->state_destroy(d->state);
     if (d->handle) api->destroy(d->handle);
   }
+  jpx_free(&d->jpx);
   delete d;
   return MC_OK;
 }
@@ -133,6 +135,51 @@ int mc_jpeg_decode(mc_jpeg* d, const uint8_t* data, int64_t len, uint8_t* rgb_de
   // NVJPEG_OUTPUT_RGBI: interleaved RGB; a grayscale stream is expanded to three equal channels (PIL's convert("RGB"))
   const nvjpegStatus_t rc = api->decode(d->handle, d->state, data, (size_t)len, NVJPEG_OUTPUT_RGBI, &dst, (cudaStream_t)stream);
   if (rc != NVJPEG_STATUS_SUCCESS) return fail(MC_ERR_CUDA, "nvjpegDecode failed with status " + std::to_string((int)rc));
+  return MC_OK;
+}
+
+int mc_jpeg_decode_exact(mc_jpeg* d, const uint8_t* data, int64_t len, uint8_t* rgb_dev, int64_t row_pitch, int32_t height,
+                         int32_t width, void* stream) {
+  if (!d || !data || len <= 0 || !rgb_dev) return fail(MC_ERR_BAD_ARG, "mc_jpeg_decode_exact: null argument");
+  JpxHeader H;
+  if (int rc = jpx_parse(data, (size_t)len, &H)) return rc;
+  if (H.height != height || H.width != width || row_pitch < (int64_t)width * 3)
+    return fail(MC_ERR_BAD_ARG, "mc_jpeg_decode_exact: destination is " + std::to_string(height) + " x " + std::to_string(width) +
+                                    ", the stream holds " + std::to_string(H.height) + " x " + std::to_string(H.width));
+  DeviceGuard g(d->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  JpxKernelArgs ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.ncomp = H.ncomp;
+  int total = 0;
+  int64_t plane_bytes = 0;
+  for (int c = 0; c < H.ncomp; ++c) {
+    ka.blk_base[c] = total;
+    ka.bx[c] = H.comp[c].bx;
+    ka.by[c] = H.comp[c].by;
+    ka.plane_off[c] = plane_bytes;
+    total += H.comp[c].bx * H.comp[c].by;
+    plane_bytes += (int64_t)H.comp[c].bx * 8 * H.comp[c].by * 8;
+    memcpy(ka.qt[c], H.qt[H.comp[c].tq], sizeof(ka.qt[c]));
+  }
+  ka.blk_base[H.ncomp] = total;
+  const size_t cap = std::min<size_t>((size_t)total * 64, (size_t)len * 4 + (size_t)total) + 64;
+  JpxScratch* s = &d->jpx;
+  if (int rc = jpx_reserve(s, cap, (size_t)total * 2, (size_t)plane_bytes)) return rc;
+  if (s->pending) {   // the previous call's copies out of the pinned buffers must have finished before they are overwritten
+    MC_CUDA(cudaEventSynchronize(s->h2d_done));
+    s->pending = false;
+  }
+  size_t n_entries = 0;
+  if (int rc = jpx_entropy_decode(data, (size_t)len, H, ka.blk_base, s->h_entries, s->cap_entries, s->h_offsets, &n_entries)) return rc;
+  MC_CUDA(cudaMemcpyAsync(s->d_entries, s->h_entries, std::max<size_t>(n_entries, 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  MC_CUDA(cudaMemcpyAsync(s->d_offsets, s->h_offsets, (size_t)total * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  MC_CUDA(cudaEventRecord(s->h2d_done, st));
+  s->pending = true;
+  jpx_idct_kernel<<<cdiv(total, JPX_IDCT_THREADS), JPX_IDCT_THREADS, 0, st>>>(s->d_entries, s->d_offsets, s->d_planes, ka);
+  MC_CHECK_LAUNCH();
+  jpx_color_kernel<<<dim3(cdiv(width, 256), height), 256, 0, st>>>(s->d_planes, ka, width, height, H.hmax, H.vmax, rgb_dev, row_pitch);
+  MC_CHECK_LAUNCH();
   return MC_OK;
 }
 

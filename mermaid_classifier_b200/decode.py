@@ -7,9 +7,13 @@ COMPRESSED bytes go to the library (``mc_jpeg_decode``: Huffman decoding on the 
 conversion on the GPU through nvJPEG) and come out as an RGB8 device image that ``EfficientNetExtractor.extract_device``
 reads directly; the decoded image never crosses PCIe.
 
-nvJPEG's inverse DCT and chroma upsampling are not libjpeg-turbo's bit for bit: against PIL the decoded bytes differ by a
-few grey levels in a small fraction of the pixels (``tests/test_gpu_decode.py`` states and checks the bound).  Files that are
-not JPEG streams (the PNG stand-ins of the tests) fall back to PIL + one host-to-device copy.
+Two device paths.  ``exact=True`` (default) is ``mc_jpeg_decode_exact``: the library's own baseline decoder -- entropy
+decoding on the calling thread into a sparse coefficient stream, then libjpeg-turbo's integer IDCT, fancy chroma upsampling
+and YCbCr -> RGB arithmetic restated as kernels -- whose bytes EQUAL PIL's (``tests/test_gpu_decode.py``; the CPU restatement
+``oracle/jpeg.py`` is pinned to PIL byte for byte by ``tests/test_oracle_jpeg.py``).  Streams it does not cover (progressive,
+CMYK, unusual sampling factors) fall through to nvJPEG (``mc_jpeg_decode``), whose inverse DCT and chroma interpolation are
+not libjpeg-turbo's bit for bit: against PIL its bytes differ by a few grey levels (the bound is stated and checked in the same
+test file).  Files that are not JPEG streams (the PNG stand-ins of the tests) fall back to PIL + one host-to-device copy.
 """
 
 from __future__ import annotations
@@ -32,9 +36,11 @@ def is_jpeg(data: bytes) -> bool:
 class JpegDecoder:
     """One ``mc_jpeg`` handle (not thread-safe: one per worker thread)."""
 
-    def __init__(self, device: int | None = None):
+    def __init__(self, device: int | None = None, exact: bool = True):
         torch = _lib.require_cuda()
         self.device = torch.cuda.current_device() if device is None else int(device)
+        self.exact = bool(exact)
+        self.last_path = None   # "exact" / "nvjpeg": which decoder produced the last image
         h = C.c_void_p()
         _lib.check(_lib.load().mc_jpeg_create(self.device, C.byref(h)))
         self._h = h
@@ -64,7 +70,15 @@ class JpegDecoder:
         H, W, _ = self.info(data)
         with torch.cuda.device(self.device):
             out = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+            if self.exact:
+                status = _lib.load().mc_jpeg_decode_exact(self._h, data, len(data), out.data_ptr(), W * 3, H, W, _lib.stream_ptr(stream))
+                if status == _lib.MC_OK:
+                    self.last_path = "exact"
+                    return out
+                if status != _lib.MC_ERR_UNSUPPORTED:
+                    _lib.check(status)
             _lib.check(_lib.load().mc_jpeg_decode(self._h, data, len(data), out.data_ptr(), W * 3, H, W, _lib.stream_ptr(stream)))
+            self.last_path = "nvjpeg"
         return out
 
 
@@ -86,9 +100,10 @@ class DecodePool:
     runs in parallel, the GPU parts overlap on the streams.  ``decode_many`` returns device images in input order, ready
     on the caller's current stream."""
 
-    def __init__(self, n_threads: int = 8, device: int | None = None):
+    def __init__(self, n_threads: int = 8, device: int | None = None, exact: bool = True):
         torch = _lib.require_cuda()
         self.device = torch.cuda.current_device() if device is None else int(device)
+        self.exact = bool(exact)
         self.n_threads = max(1, int(n_threads))
         self._pool = ThreadPoolExecutor(max_workers=self.n_threads)
         self._local = threading.local()
@@ -99,7 +114,7 @@ class DecodePool:
         torch = _lib.require_cuda()
         st = getattr(self._local, "state", None)
         if st is None:
-            dec = JpegDecoder(self.device)
+            dec = JpegDecoder(self.device, exact=self.exact)
             with self._lock:
                 self._decoders.append(dec)
             st = self._local.state = (dec, torch.cuda.Stream(device=self.device))

@@ -1,5 +1,6 @@
-"""GPU tests of the device-side image decode: nvJPEG through the C ABI against PIL's load_image semantics,
-and the bucket driver running on device-decoded images."""
+"""GPU tests of the device-side image decode: the library's own baseline decoder (bit-exact with PIL) and the
+nvJPEG fall-back through the C ABI against PIL's load_image semantics, and the bucket driver running on device-decoded
+images."""
 import io
 
 import numpy as np
@@ -30,7 +31,7 @@ def _pil(data):
 
 
 def test_jpeg_decode_matches_pil():
-    dec = JpegDecoder()
+    dec = JpegDecoder(exact=False)   # the nvJPEG path and its stated bound
     im = synth.synth_image(synth.DEFAULT_SEED, 3, 600, 840)
     data = _jpeg(im, subsampling=0)   # 4:4:4
     assert dec.info(data) == (600, 840, 3)
@@ -103,3 +104,60 @@ def test_bucket_driver_with_device_decode(tmp_path, backbone_sd):
         cos = (A * B).sum(1) / (np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1))
         assert [(p.row, p.col) for p in fa.point_features] == [(p.row, p.col) for p in fb.point_features]
         assert cos.min() >= 0.999, cos.min()
+
+
+def _photo(rng, h, w, noise=18.0):
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([128 + 90 * np.sin(xx / 9.0 + yy / 17.0), 128 + 80 * np.cos(xx / 13.0 - yy / 7.0),
+                     128 + 70 * np.sin((xx + yy) / 11.0)], -1)
+    return np.clip(base + rng.normal(0, noise, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def test_jpeg_decode_exact_equals_pil():
+    """``mc_jpeg_decode_exact``: every byte equal to PIL / libjpeg-turbo -- the decoder of the reference's ``load_image``
+    (``pyspacer/annotation.py:235``) -- for 4:4:4 / 4:2:2 / 4:2:0 / grayscale, odd and tiny sizes, extreme qualities,
+    optimised tables and restart intervals; and to the CPU oracle (``oracle/jpeg.py``), which the same fixtures pin to PIL
+    on the CPU side.  Progressive streams fall through to nvJPEG."""
+    from oracle import jpeg as oj
+
+    rng = np.random.default_rng(11)
+    dec = JpegDecoder()
+    n = 0
+    for h, w in [(48, 64), (45, 67), (17, 33), (8, 8), (1, 1), (100, 3), (3, 100), (5, 4), (231, 149), (600, 840)]:
+        for ss in (0, 1, 2):
+            for q in (95, 75, 20, 5):
+                if h * w > 100000 and q not in (95, 20):
+                    continue
+                data = _jpeg(_photo(rng, h, w), quality=q, subsampling=ss)
+                got = dec.decode(data).cpu().numpy()
+                assert dec.last_path == "exact"
+                assert np.array_equal(got, _pil(data)), (h, w, ss, q)
+                if h * w <= 4096:
+                    assert np.array_equal(got, oj.decode_rgb(data))
+                n += 1
+    sat = np.zeros((40, 56, 3), np.uint8)
+    sat[::2] = 255
+    sat[:, ::3, 1] = 0
+    im = _photo(rng, 97, 131)
+    for arr, kw in [(im[:, :, 0], dict(quality=80)), (sat, dict(quality=85, subsampling=2, optimize=True)),
+                    (sat, dict(quality=85, subsampling=0, restart_marker_blocks=3)),
+                    (im, dict(quality=60, subsampling=1, restart_marker_rows=1)), (sat, dict(quality=100, subsampling=0))]:
+        buf = io.BytesIO()
+        Image.fromarray(arr).save(buf, format="JPEG", **kw)
+        got = dec.decode(buf.getvalue()).cpu().numpy()
+        assert dec.last_path == "exact" and np.array_equal(got, _pil(buf.getvalue())), kw
+    # the full-size case of the benchmarks: 4000 x 3000, 4:2:0
+    big = np.kron(synth.synth_image(synth.DEFAULT_SEED, 4, 375, 500), np.ones((8, 8, 1), np.uint8)).astype(np.int16)
+    big = np.clip(big + rng.integers(-6, 7, big.shape), 0, 255).astype(np.uint8)
+    data = _jpeg(big, quality=90, subsampling=2)
+    assert np.array_equal(dec.decode(data).cpu().numpy(), _pil(data)) and dec.last_path == "exact"
+    # back-to-back decodes reuse the pinned staging buffers safely
+    a, b = dec.decode(data), dec.decode(_jpeg(big[::-1].copy(), quality=90, subsampling=2))
+    assert np.array_equal(a.cpu().numpy(), _pil(data)) and not torch.equal(a, b)
+    # progressive: not covered by the exact decoder -> nvJPEG, within its bound
+    buf = io.BytesIO()
+    Image.fromarray(im).save(buf, format="JPEG", quality=90, subsampling=0, progressive=True)
+    got = dec.decode(buf.getvalue()).cpu().numpy()
+    assert dec.last_path == "nvjpeg"
+    assert np.abs(got.astype(np.int16) - _pil(buf.getvalue()).astype(np.int16)).max() <= 8
+    dec.close()
