@@ -1,4 +1,5 @@
-"""Device JPEG decode throughput (mc_jpeg_decode through DecodePool) on a 4000x3000 photograph-like image, against PIL."""
+"""Device JPEG decode throughput (mc_jpeg_decode_exact and mc_jpeg_decode through DecodePool) on a 4000x3000 photograph-like
+image, against PIL."""
 import io, json, sys, time
 from pathlib import Path
 import numpy as np
@@ -20,8 +21,10 @@ t0 = time.perf_counter()
 for _ in range(4):
     np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
 res["pil_images_per_s_1thread"] = round(4 / (time.perf_counter() - t0), 1)
-for nt in (1, 4, 8, 16):
-    pool = DecodePool(nt)
+for exact in (True, False):
+  tag = "exact" if exact else "nvjpeg"
+  for nt in (1, 4, 8, 16):
+    pool = DecodePool(nt, exact=exact)
     pool.decode_many([data] * nt)
     torch.cuda.synchronize()
     n = 8 * nt
@@ -30,6 +33,6 @@ for nt in (1, 4, 8, 16):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     assert all(e is None for _, e in out)
-    res[f"device_images_per_s_{nt}threads"] = round(n / dt, 1)
+    res[f"{tag}_images_per_s_{nt}threads"] = round(n / dt, 1)
     pool.close()
 print(json.dumps(res))
