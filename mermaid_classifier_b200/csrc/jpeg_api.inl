@@ -143,6 +143,8 @@ int mc_jpeg_decode_exact(mc_jpeg* d, const uint8_t* data, int64_t len, uint8_t* 
   if (!d || !data || len <= 0 || !rgb_dev) return fail(MC_ERR_BAD_ARG, "mc_jpeg_decode_exact: null argument");
   JpxHeader H;
   if (int rc = jpx_parse(data, (size_t)len, &H)) return rc;
+  if ((int64_t)H.height * H.width > 100000000ll)   // pyspacer's MAX_IMAGE_PIXELS (check_extract_inputs): also bounds the scratch
+    return fail(MC_ERR_DATA_LIMIT, "mc_jpeg_decode_exact: " + std::to_string(H.width) + " x " + std::to_string(H.height) + " pixels exceed the 1e8 limit");
   if (H.height != height || H.width != width || row_pitch < (int64_t)width * 3)
     return fail(MC_ERR_BAD_ARG, "mc_jpeg_decode_exact: destination is " + std::to_string(height) + " x " + std::to_string(width) +
                                     ", the stream holds " + std::to_string(H.height) + " x " + std::to_string(H.width));

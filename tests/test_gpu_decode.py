@@ -162,3 +162,30 @@ def test_jpeg_decode_exact_equals_pil():
     assert dec.last_path == "nvjpeg"
     assert np.abs(got.astype(np.int16) - _pil(buf.getvalue()).astype(np.int16)).max() <= 8
     dec.close()
+
+
+def test_jpeg_decode_exact_survives_damaged_streams():
+    """Truncated and bit-flipped scans must neither hang nor fault: the exact decoder returns an image (libjpeg pads a
+    short scan the same way) or a clean error, and the handle keeps working afterwards."""
+    rng = np.random.default_rng(3)
+    good = _jpeg(_photo(rng, 120, 160), quality=85, subsampling=2)
+    want = _pil(good)
+    dec = JpegDecoder()
+    for cut in (len(good) // 2, len(good) - 3, 700):
+        try:
+            img = dec.decode(good[:cut])
+            assert tuple(img.shape) == (120, 160, 3)
+        except (ValueError, RuntimeError):
+            pass
+    for k in range(5):
+        bad = bytearray(good)
+        for pos in rng.integers(650, len(good) - 2, size=20):
+            bad[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            img = dec.decode(bytes(bad))
+            assert tuple(img.shape) == (120, 160, 3)
+        except (ValueError, RuntimeError):
+            pass
+    torch.cuda.synchronize()
+    assert np.array_equal(dec.decode(good).cpu().numpy(), want)
+    dec.close()
