@@ -172,6 +172,11 @@ int mc_jpeg_decode(mc_jpeg* d, const uint8_t* jpeg_host, int64_t n_bytes, uint8_
  * after the host-side entropy decoding. */
 int mc_jpeg_decode_exact(mc_jpeg* d, const uint8_t* jpeg_host, int64_t n_bytes, uint8_t* rgb_dev, int64_t row_pitch,
                          int32_t height, int32_t width, void* stream);
+/* Host-only half of the exact decoder: quantised DCT coefficients (dense int16 [block][64], natural order, component after
+ * component over each component's whole MCU-padded block grid); info = {height, width, components, bx0, by0, bx1, by1, bx2,
+ * by2, restart interval}; coef_out == NULL only fills info.  Needs no CUDA device. */
+int mc_jpeg_coefficients_host(const uint8_t* jpeg_host, int64_t n_bytes, int16_t* coef_out, int64_t capacity_blocks,
+                              int32_t* info /* [10] */);
 
 /* Debug/parity tap: during the NEXT extract call, copy one internal NHWC activation of the
  * first sub-batch to `out_dev` as fp32 (at most `capacity` elements).

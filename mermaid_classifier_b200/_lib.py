@@ -74,6 +74,7 @@ SIGNATURES = {
     "mc_jpeg_info": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "mc_jpeg_decode": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "mc_jpeg_decode_exact": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "mc_jpeg_coefficients_host": (C.c_int, [_vp, _i64, _vp, _i64, _vp]),
     "mc_extractor_set_tap": (C.c_int, [_vp, _i32, _vp, _i64]),
     "mc_extractor_profile": (C.c_int, [_vp, _i32]),
     "mc_extractor_profile_read": (C.c_int, [_vp, _vp, _vp, _i32]),

@@ -185,4 +185,37 @@ int mc_jpeg_decode_exact(mc_jpeg* d, const uint8_t* data, int64_t len, uint8_t* 
   return MC_OK;
 }
 
+// Host-only half of mc_jpeg_decode_exact: the quantised DCT coefficients of a baseline stream, dense, natural order,
+// component after component over each component's whole block grid ([by][bx][64] int16).  info = {height, width, components,
+// bx0, by0, bx1, by1, bx2, by2, restart interval}.  No CUDA device needed (the CPU test-suite checks the entropy decoder
+// against oracle/jpeg.py with it); coef_out == NULL only fills `info`.
+int mc_jpeg_coefficients_host(const uint8_t* data, int64_t len, int16_t* coef_out, int64_t capacity_blocks, int32_t* info) {
+  if (!data || len <= 0 || !info) return fail(MC_ERR_BAD_ARG, "mc_jpeg_coefficients_host: null argument");
+  JpxHeader H;
+  if (int rc = jpx_parse(data, (size_t)len, &H)) return rc;
+  int blk_base[4] = {0, 0, 0, 0};
+  int total = 0;
+  for (int c = 0; c < H.ncomp; ++c) {
+    blk_base[c] = total;
+    total += H.comp[c].bx * H.comp[c].by;
+  }
+  blk_base[H.ncomp] = total;
+  info[0] = H.height; info[1] = H.width; info[2] = H.ncomp;
+  for (int c = 0; c < 3; ++c) {
+    info[3 + 2 * c] = c < H.ncomp ? H.comp[c].bx : 0;
+    info[4 + 2 * c] = c < H.ncomp ? H.comp[c].by : 0;
+  }
+  info[9] = H.ri;
+  if (!coef_out) return MC_OK;
+  if (capacity_blocks < total) return fail(MC_ERR_BAD_ARG, "mc_jpeg_coefficients_host: room for " + std::to_string(capacity_blocks) + " blocks, the stream holds " + std::to_string(total));
+  const size_t cap = std::min<size_t>((size_t)total * 64, (size_t)len * 4 + (size_t)total) + 64;
+  std::vector<uint32_t> entries(cap), offsets((size_t)total * 2);
+  size_t n_entries = 0;
+  if (int rc = jpx_entropy_decode(data, (size_t)len, H, blk_base, entries.data(), cap, offsets.data(), &n_entries)) return rc;
+  memset(coef_out, 0, (size_t)total * 64 * sizeof(int16_t));
+  for (int b = 0; b < total; ++b)
+    for (uint32_t e = offsets[2 * b]; e < offsets[2 * b + 1]; ++e) coef_out[(size_t)b * 64 + (entries[e] >> 16)] = (int16_t)(entries[e] & 0xFFFFu);
+  return MC_OK;
+}
+
 }  // extern "C"

@@ -34,6 +34,9 @@ struct JpxHuff {
   int valptr[17];
   int mincode[17];
   uint8_t vals[256];
+  // AC tables only: when the code AND the magnitude bits of a coefficient fit in the 9-bit lookahead, the decoded value, its
+  // zero run and the total bit count in one entry -- (value << 8) | (run << 4) | bits, 0 = take the general path
+  int16_t fast_ac[512];
   bool present = false;
 };
 
@@ -63,6 +66,17 @@ void jpx_build_huff(JpxHuff* h, const uint8_t* counts, const uint8_t* symbols, i
     code <<= 1;
   }
   h->maxcode[17] = 0x7fffffff;
+  for (int i = 0; i < 512; ++i) {
+    h->fast_ac[i] = 0;
+    const int e = h->look[i];
+    if (!e) continue;
+    const int len = e >> 8, rs = e & 0xFF, run = rs >> 4, mag = rs & 15;
+    if (mag && len + mag <= 9) {
+      int k = ((i << len) & 511) >> (9 - mag);          // the magnitude bits that follow the code
+      if (k < (1 << (mag - 1))) k -= (1 << mag) - 1;      // EXTEND
+      if (k >= -128 && k <= 127) h->fast_ac[i] = (int16_t)(k * 256 + run * 16 + (len + mag));
+    }
+  }
   h->present = true;
 }
 
@@ -499,6 +513,16 @@ int jpx_entropy_decode(const uint8_t* d, size_t n, const JpxHeader& H, const int
             pred[c] += diff;
             if (pred[c]) entries[pos++] = (0u << 16) | ((uint32_t)pred[c] & 0xFFFFu);
             for (int k = 1; k < 64;) {
+              if (br.cnt < 16) br.fill();
+              const int fa = ha.fast_ac[br.peek(9)];
+              if (fa) {   // code + magnitude inside the lookahead: one table hit per coefficient
+                k += (fa >> 4) & 15;
+                if (k > 63) break;   // corrupt stream
+                br.skip(fa & 15);
+                entries[pos++] = ((uint32_t)JPX_ZIGZAG[k] << 16) | ((uint32_t)(fa >> 8) & 0xFFFFu);
+                ++k;
+                continue;
+              }
               const int rs = jpx_decode_symbol(br, ha);
               const int r = rs >> 4, sz = rs & 15;
               if (sz == 0) {

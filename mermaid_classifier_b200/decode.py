@@ -33,6 +33,26 @@ def is_jpeg(data: bytes) -> bool:
     return len(data) > 3 and data[0] == 0xFF and data[1] == 0xD8
 
 
+def jpeg_coefficients(data: bytes):
+    """Quantised DCT coefficients of a baseline JPEG stream as the library's host-side entropy decoder produces them
+    (``mc_jpeg_coefficients_host``; no GPU involved): ``(info, [per-component (by, bx, 64) int16 arrays])`` with
+    ``info = {"height", "width", "components", "restart_interval"}``."""
+    data = bytes(data)
+    info = (C.c_int32 * 10)()
+    lib = _lib.load()
+    _lib.check(lib.mc_jpeg_coefficients_host(data, len(data), None, 0, info))
+    nc = info[2]
+    grids = [(info[4 + 2 * c], info[3 + 2 * c]) for c in range(nc)]
+    total = sum(by * bx for by, bx in grids)
+    flat = np.zeros((total, 64), dtype=np.int16)
+    _lib.check(lib.mc_jpeg_coefficients_host(data, len(data), flat.ctypes.data, total, info))
+    out, pos = [], 0
+    for by, bx in grids:
+        out.append(flat[pos: pos + by * bx].reshape(by, bx, 64))
+        pos += by * bx
+    return {"height": info[0], "width": info[1], "components": nc, "restart_interval": info[9]}, out
+
+
 class JpegDecoder:
     """One ``mc_jpeg`` handle (not thread-safe: one per worker thread)."""
 
