@@ -316,7 +316,8 @@ struct PwTcArgs {
   int64_t M;
   int N, K, HW, BN, n_blocks, k_chunks, act, stages;
   long long* dbg;     // MC_TC_DBG: per-role wait/total cycle counters of CTA 0 (null = off)
-  int exp_flags;      // MC_TC_EXP timing experiments: 1 no activation, 2 no global stores, 4 no operand transform, 16 no MMA, 32 no tcgen05.ld
+  int exp_flags;      // MC_TC_EXP experiments: 1 no activation, 2 no global stores, 4 no operand transform, 16 no MMA, 32 no tcgen05.ld,
+                      // 64 no W lo fetch, 256 single-pass TF32 in the TS form (hi x hi only: a precision experiment)
   int w_res;          // 1: the layer's whole weight (all n-blocks x k-chunks, hi+lo) stays resident in smem
                       // 2: ONE n-block's weight (all k-chunks) stays resident: the grid is a multiple of n_blocks, so CTA c only
                       //    ever sees n-block c % n_blocks (item it = c + j * grid -> n-block it % n_blocks)
@@ -616,9 +617,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               } else if constexpr (TS) {
                 const uint32_t a_tm = tmem_base + TS_A_COL0 + (cc & (TS_SLOTS - 1u)) * TS_SLOT_COLS + (uint32_t)ks * 8u;   // hi; lo 32 columns on
                 const uint64_t whi = DESC_HI64 | (w_lo + ko), wlo = DESC_HI64 | (w_lo + w_step + ko);
-                ptx::mma_ts_tf32(d_tmem, a_tm + 32u, whi, idesc, acc);
-                ptx::mma_ts_tf32(d_tmem, a_tm, wlo, idesc, 1u);
-                ptx::mma_ts_tf32(d_tmem, a_tm, whi, idesc, 1u);
+                if (p.exp_flags & 256) {   // experiment: single-pass TF32 (hi x hi only)
+                  ptx::mma_ts_tf32(d_tmem, a_tm, whi, idesc, acc);
+                } else {
+                  ptx::mma_ts_tf32(d_tmem, a_tm + 32u, whi, idesc, acc);
+                  ptx::mma_ts_tf32(d_tmem, a_tm, wlo, idesc, 1u);
+                  ptx::mma_ts_tf32(d_tmem, a_tm, whi, idesc, 1u);
+                }
               } else if (Cfg::TF32) {
                 const uint64_t ahi = DESC_HI64 | (a_lo + ko), alo = DESC_HI64 | (l_lo + ko);
                 const uint64_t whi = DESC_HI64 | (w_lo + ko), wlo = DESC_HI64 | (w_lo + w_step + ko);
