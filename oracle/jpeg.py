@@ -8,8 +8,9 @@ YCbCr -> RGB tables of ``jdcolor.c``.  This module restates that pipeline -- ent
 only), everything after it in NumPy integer arithmetic -- and ``tests/test_oracle_jpeg.py`` pins it to PIL itself, byte for
 byte, on generated fixtures (4:4:4, 4:2:2, 4:2:0, grayscale, odd sizes, restart intervals, low quality).
 
-Covered: baseline / extended-sequential Huffman, 8-bit, 1 or 3 components, sampling factors 1x1 (luma 1x1 / 2x1 / 2x2).
-Anything else (progressive, arithmetic, CMYK, 4:4:0, 4:1:1 ...) raises ``UnsupportedJpeg``: the product falls back too.
+Covered: baseline / extended-sequential and progressive Huffman streams, 8-bit, 1 or 3 components, chroma sampling 1x1 with
+luma 1x1 / 2x1 / 2x2.  Anything else (arithmetic coding, CMYK, 4:4:0, 4:1:1 ...) raises ``UnsupportedJpeg``: the product
+falls back too.
 """
 
 from __future__ import annotations
@@ -30,8 +31,8 @@ ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 1
 # header parsing
 # ---------------------------------------------------------------------------------------------------------------------
 def parse(data: bytes) -> dict:
-    """Markers of a baseline JPEG: quantisation tables (natural order), Huffman tables, frame and scan headers, restart
-    interval, and the offset of the entropy-coded segment."""
+    """Markers of a baseline or progressive JPEG: quantisation tables (natural order), frame header, restart interval, and
+    every scan with the Huffman tables in force when it starts and the offset of its entropy-coded segment."""
     if data[:2] != b"\xff\xd8":
         raise UnsupportedJpeg("not a JPEG stream")
     qt: dict[int, np.ndarray] = {}
@@ -39,16 +40,20 @@ def parse(data: bytes) -> dict:
     frame = None
     ri = 0
     adobe_transform = None
+    scans = []
     pos = 2
-    while True:
+    n = len(data)
+    while pos < n:
         if data[pos] != 0xFF:
             raise UnsupportedJpeg("marker expected")
-        while data[pos] == 0xFF:
+        while pos < n and data[pos] == 0xFF:
             pos += 1
         m = data[pos]
         pos += 1
         if m in (0x01,) or 0xD0 <= m <= 0xD7:
             continue
+        if m == 0xD9:
+            break
         seg_len = (data[pos] << 8) | data[pos + 1]
         seg = data[pos + 2: pos + seg_len]
         if m == 0xDB:
@@ -70,31 +75,44 @@ def parse(data: bytes) -> dict:
             while i < len(seg):
                 tc, th = seg[i] >> 4, seg[i] & 15
                 counts = list(seg[i + 1: i + 17])
-                n = sum(counts)
-                ht[(tc, th)] = (counts, list(seg[i + 17: i + 17 + n]))
-                i += 17 + n
-        elif m in (0xC0, 0xC1):
+                k = sum(counts)
+                ht[(tc, th)] = (counts, list(seg[i + 17: i + 17 + k]))
+                i += 17 + k
+        elif m in (0xC0, 0xC1, 0xC2):
             if seg[0] != 8:
                 raise UnsupportedJpeg("sample precision")
             h, w, nf = (seg[1] << 8) | seg[2], (seg[3] << 8) | seg[4], seg[5]
             comps = [{"id": seg[6 + 3 * c], "h": seg[7 + 3 * c] >> 4, "v": seg[7 + 3 * c] & 15, "tq": seg[8 + 3 * c]} for c in range(nf)]
-            frame = {"height": h, "width": w, "comps": comps}
-        elif 0xC2 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
-            raise UnsupportedJpeg("not a baseline (sequential Huffman) JPEG")
+            frame = {"height": h, "width": w, "comps": comps, "progressive": m == 0xC2}
+        elif 0xC3 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
+            raise UnsupportedJpeg("not a Huffman-coded baseline / progressive JPEG")
         elif m == 0xDD:
             ri = (seg[0] << 8) | seg[1]
         elif m == 0xEE and seg[:5] == b"Adobe":
             adobe_transform = seg[11]
         elif m == 0xDA:
+            if frame is None:
+                raise UnsupportedJpeg("scan before frame")
             ns = seg[0]
-            scan = [{"id": seg[1 + 2 * c], "td": seg[2 + 2 * c] >> 4, "ta": seg[2 + 2 * c] & 15} for c in range(ns)]
-            if frame is None or ns != len(frame["comps"]):
-                raise UnsupportedJpeg("multi-scan files")
-            return {"qt": qt, "ht": ht, "frame": frame, "scan": scan, "ri": ri, "data_pos": pos + seg_len,
-                    "adobe_transform": adobe_transform}
-        elif m == 0xD9:
-            raise UnsupportedJpeg("no scan")
+            ids = [c["id"] for c in frame["comps"]]
+            sc = [{"ci": ids.index(seg[1 + 2 * c]), "td": seg[2 + 2 * c] >> 4, "ta": seg[2 + 2 * c] & 15} for c in range(ns)]
+            ss, se, ahal = seg[1 + 2 * ns], seg[2 + 2 * ns], seg[3 + 2 * ns]
+            scans.append({"comps": sc, "ss": ss, "se": se, "ah": ahal >> 4, "al": ahal & 15, "ht": dict(ht), "ri": ri,
+                          "data_pos": pos + seg_len})
+            # skip the entropy-coded segment: up to the next marker that is not RSTn / stuffing
+            q = pos + seg_len
+            while q + 1 < n and not (data[q] == 0xFF and data[q + 1] != 0 and not (0xD0 <= data[q + 1] <= 0xD7)):
+                q += 1
+            pos = q
+            continue
         pos += seg_len
+    if frame is None or not scans:
+        raise UnsupportedJpeg("no scan")
+    if not frame["progressive"] and (len(scans) != 1 or len(scans[0]["comps"]) != len(frame["comps"])):
+        raise UnsupportedJpeg("multi-scan sequential files")
+    first = scans[0]
+    return {"qt": qt, "ht": first["ht"], "frame": frame, "scan": [{"id": frame["comps"][c["ci"]]["id"], "td": c["td"], "ta": c["ta"]} for c in first["comps"]],
+            "scans": scans, "ri": first["ri"], "data_pos": first["data_pos"], "adobe_transform": adobe_transform}
 
 
 def check_supported(hdr: dict) -> None:
@@ -221,6 +239,121 @@ def decode_coefficients(data: bytes, hdr: dict) -> list[np.ndarray]:
                             k += r
                             blk[ZIGZAG[k]] = _extend(br.bits(s), s)
                             k += 1
+    return out
+
+
+def decode_coefficients_progressive(data: bytes, hdr: dict) -> list[np.ndarray]:
+    """``jdphuff.c``: DC / AC first and refinement scans accumulated into the coefficient arrays (same layout as
+    :func:`decode_coefficients`)."""
+    fr = hdr["frame"]
+    comps = fr["comps"]
+    hmax, vmax = max(c["h"] for c in comps), max(c["v"] for c in comps)
+    W, H = fr["width"], fr["height"]
+    if len(comps) == 1:
+        hmax = vmax = 1
+        grid = [((H + 7) // 8, (W + 7) // 8)]
+    else:
+        mcux = (W + 8 * hmax - 1) // (8 * hmax)
+        mcuy = (H + 8 * vmax - 1) // (8 * vmax)
+        grid = [(mcuy * c["v"], mcux * c["h"]) for c in comps]
+    out = [np.zeros((g[0], g[1], 64), dtype=np.int32) for g in grid]
+    for sc in hdr["scans"]:
+        br = _Bits(data, sc["data_pos"])
+        ss, se, ah, al = sc["ss"], sc["se"], sc["ah"], sc["al"]
+        ns = len(sc["comps"])
+        tabs = {}
+        for c in sc["comps"]:
+            tabs[c["ci"]] = (_Huff(*sc["ht"][(0, c["td"])]) if (0, c["td"]) in sc["ht"] else None,
+                             _Huff(*sc["ht"][(1, c["ta"])]) if (1, c["ta"]) in sc["ht"] else None)
+        # block visiting order of this scan
+        if ns > 1:
+            order = []
+            for my in range(mcuy):
+                for mx in range(mcux):
+                    unit = []
+                    for c in sc["comps"]:
+                        ci = c["ci"]
+                        v, h = (comps[ci]["v"], comps[ci]["h"]) if len(comps) > 1 else (1, 1)
+                        unit += [(ci, my * v + by, mx * h + bx) for by in range(v) for bx in range(h)]
+                    order.append(unit)
+        else:
+            ci = sc["comps"][0]["ci"]
+            ch_, cw_ = comps[ci]["h"], comps[ci]["v"]
+            if len(comps) == 1:
+                bw, bh = (W + 7) // 8, (H + 7) // 8
+            else:
+                bw = ((W * comps[ci]["h"] + hmax - 1) // hmax + 7) // 8
+                bh = ((H * comps[ci]["v"] + vmax - 1) // vmax + 7) // 8
+            order = [[(ci, y, x)] for y in range(bh) for x in range(bw)]
+        pred = {c["ci"]: 0 for c in sc["comps"]}
+        eobrun = 0
+        ri = sc["ri"]
+        p1, m1 = 1 << al, -1 << al
+        for count, unit in enumerate(order):
+            if ri and count and count % ri == 0:
+                br.restart()
+                pred = {k: 0 for k in pred}
+                eobrun = 0
+            for ci, y, x in unit:
+                blk = out[ci][y, x]
+                dc_t, ac_t = tabs[ci]
+                if ss == 0:
+                    if ah == 0:
+                        s = _sym(br, dc_t)
+                        pred[ci] += _extend(br.bits(s), s) if s else 0
+                        blk[0] = pred[ci] << al
+                    elif br.bit():
+                        blk[0] |= p1
+                    continue
+                if ah == 0:   # AC first
+                    if eobrun > 0:
+                        eobrun -= 1
+                        continue
+                    k = ss
+                    while k <= se:
+                        rs = _sym(br, ac_t)
+                        r, s = rs >> 4, rs & 15
+                        if s:
+                            k += r
+                            blk[ZIGZAG[k]] = _extend(br.bits(s), s) << al
+                        elif r == 15:
+                            k += 15
+                        else:
+                            eobrun = (1 << r) + (br.bits(r) if r else 0) - 1
+                            break
+                        k += 1
+                    continue
+                # AC refinement
+                k = ss
+                if eobrun == 0:
+                    while k <= se:
+                        rs = _sym(br, ac_t)
+                        r, s = rs >> 4, rs & 15
+                        if s:
+                            s = p1 if br.bit() else m1
+                        elif r != 15:
+                            eobrun = (1 << r) + (br.bits(r) if r else 0)
+                            break
+                        while k <= se:
+                            z = ZIGZAG[k]
+                            if blk[z] != 0:
+                                if br.bit() and (blk[z] & p1) == 0:
+                                    blk[z] += p1 if blk[z] >= 0 else m1
+                            else:
+                                r -= 1
+                                if r < 0:
+                                    break
+                            k += 1
+                        if s:
+                            blk[ZIGZAG[k]] = s
+                        k += 1
+                if eobrun > 0:
+                    while k <= se:
+                        z = ZIGZAG[k]
+                        if blk[z] != 0 and br.bit() and (blk[z] & p1) == 0:
+                            blk[z] += p1 if blk[z] >= 0 else m1
+                        k += 1
+                    eobrun -= 1
     return out
 
 
@@ -396,4 +529,5 @@ def decode_rgb(data: bytes) -> np.ndarray:
     """``(H, W, 3) uint8``: what ``PIL.Image.open(io.BytesIO(data)).convert("RGB")`` returns."""
     hdr = parse(data)
     check_supported(hdr)
-    return rgb_from_planes(planes_from_coefficients(decode_coefficients(data, hdr), hdr), hdr)
+    coefs = decode_coefficients_progressive(data, hdr) if hdr["frame"]["progressive"] else decode_coefficients(data, hdr)
+    return rgb_from_planes(planes_from_coefficients(coefs, hdr), hdr)

@@ -49,9 +49,24 @@ def test_oracle_decode_variants():
         data = _jpeg(arr, **kw)
         assert np.array_equal(oj.decode_rgb(data), _pil(data)), kw
     with pytest.raises(oj.UnsupportedJpeg):
-        oj.decode_rgb(_jpeg(im, quality=80, progressive=True))
-    with pytest.raises(oj.UnsupportedJpeg):
         oj.decode_rgb(b"\x89PNG not a jpeg")
     # the pieces, on their own edge cases
     assert np.array_equal(oj.h2v1_fancy(np.array([[10, 20, 30]], np.uint8)), [[10, 13, 17, 23, 27, 30]])
     assert oj.range_limit_idct(np.array([-600, -129, -128, 0, 127, 128, 600])).tolist() == [255, 0, 0, 128, 255, 255, 0]   # the table wraps outside [-512, 511]
+
+
+@pytest.mark.parametrize("subsampling", [0, 1, 2])
+def test_oracle_progressive_decode_equals_pil(subsampling):
+    """``jdphuff.c``: DC / AC first and refinement scans (spectral selection + successive approximation, EOB runs, restart
+    intervals) accumulate to the same coefficients, hence the same bytes as PIL."""
+    rng = np.random.default_rng(20 + subsampling)
+    for h, w in [(48, 64), (45, 67), (17, 33), (8, 8), (1, 1), (100, 3), (31, 49)]:
+        for q in (95, 60, 10):
+            data = _jpeg(_photo(rng, h, w), quality=q, subsampling=subsampling, progressive=True)
+            assert oj.parse(data)["frame"]["progressive"]
+            assert np.array_equal(oj.decode_rgb(data), _pil(data)), (h, w, q)
+    im = _photo(rng, 40, 56)
+    for arr, kw in [(im[:, :, 0], dict(quality=80, progressive=True)),
+                    (im, dict(quality=70, subsampling=subsampling, progressive=True, restart_marker_rows=1))]:
+        data = _jpeg(arr, **kw)
+        assert np.array_equal(oj.decode_rgb(data), _pil(data)), kw
