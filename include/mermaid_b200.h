@@ -167,8 +167,8 @@ int mc_jpeg_decode(mc_jpeg* d, const uint8_t* jpeg_host, int64_t n_bytes, uint8_
                    int32_t height, int32_t width, void* stream);
 /* The same, BIT FOR BIT what PIL / libjpeg-turbo decode (the reference's spacer.storage.load_image): the entropy decoding runs
  * on the calling thread, libjpeg-turbo's integer IDCT (jidctint.c), fancy chroma upsampling (jdsample.c) and YCbCr -> RGB
- * tables (jdcolor.c) are restated as kernels.  Baseline / extended-sequential Huffman streams, grayscale or YCbCr 4:4:4 /
- * 4:2:2 / 4:2:0; anything else returns MC_ERR_UNSUPPORTED (use mc_jpeg_decode or a host decoder).  Asynchronous on `stream`
+ * tables (jdcolor.c) are restated as kernels.  Baseline / extended-sequential and progressive (jdphuff.c) Huffman streams,
+ * grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0; anything else returns MC_ERR_UNSUPPORTED (use mc_jpeg_decode or a host decoder).  Asynchronous on `stream`
  * after the host-side entropy decoding. */
 int mc_jpeg_decode_exact(mc_jpeg* d, const uint8_t* jpeg_host, int64_t n_bytes, uint8_t* rgb_dev, int64_t row_pitch,
                          int32_t height, int32_t width, void* stream);

@@ -173,7 +173,13 @@ int mc_jpeg_decode_exact(mc_jpeg* d, const uint8_t* data, int64_t len, uint8_t* 
     s->pending = false;
   }
   size_t n_entries = 0;
-  if (int rc = jpx_entropy_decode(data, (size_t)len, H, ka.blk_base, s->h_entries, s->cap_entries, s->h_offsets, &n_entries)) return rc;
+  if (H.progressive) {
+    s->dense.assign((size_t)total * 64, 0);
+    if (int rc = jpx_decode_progressive(data, (size_t)len, H, ka.blk_base, s->dense.data())) return rc;
+    if (int rc = jpx_sparsify(s->dense.data(), total, s->h_entries, s->cap_entries, s->h_offsets, &n_entries)) return rc;
+  } else if (int rc = jpx_entropy_decode(data, (size_t)len, H, ka.blk_base, s->h_entries, s->cap_entries, s->h_offsets, &n_entries)) {
+    return rc;
+  }
   MC_CUDA(cudaMemcpyAsync(s->d_entries, s->h_entries, std::max<size_t>(n_entries, 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   MC_CUDA(cudaMemcpyAsync(s->d_offsets, s->h_offsets, (size_t)total * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   MC_CUDA(cudaEventRecord(s->h2d_done, st));
@@ -208,6 +214,10 @@ int mc_jpeg_coefficients_host(const uint8_t* data, int64_t len, int16_t* coef_ou
   info[9] = H.ri;
   if (!coef_out) return MC_OK;
   if (capacity_blocks < total) return fail(MC_ERR_BAD_ARG, "mc_jpeg_coefficients_host: room for " + std::to_string(capacity_blocks) + " blocks, the stream holds " + std::to_string(total));
+  if (H.progressive) {
+    memset(coef_out, 0, (size_t)total * 64 * sizeof(int16_t));
+    return jpx_decode_progressive(data, (size_t)len, H, blk_base, coef_out);
+  }
   const size_t cap = std::min<size_t>((size_t)total * 64, (size_t)len * 4 + (size_t)total) + 64;
   std::vector<uint32_t> entries(cap), offsets((size_t)total * 2);
   size_t n_entries = 0;

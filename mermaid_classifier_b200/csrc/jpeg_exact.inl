@@ -13,9 +13,10 @@
 //   idct kernel   one thread per block: scatter into shared memory, dequantise, two LL&M butterfly passes, range limit
 //   colour kernel one thread per pixel: chroma upsampled on the fly from the component planes, YCbCr -> RGB, 3 bytes out
 //
-// Covered: baseline / extended-sequential Huffman, 8-bit, grayscale or YCbCr with chroma 1x1 and luma 1x1 / 2x1 / 2x2
-// (4:4:4, 4:2:2, 4:2:0), restart intervals.  Anything else returns MC_ERR_UNSUPPORTED (callers fall back to mc_jpeg_decode
-// or PIL).
+// Covered: baseline / extended-sequential and progressive (jdphuff.c: DC / AC first and refinement scans, accumulated on the
+// host into dense coefficients, then sparsified) Huffman streams, 8-bit, grayscale or YCbCr with chroma 1x1 and luma 1x1 / 2x1
+// / 2x2 (4:4:4, 4:2:2, 4:2:0), restart intervals.  Anything else returns MC_ERR_UNSUPPORTED (callers fall back to
+// mc_jpeg_decode or PIL).
 namespace {
 
 constexpr int JPX_ZIGZAG[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,
@@ -42,6 +43,7 @@ struct JpxHuff {
 
 struct JpxHeader {
   int width = 0, height = 0, ncomp = 0, ri = 0, hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
+  bool progressive = false;
   JpxComp comp[3];
   uint16_t qt[4][64];          // natural order
   bool qt_present[4] = {false, false, false, false};
@@ -120,7 +122,8 @@ int jpx_parse(const uint8_t* d, size_t n, JpxHeader* H) {
         jpx_build_huff(tc ? &H->ac[th] : &H->dc[th], s + i + 1, s + i + 17, nsym);
         i += 17 + (size_t)nsym;
       }
-    } else if (m == 0xC0 || m == 0xC1) {
+    } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+      H->progressive = m == 0xC2;
       if (sl < 6 || s[0] != 8) return fail(MC_ERR_UNSUPPORTED, "JPEG: sample precision other than 8 bits");
       H->height = (s[1] << 8) | s[2];
       H->width = (s[3] << 8) | s[4];
@@ -134,15 +137,19 @@ int jpx_parse(const uint8_t* d, size_t n, JpxHeader* H) {
         H->comp[c].tq = s[8 + 3 * c];
       }
       have_frame = true;
-    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
-      return fail(MC_ERR_UNSUPPORTED, "JPEG: not a baseline (sequential Huffman) stream");
+    } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      return fail(MC_ERR_UNSUPPORTED, "JPEG: not a Huffman-coded baseline or progressive stream");
     } else if (m == 0xDD) {
       if (sl >= 2) H->ri = (s[0] << 8) | s[1];
     } else if (m == 0xEE && sl >= 12 && memcmp(s, "Adobe", 5) == 0) {
       adobe_transform = s[11];
     } else if (m == 0xDA) {
+      if (have_frame && H->progressive) {   // the scans are walked by jpx_decode_progressive
+        H->data_pos = pos + len;
+        break;
+      }
       if (!have_frame || sl < 1 || s[0] != H->ncomp || sl < 1 + 2 * (size_t)H->ncomp)
-        return fail(MC_ERR_UNSUPPORTED, "JPEG: multi-scan streams are not decoded exactly");
+        return fail(MC_ERR_UNSUPPORTED, "JPEG: multi-scan sequential streams are not decoded exactly");
       for (int c = 0; c < H->ncomp; ++c) {
         int ci = -1;
         for (int k = 0; k < H->ncomp; ++k)
@@ -184,7 +191,8 @@ int jpx_parse(const uint8_t* d, size_t n, JpxHeader* H) {
   }
   for (int c = 0; c < H->ncomp; ++c) {
     if (H->comp[c].tq > 3 || !H->qt_present[H->comp[c].tq]) return fail(MC_ERR_BAD_ARG, "JPEG: missing quantisation table");
-    if (H->comp[c].td > 3 || H->comp[c].ta > 3 || !H->dc[H->comp[c].td].present || !H->ac[H->comp[c].ta].present)
+    if (!H->progressive &&
+        (H->comp[c].td > 3 || H->comp[c].ta > 3 || !H->dc[H->comp[c].td].present || !H->ac[H->comp[c].ta].present))
       return fail(MC_ERR_BAD_ARG, "JPEG: missing Huffman table");
   }
   return MC_OK;
@@ -426,6 +434,7 @@ jpx_color_kernel(const uint8_t* __restrict__ planes, const JpxKernelArgs a, int 
 
 // scratch of the exact path, owned by the mc_jpeg handle
 struct JpxScratch {
+  std::vector<int16_t> dense;      // progressive streams: coefficients accumulate over the scans before they are sparsified
   uint32_t* h_entries = nullptr;   // pinned
   uint32_t* h_offsets = nullptr;   // pinned
   uint32_t* d_entries = nullptr;
@@ -445,7 +454,13 @@ void jpx_free(JpxScratch* s) {
   if (s->d_offsets) cudaFree(s->d_offsets);
   if (s->d_planes) cudaFree(s->d_planes);
   if (s->h2d_done) cudaEventDestroy(s->h2d_done);
-  *s = JpxScratch();
+  s->h_entries = s->h_offsets = s->d_entries = s->d_offsets = nullptr;
+  s->d_planes = nullptr;
+  s->h2d_done = nullptr;
+  s->cap_entries = s->cap_offsets = s->cap_planes = 0;
+  s->pending = false;
+  s->dense.clear();
+  s->dense.shrink_to_fit();
 }
 
 int jpx_reserve(JpxScratch* s, size_t entries, size_t offsets, size_t planes) {
@@ -541,6 +556,186 @@ int jpx_entropy_decode(const uint8_t* d, size_t n, const JpxHeader& H, const int
         }
       }
     }
+  }
+  *n_entries = pos;
+  return MC_OK;
+}
+
+// jdphuff.c: every scan of a progressive stream (DC / AC, first / refinement) accumulated into dense coefficients
+// coef[block][64] (natural order, zero-initialised by the caller; block = blk_base[c] + y * bx + x).  Huffman tables and the
+// restart interval may change between scans, so the markers are walked again from the top.
+int jpx_decode_progressive(const uint8_t* d, size_t n, JpxHeader& H, const int* blk_base, int16_t* coef) {
+  size_t pos = 2;
+  int ri = 0;
+  int scans = 0;
+  while (pos + 4 <= n) {
+    if (d[pos] != 0xFF) return fail(MC_ERR_BAD_ARG, "JPEG: marker expected");
+    while (pos < n && d[pos] == 0xFF) ++pos;
+    if (pos >= n) break;
+    const int m = d[pos++];
+    if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+    if (m == 0xD9) break;
+    if (pos + 2 > n) break;
+    const size_t len = ((size_t)d[pos] << 8) | d[pos + 1];
+    if (len < 2 || pos + len > n) return fail(MC_ERR_BAD_ARG, "JPEG: truncated segment");
+    const uint8_t* s = d + pos + 2;
+    const size_t sl = len - 2;
+    if (m == 0xC4) {
+      size_t i = 0;
+      while (i + 17 <= sl) {
+        const int tc = s[i] >> 4, th = s[i] & 15;
+        int nsym = 0;
+        for (int k = 0; k < 16; ++k) nsym += s[i + 1 + k];
+        if (tc > 1 || th > 3 || nsym > 256 || i + 17 + (size_t)nsym > sl) return fail(MC_ERR_BAD_ARG, "JPEG: bad DHT");
+        jpx_build_huff(tc ? &H.ac[th] : &H.dc[th], s + i + 1, s + i + 17, nsym);
+        i += 17 + (size_t)nsym;
+      }
+    } else if (m == 0xDD) {
+      if (sl >= 2) ri = (s[0] << 8) | s[1];
+    } else if (m == 0xDA) {
+      if (sl < 1) return fail(MC_ERR_BAD_ARG, "JPEG: bad SOS");
+      const int ns = s[0];
+      if (ns < 1 || ns > H.ncomp || sl < 4 + 2 * (size_t)ns) return fail(MC_ERR_BAD_ARG, "JPEG: bad SOS");
+      int ci[3], td[3], ta[3];
+      for (int c = 0; c < ns; ++c) {
+        ci[c] = -1;
+        for (int k = 0; k < H.ncomp; ++k)
+          if (H.comp[k].id == s[1 + 2 * c]) ci[c] = k;
+        if (ci[c] < 0) return fail(MC_ERR_BAD_ARG, "JPEG: scan names an unknown component");
+        td[c] = s[2 + 2 * c] >> 4;
+        ta[c] = s[2 + 2 * c] & 15;
+        if (td[c] > 3 || ta[c] > 3) return fail(MC_ERR_BAD_ARG, "JPEG: bad table index");
+      }
+      const int ss = s[1 + 2 * ns], se = s[2 + 2 * ns], ah = s[3 + 2 * ns] >> 4, al = s[3 + 2 * ns] & 15;
+      if (ss > se || se > 63 || (ss == 0 && se != 0) || (ss > 0 && ns != 1) || al > 13)
+        return fail(MC_ERR_BAD_ARG, "JPEG: bad progressive scan parameters");
+      for (int c = 0; c < ns; ++c) {
+        if (ss == 0 && ah == 0 && !H.dc[td[c]].present) return fail(MC_ERR_BAD_ARG, "JPEG: missing Huffman table");
+        if (ss > 0 && !H.ac[ta[c]].present) return fail(MC_ERR_BAD_ARG, "JPEG: missing Huffman table");
+      }
+      ++scans;
+      JpxBits br{d, pos + len, n};
+      // blocks of this scan: MCU-interleaved over the padded grids, or the component's own (unpadded) block grid
+      int gw, gh;
+      if (ns > 1) {
+        gw = H.mcux;
+        gh = H.mcuy;
+      } else {
+        const JpxComp& cp = H.comp[ci[0]];
+        const int cw = H.ncomp == 1 ? H.width : (H.width * cp.h + H.hmax - 1) / H.hmax;
+        const int chh = H.ncomp == 1 ? H.height : (H.height * cp.v + H.vmax - 1) / H.vmax;
+        gw = (cw + 7) / 8;
+        gh = (chh + 7) / 8;
+      }
+      int pred[3] = {0, 0, 0};
+      int eobrun = 0;
+      const int p1 = 1 << al, m1 = -(1 << al);
+      long count = 0;
+      for (int gy = 0; gy < gh; ++gy) {
+        for (int gx = 0; gx < gw; ++gx) {
+          if (ri && count && count % ri == 0) {
+            br.restart();
+            pred[0] = pred[1] = pred[2] = 0;
+            eobrun = 0;
+          }
+          ++count;
+          for (int c = 0; c < ns; ++c) {
+            const JpxComp& cp = H.comp[ci[c]];
+            const int vb = ns > 1 ? cp.v : 1, hb = ns > 1 ? cp.h : 1;
+            for (int by = 0; by < vb; ++by) {
+              for (int bx = 0; bx < hb; ++bx) {
+                int16_t* blk = coef + (size_t)(blk_base[ci[c]] + (gy * vb + by) * cp.bx + (gx * hb + bx)) * 64;
+                if (ss == 0) {
+                  if (ah == 0) {
+                    int sz = jpx_decode_symbol(br, H.dc[td[c]]);
+                    if (sz > 15) sz = 0;
+                    pred[c] += sz ? jpx_extend(br.get(sz), sz) : 0;
+                    blk[0] = (int16_t)(pred[c] * (1 << al));
+                  } else if (br.get(1)) {
+                    blk[0] |= (int16_t)p1;
+                  }
+                  continue;
+                }
+                const JpxHuff& ha = H.ac[ta[c]];
+                if (ah == 0) {   // AC first
+                  if (eobrun > 0) {
+                    --eobrun;
+                    continue;
+                  }
+                  for (int k = ss; k <= se; ++k) {
+                    const int rs = jpx_decode_symbol(br, ha);
+                    const int r = rs >> 4, sz = rs & 15;
+                    if (sz) {
+                      k += r;
+                      if (k > 63) break;
+                      blk[JPX_ZIGZAG[k]] = (int16_t)(jpx_extend(br.get(sz), sz) * (1 << al));
+                    } else if (r == 15) {
+                      k += 15;
+                    } else {
+                      eobrun = (1 << r) + (r ? br.get(r) : 0) - 1;
+                      break;
+                    }
+                  }
+                  continue;
+                }
+                // AC refinement (decode_mcu_AC_refine)
+                int k = ss;
+                if (eobrun == 0) {
+                  for (; k <= se; ++k) {
+                    const int rs = jpx_decode_symbol(br, ha);
+                    int r = rs >> 4, sz = rs & 15;
+                    if (sz) {
+                      sz = br.get(1) ? p1 : m1;   // the size must be 1; any other value is treated the same way (libjpeg warns)
+                    } else if (r != 15) {
+                      eobrun = (1 << r) + (r ? br.get(r) : 0);
+                      break;
+                    }
+                    do {
+                      int16_t* cf = blk + JPX_ZIGZAG[k];
+                      if (*cf != 0) {
+                        if (br.get(1) && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
+                      } else if (--r < 0) {
+                        break;
+                      }
+                      ++k;
+                    } while (k <= se);
+                    if (sz && k <= 63) blk[JPX_ZIGZAG[k]] = (int16_t)sz;
+                  }
+                }
+                if (eobrun > 0) {
+                  for (; k <= se; ++k) {
+                    int16_t* cf = blk + JPX_ZIGZAG[k];
+                    if (*cf != 0 && br.get(1) && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
+                  }
+                  --eobrun;
+                }
+              }
+            }
+          }
+        }
+      }
+      // on to the next marker after the entropy-coded segment
+      size_t q = pos + len;
+      while (q + 1 < n && !(d[q] == 0xFF && d[q + 1] != 0 && !(d[q + 1] >= 0xD0 && d[q + 1] <= 0xD7))) ++q;
+      pos = q;
+      continue;
+    }
+    pos += len;
+  }
+  if (!scans) return fail(MC_ERR_BAD_ARG, "JPEG: no scan");
+  return MC_OK;
+}
+
+// dense coefficients -> the sparse stream of the kernels
+int jpx_sparsify(const int16_t* coef, int total, uint32_t* entries, size_t cap_entries, uint32_t* offsets, size_t* n_entries) {
+  size_t pos = 0;
+  for (int b = 0; b < total; ++b) {
+    if (pos + 64 > cap_entries) return fail(MC_ERR_BAD_ARG, "JPEG: more coefficients than the stream can hold (corrupt data)");
+    offsets[2 * b] = (uint32_t)pos;
+    const int16_t* blk = coef + (size_t)b * 64;
+    for (int k = 0; k < 64; ++k)
+      if (blk[k]) entries[pos++] = ((uint32_t)k << 16) | ((uint32_t)blk[k] & 0xFFFFu);
+    offsets[2 * b + 1] = (uint32_t)pos;
   }
   *n_entries = pos;
   return MC_OK;

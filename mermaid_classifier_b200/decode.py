@@ -7,11 +7,11 @@ COMPRESSED bytes go to the library (``mc_jpeg_decode``: Huffman decoding on the 
 conversion on the GPU through nvJPEG) and come out as an RGB8 device image that ``EfficientNetExtractor.extract_device``
 reads directly; the decoded image never crosses PCIe.
 
-Two device paths.  ``exact=True`` (default) is ``mc_jpeg_decode_exact``: the library's own baseline decoder -- entropy
+Two device paths.  ``exact=True`` (default) is ``mc_jpeg_decode_exact``: the library's own baseline + progressive decoder -- entropy
 decoding on the calling thread into a sparse coefficient stream, then libjpeg-turbo's integer IDCT, fancy chroma upsampling
 and YCbCr -> RGB arithmetic restated as kernels -- whose bytes EQUAL PIL's (``tests/test_gpu_decode.py``; the CPU restatement
-``oracle/jpeg.py`` is pinned to PIL byte for byte by ``tests/test_oracle_jpeg.py``).  Streams it does not cover (progressive,
-CMYK, unusual sampling factors) fall through to nvJPEG (``mc_jpeg_decode``), whose inverse DCT and chroma interpolation are
+``oracle/jpeg.py`` is pinned to PIL byte for byte by ``tests/test_oracle_jpeg.py``).  Streams it does not cover (CMYK,
+arithmetic coding, unusual sampling factors) fall through to nvJPEG (``mc_jpeg_decode``), whose inverse DCT and chroma interpolation are
 not libjpeg-turbo's bit for bit: against PIL its bytes differ by a few grey levels (the bound is stated and checked in the same
 test file).  Files that are not JPEG streams (the PNG stand-ins of the tests) fall back to PIL + one host-to-device copy.
 """

@@ -117,8 +117,8 @@ def _photo(rng, h, w, noise=18.0):
 def test_jpeg_decode_exact_equals_pil():
     """``mc_jpeg_decode_exact``: every byte equal to PIL / libjpeg-turbo -- the decoder of the reference's ``load_image``
     (``pyspacer/annotation.py:235``) -- for 4:4:4 / 4:2:2 / 4:2:0 / grayscale, odd and tiny sizes, extreme qualities,
-    optimised tables and restart intervals; and to the CPU oracle (``oracle/jpeg.py``), which the same fixtures pin to PIL
-    on the CPU side.  Progressive streams fall through to nvJPEG."""
+    optimised tables, restart intervals and progressive streams; and to the CPU oracle (``oracle/jpeg.py``), which the same
+    fixtures pin to PIL on the CPU side."""
     from oracle import jpeg as oj
 
     rng = np.random.default_rng(11)
@@ -155,12 +155,21 @@ def test_jpeg_decode_exact_equals_pil():
     # back-to-back decodes reuse the pinned staging buffers safely
     a, b = dec.decode(data), dec.decode(_jpeg(big[::-1].copy(), quality=90, subsampling=2))
     assert np.array_equal(a.cpu().numpy(), _pil(data)) and not torch.equal(a, b)
-    # progressive: not covered by the exact decoder -> nvJPEG, within its bound
+    # progressive streams: scans accumulated on the host, the same device IDCT / upsampling / colour stages
+    for hw, kw in [((97, 131), dict(quality=90, subsampling=0)), ((45, 67), dict(quality=30, subsampling=2, optimize=True)),
+                   ((120, 90), dict(quality=75, subsampling=1, restart_marker_blocks=5)), ((1200, 1600), dict(quality=88, subsampling=2))]:
+        buf = io.BytesIO()
+        Image.fromarray(_photo(rng, *hw)).save(buf, format="JPEG", progressive=True, **kw)
+        got = dec.decode(buf.getvalue()).cpu().numpy()
+        assert dec.last_path == "exact" and np.array_equal(got, _pil(buf.getvalue())), kw
+    # four-component (CMYK) streams are outside the exact decoder: nvJPEG or an error, never wrong bytes labelled exact
     buf = io.BytesIO()
-    Image.fromarray(im).save(buf, format="JPEG", quality=90, subsampling=0, progressive=True)
-    got = dec.decode(buf.getvalue()).cpu().numpy()
-    assert dec.last_path == "nvjpeg"
-    assert np.abs(got.astype(np.int16) - _pil(buf.getvalue()).astype(np.int16)).max() <= 8
+    Image.fromarray(np.dstack([im, im[:, :, 0]]), mode="CMYK").save(buf, format="JPEG", quality=80)
+    try:
+        dec.decode(buf.getvalue())
+        assert dec.last_path == "nvjpeg"
+    except (ValueError, RuntimeError):
+        pass
     dec.close()
 
 

@@ -45,11 +45,50 @@ def test_host_entropy_decoder_matches_oracle_and_pil():
         assert np.array_equal(rgb, np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))), kw
 
 
+def test_host_progressive_decoder_matches_oracle_and_pil():
+    """Progressive streams (jdphuff.c: DC / AC first and refinement scans, EOB runs, per-scan tables, restarts)."""
+    rng = np.random.default_rng(8)
+    cases = [(_photo(rng, h, w), dict(quality=q, subsampling=ss, progressive=True, **extra))
+             for (h, w) in [(48, 64), (45, 67), (8, 8), (1, 1), (100, 3), (5, 4), (31, 49)] for ss in (0, 1, 2)
+             for q, extra in ((95, {}), (40, dict(optimize=True)), (8, dict(restart_marker_blocks=3)))]
+    cases.append((_photo(rng, 33, 47)[:, :, 0], dict(quality=75, progressive=True)))
+    for arr, kw in cases:
+        data = _jpeg(arr, **kw)
+        info, coefs = jpeg_coefficients(data)
+        hdr = oj.parse(data)
+        assert hdr["frame"]["progressive"] and (info["height"], info["width"]) == arr.shape[:2]
+        want = oj.decode_coefficients_progressive(data, hdr)
+        for a, b in zip(coefs, want):
+            assert a.shape == b.shape and np.array_equal(a, b), kw
+        rgb = oj.rgb_from_planes(oj.planes_from_coefficients([c.astype(np.int32) for c in coefs], hdr), hdr)
+        assert np.array_equal(rgb, np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))), kw
+
+
+def test_host_progressive_decoder_survives_damaged_streams():
+    rng = np.random.default_rng(9)
+    good = _jpeg(_photo(rng, 96, 128), quality=85, subsampling=2, progressive=True)
+    for cut in range(300, len(good), 211):
+        try:
+            jpeg_coefficients(good[:cut])
+        except (ValueError, RuntimeError):
+            pass
+    for _ in range(60):
+        bad = bytearray(good)
+        for pos in rng.integers(20, len(good) - 2, size=10):
+            bad[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            jpeg_coefficients(bytes(bad))
+        except (ValueError, RuntimeError):
+            pass
+
+
 def test_host_entropy_decoder_rejects_what_it_does_not_cover():
     rng = np.random.default_rng(6)
     im = _photo(rng, 40, 40)
-    with pytest.raises(RuntimeError):   # MC_ERR_UNSUPPORTED
-        jpeg_coefficients(_jpeg(im, quality=80, progressive=True))
+    cmyk = io.BytesIO()
+    Image.fromarray(np.dstack([im, im[:, :, 0]]), mode="CMYK").save(cmyk, format="JPEG", quality=80)
+    with pytest.raises(RuntimeError):   # MC_ERR_UNSUPPORTED: four components
+        jpeg_coefficients(cmyk.getvalue())
     with pytest.raises(ValueError):     # MC_ERR_BAD_ARG
         jpeg_coefficients(b"\x89PNG\r\n not a jpeg stream")
     good = _jpeg(im, quality=80)
