@@ -324,6 +324,7 @@ int forward(mc_extractor* h, int nb, float* feats_dev, cudaStream_t st) {
         fa.out = D;
         fa.pool_partial = h->d_pool;
         fa.nb = nb;
+        fa.num_sms = h->tc ? h->tc->num_sms : 148;
         {
           ProfScope ps(h, 2 + 4 * (int)bi, st);
           if ((rc = fused_launch<T>(fl, Xc, b.c_in, b.h_in, fa, st))) return rc;

@@ -98,6 +98,7 @@ struct FusedArgs {
   void* out;               // [n][Hout][Hout][C]
   float* pool_partial;     // [n][nbands][C]
   int nb;
+  int num_sms = 148;       // host side only: the launch takes one CTA per SM
 };
 
 template <typename T, int SHAPE>
@@ -148,12 +149,28 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   constexpr int WARP_EPI0 = WARP_TR0 + FUSED_TR_WARPS;        // 10..17: warp & 3 = TMEM lane quarter
   constexpr int WARP_MMA = WARP_EPI0 + FUSED_EPI_WARPS, WARP_TMA = WARP_MMA + 1;
 
-  const int band = blockIdx.y;
+  // Work unit = (patch, band) of this CTA's channel slice.  The grid is (slices, workers) with slices * workers <= the SM
+  // count: one CTA per SM for the whole launch, so barrier / TMEM / weight set-up and the pipeline fill are paid once and not
+  // once per unit.  Worker w takes units w, w + workers, ...; the CTAs of one worker (the slices) walk the same units at the
+  // same time and share the x tiles in L2.
+  constexpr int NBANDS = SH.nbands;
   const int cb0 = blockIdx.x * CB;
-  const int y0 = band * RPB, y1 = min(HOUT, y0 + RPB);
-  const int nsteps = (y1 - 1 - y0) * S + K;              // input rows this band consumes
-  const int ntiles = (nsteps + R - 1) / R;
-  const int iy0 = y0 * S - PAD;
+  const int worker = blockIdx.y, nworkers = gridDim.y;
+  const int nunits = a.nb * NBANDS;
+  struct Unit {
+    int n, band, y0, y1, nsteps, ntiles, iy0;
+  };
+  auto unit_of = [&](int u) {
+    Unit q;
+    q.n = u / NBANDS;
+    q.band = u - q.n * NBANDS;
+    q.y0 = q.band * RPB;
+    q.y1 = min(HOUT, q.y0 + RPB);
+    q.nsteps = (q.y1 - 1 - q.y0) * S + K;                // input rows this band consumes
+    q.ntiles = (q.nsteps + R - 1) / R;
+    q.iy0 = q.y0 * S - PAD;
+    return q;
+  };
 
   for (int i = tid; i < CB; i += FUSED_THREADS) bias_s[i] = a.b_exp[cb0 + i] * (F32 ? 1.f : 0.5f);
   // pad columns of every ring row are zero for the whole launch (the epilogue only writes image columns)
@@ -204,7 +221,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       pdl_wait();
       int hs = 0;
       uint32_t hph = 0;
-      for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
+      for (int u = worker; u < nunits; u += nworkers) {
+        const Unit q = unit_of(u);
+        const int n = q.n, ntiles = q.ntiles, iy0 = q.iy0;
         for (int tt = 0; tt < ntiles; ++tt) {
           ptx::mbar_wait(&a_empty[hs], hph ^ 1);
           ptx::mbar_expect_tx(&a_full[hs], (uint32_t)(KCH * FUSED_TILE_PIX * 128));
@@ -227,7 +246,8 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       ptx::tc_fence_after();
       int li = 0, hs = 0;
       uint32_t hph = 0;
-      for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
+      for (int u = worker; u < nunits; u += nworkers) {
+        const int ntiles = unit_of(u).ntiles;
         for (int tt = 0; tt < ntiles; ++tt, ++li) {
           const int as = li & 1;
           const uint32_t use = (uint32_t)(li >> 1) & 1u;
@@ -284,7 +304,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     int li = 0;
     int g_rows = 0;                                       // ring rows produced before this (patch, tile)
     uint32_t use = 0;                                     // phase of this set's accumulator stage
-    for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
+    for (int u = worker; u < nunits; u += nworkers) {
+      const Unit q = unit_of(u);
+      const int ntiles = q.ntiles, nsteps = q.nsteps, iy0 = q.iy0;
       for (int tt = 0; tt < ntiles; ++tt, ++li) {
         if ((li & 1) != set) continue;
         const int t_my = tt * R + pr;                     // row step of this pixel inside the band
@@ -366,7 +388,8 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       int li = 0, hs = 0;
       uint32_t hph = 0;
       constexpr int NCH = SH.Cin / 4;                    // 16-byte chunks of a row that hold real data
-      for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
+      for (int u = worker; u < nunits; u += nworkers) {
+        const int ntiles = unit_of(u).ntiles;
         for (int tt = 0; tt < ntiles; ++tt, ++li) {
           const int as = li & 1;
           ptx::mbar_wait(&lo_empty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
@@ -420,7 +443,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint32_t ph = 0;
     int pbuf = 0;
     constexpr int cons_threads = FUSED_CONS_WARPS * 32;
-    for (int n = blockIdx.z; n < a.nb; n += gridDim.z) {
+    for (int u = worker; u < nunits; u += nworkers) {
+      const Unit q = unit_of(u);
+      const int n = q.n, y0 = q.y0, y1 = q.y1, nsteps = q.nsteps;
       T* out_n = (T*)a.out + ((int64_t)n * HOUT * HOUT + ox0) * C + c;
       float2 acc[NL][TW];
 #pragma unroll
@@ -492,7 +517,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int i = tid; i < CB; i += cons_threads) {
         float sum = 0.f;
         for (int pp = 0; pp < PTC; ++pp) sum += ps[pp * CB + i];
-        a.pool_partial[((int64_t)n * gridDim.y + blockIdx.y) * C + cb0 + i] = sum;
+        a.pool_partial[((int64_t)n * NBANDS + q.band) * C + cb0 + i] = sum;
       }
       pbuf ^= 1;
     }
@@ -588,9 +613,12 @@ inline int fused_launch_shape(FusedLayer& l, int slot, const FusedArgs& a, cudaS
     static std::atomic<unsigned long long> attr_mask{0};
     if (first_use_on_device(attr_mask))
       MC_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<T, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh.smem));
-    const int per_patch = sh.cz * sh.nbands;
-    const int gz = std::max(1, std::min(a.nb, 3000 / per_patch));
-    MC_CUDA(launch_pdl(PDL_FUSED, mbconv_fused_kernel<T, SHAPE>, dim3(sh.cz, sh.nbands, gz), dim3(FUSED_THREADS), sh.smem, st, l.tmX[slot], l.tmW, l.tmWlo, a));
+    // one CTA per SM (the kernel's shared memory allows no second one): slices x workers <= SMs.  MC_FUSED_WORKERS overrides
+    // the workers per slice (experiments: 1000 ~ the earlier one-or-two-units-per-CTA grid)
+    static const int workers_env = getenv("MC_FUSED_WORKERS") ? atoi(getenv("MC_FUSED_WORKERS")) : 0;
+    int workers = workers_env > 0 ? workers_env : std::max(1, a.num_sms / sh.cz);
+    workers = std::max(1, std::min(workers, a.nb * sh.nbands));
+    MC_CUDA(launch_pdl(PDL_FUSED, mbconv_fused_kernel<T, SHAPE>, dim3(sh.cz, workers), dim3(FUSED_THREADS), sh.smem, st, l.tmX[slot], l.tmW, l.tmWlo, a));
     MC_CHECK_LAUNCH();
     return MC_OK;
   }
