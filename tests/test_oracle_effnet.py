@@ -100,3 +100,55 @@ def test_batched_equals_unbatched(backbone_sd):
     a = effnet.extract_features(backbone_sd, x)
     b = effnet.extract_features_batched(backbone_sd, x, batch_size=2)
     assert torch.allclose(a, b, atol=1e-5)
+
+
+def _hf_model(sd):
+    """A second, independent construction: the Hugging Face ``transformers`` port of the Keras EfficientNet
+    (``modeling_efficientnet.py``), which carries the TF-"SAME" asymmetric padding natively (ZeroPad2d + valid convs
+    on the stride-2 layers), built from a B0 config with random init and loaded through a pyspacer -> HF key map."""
+    tr = pytest.importorskip("transformers")
+    cfg = tr.EfficientNetConfig(width_coefficient=1.0, depth_coefficient=1.0, image_size=224, hidden_dim=1280,
+                                batch_norm_eps=1e-3, hidden_act="swish")
+    net = tr.EfficientNetModel(cfg).eval()
+    sd = effnet.strip_module_prefix(sd)
+    out = {}
+
+    def conv(dst, src):
+        out[dst + ".weight"] = sd[src + ".weight"]
+        if src + ".bias" in sd:
+            out[dst + ".bias"] = sd[src + ".bias"]
+
+    def bn(dst, src):
+        for f in ("weight", "bias", "running_mean", "running_var"):
+            out[f"{dst}.{f}"] = sd[f"{src}.{f}"]
+
+    conv("embeddings.convolution", "_conv_stem")
+    bn("embeddings.batchnorm", "_bn0")
+    for i, blk in enumerate(effnet.b0_blocks()):
+        p, q = f"_blocks.{i}.", f"encoder.blocks.{i}."
+        if blk.expand != 1:
+            conv(q + "expansion.expand_conv", p + "_expand_conv")
+            bn(q + "expansion.expand_bn", p + "_bn0")
+        conv(q + "depthwise_conv.depthwise_conv", p + "_depthwise_conv")
+        bn(q + "depthwise_conv.depthwise_norm", p + "_bn1")
+        conv(q + "squeeze_excite.reduce", p + "_se_reduce")
+        conv(q + "squeeze_excite.expand", p + "_se_expand")
+        conv(q + "projection.project_conv", p + "_project_conv")
+        bn(q + "projection.project_bn", p + "_bn2")
+    conv("encoder.top_conv", "_conv_head")
+    bn("encoder.top_bn", "_bn1")
+    missing, unexpected = net.load_state_dict(out, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    return net
+
+
+def test_oracle_matches_transformers_keras_port(backbone_sd):
+    net = _hf_model(backbone_sd)
+    im = synth.synth_image(synth.DEFAULT_SEED, 2, 420, 380)
+    pts = synth.synth_points(synth.DEFAULT_SEED, 2, 420, 380, 6, corners=True)
+    x = torch.from_numpy(crop.normalize_patches(crop.crop_patches(im, pts)))
+    with torch.no_grad():
+        want = net(pixel_values=x).pooler_output
+    got = effnet.extract_features(backbone_sd, x)
+    assert got.shape == want.shape == (len(pts), 1280)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-4), (got - want).abs().max()
