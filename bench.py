@@ -55,8 +55,8 @@ B0 = [  # (k, stride, expand, c_in, c_out, h_in)
 
 def fused_blocks(e: int) -> int:
     """Bit mask of the MBConv blocks whose expand + depthwise run as ONE kernel: the library's defaults (csrc/api.cu
-    MC_FUSE_DEFAULT_FP32 = b1-b3 in fp32 mode, MC_FUSE_DEFAULT = b1 in bf16 mode) unless MC_FUSE_MASK overrides them."""
-    return int(os.environ.get("MC_FUSE_MASK", "e" if e == 4 else "2"), 16)
+    MC_FUSE_DEFAULT_FP32 = b1-b3 in fp32 mode, MC_FUSE_DEFAULT = b1-b2 in bf16 mode) unless MC_FUSE_MASK overrides them."""
+    return int(os.environ.get("MC_FUSE_MASK", "e" if e == 4 else "6"), 16)
 
 
 def layer_bytes(e: int) -> dict[int, tuple[str, float]]:

@@ -24,8 +24,9 @@
 using namespace mc;
 
 #ifndef MC_FUSE_DEFAULT
-#define MC_FUSE_DEFAULT 0x2u   // blocks fused by default (bit b = block b): b1 (measured -28 % fp32 / -33 % bf16 against expand + depthwise);
-                               // b2 / b3 measure equal or slower fused (stride-1 consumers are the bound), b4 does not fit in fp32
+#define MC_FUSE_DEFAULT 0x6u   // blocks fused by default in bf16 mode (bit b = block b): b1 (-33 % against expand + depthwise) and, since the
+                               // persistent one-CTA-per-SM form of the fused kernel, b2 (+1.8 % on the step: 116.6 -> 118.7 k patches/s);
+                               // b3 on top measures the same (118.8 k) and stays on the two-kernel path; b4 does not fit in fp32
 #endif
 #ifndef MC_FUSE_DEFAULT_FP32
 // fp32 mode runs into the board's power cap (~1 kW, SM clock 1.72-1.75 GHz): with b2 and b3 fused as well the step moves

@@ -583,6 +583,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t ph = 0;
       int li = 0;
       long long w_tempty = 0, w_full = 0;
+      [[maybe_unused]] long long t_commit = 0, t_issue = 0;   // MC_TC_TIMING: cycles the issuing thread spends in tcgen05.commit / tcgen05.mma
       const long long t_begin = ptx::tc_clock();
       if (w_res) {
         ptx::mbar_wait(wbar, 0);
@@ -606,6 +607,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                       : a_lo + (uint32_t)(Cfg::A_BYTES >> 4);
           const int krem = p.K - kc * Cfg::KC;
           const int ksteps = (p.exp_flags & 16) ? 0 : (min(krem, Cfg::KC) + Cfg::UK - 1) / Cfg::UK;
+          const long long t_i0 = ptx::tc_clock();
 #pragma unroll
           for (int ks = 0; ks < Cfg::KC / Cfg::UK; ++ks) {
             if (ks < ksteps) {
@@ -635,21 +637,28 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           }
+          const long long t_c0 = ptx::tc_clock();
+          t_issue += t_c0 - t_i0;
           ptx::mma_commit(&empty[s]);
           if (TS) ptx::mma_commit(&lo_empty[cc & (TS_SLOTS - 1u)]);
           else if (Cfg::TF32) ptx::mma_commit(&lo_empty[cc & 1u]);
+          t_commit += ptx::tc_clock() - t_c0;
           if (++s == S) {
             s = 0;
             ph ^= 1;
           }
         }
+        const long long t_c1 = ptx::tc_clock();
         ptx::mma_commit(&tfull[as]);
+        t_commit += ptx::tc_clock() - t_c1;
       }
       if (MC_TC_TIMING && p.dbg && blockIdx.x == 0) {
         p.dbg[2] = w_tempty;
         p.dbg[3] = w_full;
         p.dbg[4] = ptx::tc_clock() - t_begin;
         p.dbg[5] = li;
+        p.dbg[24] = t_commit;
+        p.dbg[25] = t_issue;
       }
     }
   } else if (warp < ntw) {
@@ -881,6 +890,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int quarter = warp & 3;     // TMEM lanes 32*quarter .. +31 are visible to this warp
     int li = 0;
     long long w_tfull = 0, t_work = 0;
+    [[maybe_unused]] long long t_ld = 0;
     const long long t_begin = ptx::tc_clock();
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++li) {
       if (li % n_groups != eg) continue;           // not this group's item
@@ -1136,6 +1146,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ptx::tmem_ld16x256b_x4(taddr + (uint32_t)c0, v[0]);                      // lanes  0..15 of this warp's quarter
           ptx::tmem_ld16x256b_x4(taddr + (16u << 16) + (uint32_t)c0, v[1]);        // lanes 16..31
           ptx::tmem_ld_wait();
+          t_ld += ptx::tc_clock() - t_item;
         } else {
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[0][e] = v[1][e] = 0u;
@@ -1202,6 +1213,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       p.dbg[8 + 3 * eg] = w_tfull;
       p.dbg[9 + 3 * eg] = t_work;
       p.dbg[10 + 3 * eg] = ptx::tc_clock() - t_begin;
+      p.dbg[26 + eg] = t_ld;
     }
   }
   ptx::tc_fence_before();
@@ -1568,8 +1580,8 @@ inline int pw_tc_run(PwTcPlan* plan, int id, const void* A, int64_t a_row_off, c
     if (printed++ < 3) {
       const double it = (double)std::max<long long>(d[5], 1);
       fprintf(stderr, "[MC_TC_DBG layer %d] M=%lld N=%d K=%d BN=%d stages=%d items/CTA=%lld | per item (cycles): producer wait_empty %.0f total %.0f | "
-                      "mma wait_tempty %.0f wait_full %.0f total %.0f | transform wait_full %.0f total %.0f |",
-              id, (long long)M, l.N, l.K, l.BN, a.stages, d[5], d[0] / it, d[1] / it, d[2] / it, d[3] / it, d[4] / it, d[6] / it, d[7] / it);
+                      "mma wait_tempty %.0f wait_full %.0f commits %.0f issue %.0f epi0_ld %.0f total %.0f | transform wait_full %.0f total %.0f |",
+              id, (long long)M, l.N, l.K, l.BN, a.stages, d[5], d[0] / it, d[1] / it, d[2] / it, d[3] / it, d[24] / it, d[25] / it, d[26] / it, d[4] / it, d[6] / it, d[7] / it);
       for (int g = 0; g < (gated ? 2 : 4); ++g)
         fprintf(stderr, " epi%d wait_tfull %.0f work %.0f total %.0f |", g, d[8 + 3 * g] / it, d[9 + 3 * g] / it, d[10 + 3 * g] / it);
       fprintf(stderr, "\n");

@@ -432,9 +432,9 @@ def test_pooled_head_conv_matches_two_launch_form(backbone_sd, mode, monkeypatch
     assert launches > 0
 
 
-@pytest.mark.parametrize("mode,mask", [("fp32", "0"), ("fp32", "2"), ("fp32", "e"), ("bf16", "2"), ("bf16", "e")])
+@pytest.mark.parametrize("mode,mask", [("fp32", "0"), ("fp32", "2"), ("fp32", "e"), ("bf16", "2"), ("bf16", "6"), ("bf16", "e")])
 def test_fused_expand_depthwise_matches_two_kernel_path(backbone_sd, mode, mask, monkeypatch):
-    """MC_FUSE_MASK routes MBConv blocks through mbconv_fused_kernel (expand + depthwise in one launch; default: b1).
+    """MC_FUSE_MASK routes MBConv blocks through mbconv_fused_kernel (expand + depthwise in one launch; defaults: b1-b3 in fp32 mode, b1-b2 in bf16 mode).
     Against the two-kernel path the features agree to fp32 rounding (BN scale folded into the weights, different SE pool
     partial order); against the oracle both meet the mode's bound."""
     im = synth.synth_image(13, 2, 500, 700)
