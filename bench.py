@@ -378,6 +378,9 @@ def run_b200(args, rank: int, world: int, local: int):
         "e2e": {"value": e2e_value, "unit": "point-patches/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                 "ms_per_step": ms_e2e / args.steps, "host_pool_images": e2e["pool"], "images_per_group": e2e["group"],
                 "api": "EfficientNetExtractor.extract_many -> mc_extract_images_host (one call per step)",
+                "h2d": ("whole images from pinned host memory (MC_SPARSE_H2D=0)" if os.environ.get("MC_SPARSE_H2D") == "0" else
+                        "per point, the clipped 224x224 window its patch reads, from the pinned host images (an image whose "
+                        "windows exceed 60 % of its pixels goes whole); bytes counted by the library"),
                 "labels_checksum": e2e["labels_checksum"]},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -141,7 +141,8 @@ int mc_extract_image_host(mc_extractor* h, const uint8_t* img_host, int32_t heig
  *      for a whole list of decoded images in one call.  images_host[i].data are HOST pointers (pinned memory is
  *      DMA'd directly, pageable memory goes through the handle's pinned staging buffers); points_host must be
  *      grouped by image (non-decreasing .image).  Inside: a three-slot pipeline on the handle's own copy streams --
- *      one cudaMemcpyAsync per image into a device arena, the backbone (+ head) on `stream`, features / labels
+ *      one cudaMemcpyAsync per image (or, for sparsely annotated images, one 2-D copy per point of the window its
+ *      patch reads: mc_upload_window) into a device arena, the backbone (+ head) on `stream`, features / labels
  *      back -- so the copy of one group of images overlaps the compute of the previous one.  feats_host
  *      (n_points x 1280 fp32) and labels_host (n_points int32, needs `head`) may each be NULL.  Synchronises
  *      before returning. ------------------------------------------------------------------------------------ */
@@ -150,6 +151,14 @@ int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_image* image
                            int32_t* labels_host, void* stream);
 /* Bytes copied host->device / device->host and image groups of the last mc_extract_images_host call. */
 int mc_extractor_pipe_stats(const mc_extractor* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* groups);
+/* Host-only.  The window of a height x width image that mc_extract_images_host uploads for a point when the image's points
+ * need under 60 % of its pixels: rows [*r0, *r0 + *h) x columns [*c0, *c0 + *w) hold every pixel crop_patches reads for the
+ * 224 x 224 patch centred on (row, col) -- reflection at the image border included -- so cropping the window around
+ * (row - *r0, col - *c0) gives the patch of the whole image byte for byte (tests/test_cabi.py checks this against the oracle
+ * for every centre of small images).  Replaces nothing in the reference (it pads and slices whole images on the host,
+ * SURVEY 8a A2); it is the data-movement rule of the host pipeline, exported so that it can be tested without a GPU. */
+int mc_upload_window(int32_t height, int32_t width, int32_t row, int32_t col, int32_t* r0, int32_t* c0, int32_t* h,
+                     int32_t* w);
 
 /* ---- (f)2: image decode feeding the crop kernel: spacer.storage.load_image (call site
  *      mermaid_classifier/pyspacer/annotation.py:235; inside spacer.tasks.extract_features,

@@ -137,6 +137,7 @@ struct mc_extractor {
   int64_t launches = 0;
   int64_t l2_budget = 0;  // bytes of per-chunk working set kept L2-resident (0 = no chunking)
   bool no_pool_fusion = false;   // MC_NO_POOL_FUSION: head conv and average pool as two launches (A/B timing)
+  bool sparse_h2d = true;        // MC_SPARSE_H2D=0: the host pipeline uploads every image whole (A/B of the per-point window upload)
   int tap_layer = -1;
   float* tap_out = nullptr;
   int64_t tap_cap = 0;
@@ -588,6 +589,7 @@ int mc_extractor_create(const float* params, int64_t n_params, int32_t mode, int
   h->no_pool_fusion = getenv("MC_NO_POOL_FUSION") != nullptr;
   h->fuse_mask = mode == MC_MODE_FP32 ? MC_FUSE_DEFAULT_FP32 : MC_FUSE_DEFAULT;
   if (const char* env = getenv("MC_FUSE_MASK")) h->fuse_mask = (unsigned)strtoul(env, nullptr, 16);
+  if (const char* env = getenv("MC_SPARSE_H2D")) h->sparse_h2d = atoi(env) != 0;
   if ((rc = pw_tc_build(&h->tc, h->net, params, h->d_params, mode, max_batch, device, (unsigned)(tc_mask & 0xffffffffu),
                         (unsigned)(tc_mask >> 32)))) {
     mc_extractor_destroy(h);

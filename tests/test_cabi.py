@@ -40,6 +40,41 @@ def test_check_extract_inputs_host_only():
         _lib.check(lib.mc_check_extract_inputs(100, 200, rc.ctypes.data, 1001, 0, 0))
 
 
+@pytest.mark.parametrize("hw", [(1, 1), (1, 300), (5, 3), (100, 400), (112, 113), (113, 112), (150, 260), (223, 224),
+                                (224, 225), (300, 340), (460, 230)])
+def test_upload_window_holds_every_pixel_of_the_patch(hw):
+    """mc_upload_window (the data-movement rule of mc_extract_images_host for sparsely annotated images): cropping the
+    window around the re-expressed point gives the bytes of the whole-image crop -- checked with the oracle's crop_patches
+    for the centres where reflection happens (all four borders and corners, +-2 around the 112 / 113 thresholds) and a
+    grid of interior ones, on images smaller than, equal to and larger than a patch."""
+    from oracle import crop as ocrop
+
+    H, W = hw
+    lib = _lib.load()
+    rng = np.random.default_rng(H * 1000 + W)
+    im = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+
+    def axis(n):
+        c = {0, 1, 2, n - 1, n - 2, n - 3, n // 2}
+        for t in (110, 111, 112, 113, 114):
+            c.update({t, n - 1 - t})
+        return sorted(x for x in c if 0 <= x < n)
+
+    pts = [(r, c) for r in axis(H) for c in axis(W)]
+    want = ocrop.crop_patches(im, pts)
+    out = (C.c_int32 * 4)()
+    ptr = [C.cast(C.byref(out, 4 * i), C.c_void_p) for i in range(4)]
+    for k, (r, c) in enumerate(pts):
+        _lib.check(lib.mc_upload_window(H, W, r, c, *ptr))
+        r0, c0, h, w = out[0], out[1], out[2], out[3]
+        assert 0 <= r0 <= r < r0 + h <= H and 0 <= c0 <= c < c0 + w <= W
+        assert h <= 225 and w <= 225
+        got = ocrop.crop_patches(np.ascontiguousarray(im[r0:r0 + h, c0:c0 + w]), [(r - r0, c - c0)])[0]
+        assert np.array_equal(got, want[k]), (hw, (r, c), (r0, c0, h, w))
+    with pytest.raises(_lib.RowColumnInvalidError):
+        _lib.check(lib.mc_upload_window(H, W, H, 0, *ptr))
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
 def test_no_cpu_fallback(backbone_sd):
     from mermaid_classifier_b200.extractor import EfficientNetExtractor

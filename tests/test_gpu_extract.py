@@ -378,7 +378,7 @@ def test_extract_many_equals_per_image(ext32):
     got2, _ = ext32.extract_many(pinned, rcs)
     assert np.array_equal(got2, want)
     st = ext32.pipe_stats()
-    assert st["h2d"] >= sum(im.size for im, rc in zip(ims, rcs) if len(rc)) and st["d2h"] == want.nbytes
+    assert st["h2d"] >= sum(im.size for im, rc in zip(ims, rcs) if len(rc)) and st["d2h"] == want.nbytes   # small images: uploaded whole
     # a view with a row pitch (columns of a wider array)
     wide = np.zeros((300, 520, 3), np.uint8)
     wide[:, :500] = ims[0]
@@ -391,6 +391,40 @@ def test_extract_many_equals_per_image(ext32):
         ext32.extract_many([ims[0]], [[(300, 0)]])
     with pytest.raises(ValueError):
         ext32.extract_many(ims[:2], rcs[:1])
+
+
+def test_extract_many_window_upload_is_bit_identical(ext32, backbone_sd, monkeypatch):
+    """Images whose points need under 60 % of their pixels are uploaded as one clipped 224 x 224 window per point
+    (csrc/host_pipe.inl) instead of whole.  The crop reflects at the image border, which a clipped window shares, so the
+    features are the bits of the whole-image path: corners, edge points, images thinner than a patch (double reflection
+    inside a window that spans the whole height), heights between 112 and 224, pageable / pinned / pitched sources."""
+    shapes = [(1500, 2000), (100, 3000), (150, 2600), (3000, 100), (900, 1200)]
+    counts = [12, 6, 5, 6, 40]            # the last image needs most of its pixels: uploaded whole, in the same call
+    ims = [synth.synth_image(5, i, h, w) for i, (h, w) in enumerate(shapes)]
+    rcs = [synth.synth_points(5, i, h, w, c, corners=(i < 4)) for i, ((h, w), c) in enumerate(zip(shapes, counts))]
+    want = np.concatenate([ext32.extract_array(im, rc) for im, rc in zip(ims, rcs)])   # one-image call: whole upload
+    got, _ = ext32.extract_many(ims, rcs)
+    st = ext32.pipe_stats()
+    assert np.array_equal(got, want)
+    whole = sum(im.size for im in ims)
+    assert st["h2d"] < 0.6 * whole, (st, whole)          # windows of images 0-3 + image 4 whole
+    assert st["h2d"] > ims[4].size
+    pinned = [torch.from_numpy(im).pin_memory() for im in ims]
+    got_p, _ = ext32.extract_many(pinned, rcs)
+    assert np.array_equal(got_p, want)
+    wide = np.zeros((1500, 2040, 3), np.uint8)
+    wide[:, :2000] = ims[0]
+    got_w, _ = ext32.extract_many([wide[:, :2000]], [rcs[0]])
+    assert np.array_equal(got_w, want[: len(rcs[0])])
+    # A/B switch: every image whole
+    monkeypatch.setenv("MC_SPARSE_H2D", "0")
+    ref = EfficientNetExtractor(state_dict=backbone_sd, mode="fp32", max_batch=24)
+    try:
+        got_ref, _ = ref.extract_many(ims, rcs)
+        assert ref.pipe_stats()["h2d"] >= whole
+    finally:
+        ref.close()
+    assert np.array_equal(got_ref, want)
 
 
 def test_extract_many_with_head_labels(ext32):
