@@ -39,6 +39,8 @@ struct HostPipe {
     bool used = false;
   } slot[SLOTS];
   int64_t h2d_bytes = 0, d2h_bytes = 0, groups = 0;   // totals of the last call (bench accounting)
+  int64_t copies = 0;                                // H2D copy operations of the last call
+  double issue_ms = 0;                               // host time spent issuing them (MC_PIPE_DEBUG prints both)
 };
 
 namespace {
@@ -137,7 +139,8 @@ extern "C" int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_i
   cudaStream_t st = (cudaStream_t)stream;
   HostPipe* P = nullptr;
   if ((rc = host_pipe_get(h, &P))) return rc;
-  P->h2d_bytes = P->d2h_bytes = P->groups = 0;
+  P->h2d_bytes = P->d2h_bytes = P->groups = P->copies = 0;
+  P->issue_ms = 0;
 
   // the streams of the pipeline start after whatever the caller already queued on `st`
   cudaEvent_t& enter = P->slot[0].scored;   // any idle event will do before the first group
@@ -248,6 +251,7 @@ extern "C" int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_i
     if (s.used) MC_CUDA(cudaStreamWaitEvent(P->h2d, s.freed, 0));   // the arena's previous group has been convolved
     MC_CUDA(cudaMemcpyAsync(s.tab_dev, s.tab_host, (size_t)tab_bytes, cudaMemcpyHostToDevice, P->h2d));
     int64_t stage_off = 0;
+    const auto t_issue0 = std::chrono::steady_clock::now();
     int pinned_src = -1;
     bool src_is_pinned = false;
     for (size_t k = 0; k < vims.size(); ++k) {
@@ -281,6 +285,8 @@ extern "C" int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_i
                                   cudaMemcpyHostToDevice, P->h2d));
       P->h2d_bytes += row * v.h;
     }
+    P->copies += (int64_t)vims.size();
+    P->issue_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_issue0).count();
     P->h2d_bytes += tab_bytes;
     MC_CUDA(cudaEventRecord(s.copied, P->h2d));
     // ---- compute stream -----------------------------------------------------------------------------------------------
@@ -322,6 +328,9 @@ extern "C" int mc_extract_images_host(mc_extractor* h, mc_head* head, const mc_i
   restore();
   MC_CUDA(cudaStreamSynchronize(P->d2h));
   MC_CUDA(cudaStreamSynchronize(st));
+  if (getenv("MC_PIPE_DEBUG"))
+    fprintf(stderr, "[mc pipe] %lld points, %lld groups, %lld H2D copies issued in %.2f ms (%.2f us each), %.1f MB\n", (long long)n,
+            (long long)P->groups, (long long)P->copies, P->issue_ms, 1e3 * P->issue_ms / (double)std::max<int64_t>(1, P->copies), P->h2d_bytes / 1e6);
   return prof_collect(h, st);
 }
 
