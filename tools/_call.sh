@@ -1,10 +1,9 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-PYTHONPATH=. timeout 200 python tools/sparse_check.py 2>&1 | tail -6
-timeout 300 python -m pytest tests/test_gpu_extract.py tests/test_gpu_drivers.py -x -q -m gpu -k "not 10k" 2>&1 | tail -3
-show() { python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('$1', 'value', round(d['value']), 'e2e', round(e['value']), 'h2d_GB', round(e['h2d_bytes_per_step']/1e9,2), 'ms/step', round(e['ms_per_step'],1), 'chk', e['labels_checksum'])"; }
-for g in 1 0; do
-MC_H2D_GATHER=$g MC_PIPE_DEBUG=1 timeout 200 python bench.py --mode bf16 --points 50 --images 300 --no-cpu-baseline --no-sub 2> gpurun_out/pipe_dbg.txt | show "bf16 C3 gather=$g"
-grep "mc pipe" gpurun_out/pipe_dbg.txt | tail -1
-MC_H2D_GATHER=$g MC_PIPE_DEBUG=1 timeout 200 python bench.py --images 150 --no-cpu-baseline --no-sub 2> gpurun_out/pipe_dbg2.txt | show "fp32 C2 gather=$g"
-grep "mc pipe" gpurun_out/pipe_dbg2.txt | tail -1
-done
+T0=$(date +%s)
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/v2_tests.log 2>&1; echo tests rc=$? t=$(( $(date +%s) - T0 )); tail -2 gpurun_out/v2_tests.log | cut -c1-200
+timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -1
+timeout 420 python bench.py > gpurun_out/v2_bench.json 2> gpurun_out/v2_bench.err; echo bench rc=$? t=$(( $(date +%s) - T0 )); cut -c1-300 gpurun_out/v2_bench.json
+timeout 200 python bench.py --mode bf16 --images 300 --no-cpu-baseline > gpurun_out/v2_bench_bf16.json 2>/dev/null; echo bf16 rc=$? t=$(( $(date +%s) - T0 )); cut -c1-200 gpurun_out/v2_bench_bf16.json
+timeout 100 python bench.py --mode fp32 --images 100 --no-cpu-baseline --no-sub --profile-out gpurun_out/v2_layers_fp32.csv > /dev/null 2>&1
+timeout 100 python bench.py --mode bf16 --images 100 --no-cpu-baseline --no-sub --profile-out gpurun_out/v2_layers_bf16.csv > /dev/null 2>&1
+echo t=$(( $(date +%s) - T0 ))
