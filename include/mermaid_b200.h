@@ -288,6 +288,7 @@ int mc_mlp_set_adam(mc_mlp* h, const float* const* m_w_host, const float* const*
                     const float* const* v_w_host, const float* const* v_b_host, int64_t t);
 int64_t mc_mlp_steps(const mc_mlp* h);     /* Adam steps taken */
 int64_t mc_mlp_launches(const mc_mlp* h);  /* kernels launched so far by this handle */
+int64_t mc_mlp_graph_steps(const mc_mlp* h);  /* Adam steps of this handle taken by CUDA-graph replay (runs of >= 8 equal-sized steps) */
 int64_t mc_mlp_grad_size(const mc_mlp* h); /* floats in the flat gradient buffer (incl. 4 statistics) */
 
 #ifdef __cplusplus

@@ -99,6 +99,7 @@ SIGNATURES = {
     "mc_mlp_set_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64]),
     "mc_mlp_steps": (_i64, [_vp]),
     "mc_mlp_launches": (_i64, [_vp]),
+    "mc_mlp_graph_steps": (_i64, [_vp]),
     "mc_mlp_grad_size": (_i64, [_vp]),
 }
 

@@ -88,6 +88,22 @@ struct mc_mlp {
   float lr = 1e-3f, alpha = 1e-4f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
   int64_t t = 0;          // Adam steps taken
   int64_t launches = 0;   // kernels launched
+  // CUDA-graph replay of runs of equal-sized steps (mc_mlp_partial_fit): one captured PAIR of steps (the weight-norm partials
+  // ping-pong between two buffers), a device cursor, the mini-batch staging buffers the captured kernels read
+  cudaStream_t cap_st = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int g_rows = 0, g_parity = 0;
+  const void* g_ptrs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  MlpCtl* d_ctl = nullptr;
+  float* d_xb = nullptr;
+  int64_t cap_xb = 0;
+  int32_t* d_yb = nullptr;
+  int64_t cap_yb = 0;
+  int64_t* d_offs = nullptr;
+  int64_t cap_offs = 0;
+  float2* d_bc = nullptr;
+  int64_t cap_bc = 0;
+  int64_t graph_steps = 0;   // Adam steps taken through graph replay (diagnostics / tests)
 };
 
 namespace {
@@ -166,6 +182,45 @@ int mlp_ssq_init(mc_mlp* h, cudaStream_t st) {
   mlp_ssq_kernel<<<h->n_blocks, MLP_ADAM_THREADS, 0, st>>>(h->d_p, h->segs, h->d_ssq[h->ssq_cur]);
   MC_CHECK_LAUNCH();
   h->launches++;
+  return MC_OK;
+}
+
+// The captured pair of steps for mini-batches of `rows` rows: built on first use, rebuilt when `rows` or any buffer the
+// captured kernels address has changed.  `body(stream)` issues the two steps on the capture stream.
+template <typename Body>
+int mlp_graph_prepare(mc_mlp* h, int rows, int Dp, Body body) {
+  int rc;
+  if (!h->cap_st) MC_CUDA(cudaStreamCreateWithFlags(&h->cap_st, cudaStreamNonBlocking));
+  if (!h->d_ctl) MC_CUDA(cudaMalloc((void**)&h->d_ctl, sizeof(MlpCtl)));
+  if ((rc = grow(&h->d_xb, &h->cap_xb, (int64_t)rows * Dp)) || (rc = grow(&h->d_yb, &h->cap_yb, (int64_t)rows))) return rc;
+  const void* now[8] = {h->d_part[0], h->d_part[1], h->d_act[0], h->d_delta[0], h->d_rowstat, h->d_xb, h->d_yb, h->d_ctl};
+  bool valid = h->gexec != nullptr && h->g_rows == rows;
+  for (int i = 0; i < 8 && valid; ++i) valid = h->g_ptrs[i] == now[i];
+  if (valid) return MC_OK;
+  if (h->gexec) {
+    cudaGraphExecDestroy(h->gexec);
+    h->gexec = nullptr;
+  }
+  const int parity = h->ssq_cur;
+  MC_CUDA(cudaStreamBeginCapture(h->cap_st, cudaStreamCaptureModeThreadLocal));
+  rc = body(h->cap_st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e_end = cudaStreamEndCapture(h->cap_st, &graph);   // always: the stream must leave capture mode
+  h->ssq_cur = parity;   // a captured pair toggles twice; a failed capture may have toggled once
+  if (rc != MC_OK || e_end != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc != MC_OK ? rc : fail(MC_ERR_CUDA, std::string("mc_mlp_partial_fit: graph capture: ") + cudaGetErrorString(e_end));
+  }
+  const cudaError_t e_inst = cudaGraphInstantiate(&h->gexec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e_inst != cudaSuccess) {
+    h->gexec = nullptr;
+    return fail(MC_ERR_CUDA, std::string("mc_mlp_partial_fit: cudaGraphInstantiate: ") + cudaGetErrorString(e_inst));
+  }
+  h->g_rows = rows;
+  h->g_parity = parity;
+  for (int i = 0; i < 8; ++i) h->g_ptrs[i] = now[i];
   return MC_OK;
 }
 
@@ -309,8 +364,11 @@ int mc_mlp_destroy(mc_mlp* h) {
   DeviceGuard g(h->device);
   for (float* p : h->d_act) if (p) cudaFree(p);
   for (float* p : h->d_delta) if (p) cudaFree(p);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->cap_st) cudaStreamDestroy(h->cap_st);
   void* ptrs[] = {h->d_p, h->d_m, h->d_v, h->d_g, h->d_cw, h->d_ssq[0], h->d_ssq[1], h->d_loss,
-                  h->d_part[0], h->d_part[1], h->d_rowstat, h->d_xs, h->d_ys, h->d_tickets};
+                  h->d_part[0], h->d_part[1], h->d_rowstat, h->d_xs, h->d_ys, h->d_tickets,
+                  h->d_ctl, h->d_xb, h->d_yb, h->d_offs, h->d_bc};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return MC_OK;
@@ -346,9 +404,14 @@ int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, cons
     ys = h->d_ys;
   }
   MC_CUDA(cudaMemsetAsync(h->d_loss, 0, 2 * sizeof(double), st));
-  for (int s = 0; s < n_steps; ++s) {
+  // graph replay (below) redirects a step to the staging buffers, the cursor and the capture stream
+  const float* x_over = nullptr;
+  const int32_t* y_over = nullptr;
+  const MlpCtl* ctl_arg = nullptr;
+  auto run_step = [&](int s) -> int {
     const int rows = (int)(step_offsets[s + 1] - step_offsets[s]);
-    const float* x = xs + step_offsets[s] * Dp;
+    const float* x = x_over ? x_over : xs + step_offsets[s] * Dp;
+    const int32_t* y_step = y_over ? y_over : ys + step_offsets[s];
     // Experiment, off by default (MC_MLP_ROWLOCAL=1; MC_MLP_RL_R = rows per CTA): first-layer GEMM -> ONE launch for layers
     // 1..L-1, the loss and every delta (mlp_rowlocal_kernel) -> one launch for all weight gradients: 4 launches per step
     // instead of 10.  Measured at (500,300,100) / 500 classes / mini-batch 200: 6.0 k Adam steps/s (R = 2) against 7.1 k for
@@ -380,7 +443,7 @@ int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, cons
       }
       rp.params = h->d_p;
       rp.act0 = h->d_act[0];
-      rp.y = ys + step_offsets[s];
+      rp.y = y_step;
       rp.class_w = h->d_cw;
       rp.row_stat = h->d_rowstat;
       rp.stats = h->d_g + h->n_flat;
@@ -423,7 +486,7 @@ int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, cons
         in = h->d_act[i];
       }
       // loss + un-normalised output delta + statistics
-      mlp_ce_kernel<<<cdiv(rows, 8), 256, 0, st>>>(h->d_act[L - 1], Kp, K, ys + step_offsets[s], h->d_cw, h->d_delta[L - 1],
+      mlp_ce_kernel<<<cdiv(rows, 8), 256, 0, st>>>(h->d_act[L - 1], Kp, K, y_step, h->d_cw, h->d_delta[L - 1],
                                                   h->d_rowstat, rows, h->d_g + h->n_flat, h->d_tickets + 2 * h->n_tickets);
       MC_CHECK_LAUNCH();
       h->launches++;
@@ -457,10 +520,82 @@ int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, cons
     mlp_adam_kernel<<<h->n_blocks, MLP_ADAM_THREADS, 0, st>>>(h->d_p, h->d_m, h->d_v, h->d_g, h->segs, h->d_g + h->n_flat,
                                                              h->lr, h->alpha, h->beta1, h->beta2, h->eps, (float)bc1,
                                                              (float)sqrt(bc2), h->d_ssq[h->ssq_cur], h->n_blocks,
-                                                             h->d_ssq[h->ssq_cur ^ 1], h->d_loss);
+                                                             h->d_ssq[h->ssq_cur ^ 1], h->d_loss, ctl_arg);
     MC_CHECK_LAUNCH();
     h->launches++;
     h->ssq_cur ^= 1;
+    return MC_OK;
+  };
+  auto rows_of = [&](int s) { return (int)(step_offsets[s + 1] - step_offsets[s]); };
+  // ---- runs of equal-sized steps: CUDA-graph replay -----------------------------------------------------------------------
+  // A step is ten dependent launches of 5-25 us; on a host that needs longer than that per launch the loop is launch-bound
+  // (measured on two boxes of the same pool: 7.1 k and 2.8 k Adam steps/s).  A run of >= 8 equal-sized steps of a single
+  // process is therefore replayed from ONE captured pair of steps: a stage kernel copies the cursor's mini-batch into fixed
+  // buffers, the step's kernels read those (same kernels, same order, same operands: bit-identical weights), Adam takes its
+  // bias corrections through the cursor, a one-thread kernel advances it.  The first two steps of a run are launched the
+  // ordinary way (lazy allocations); MC_MLP_GRAPH=0 turns the replay off.
+  static const bool graph_on = !(getenv("MC_MLP_GRAPH") && atoi(getenv("MC_MLP_GRAPH")) == 0) && getenv("MC_MLP_ROWLOCAL") == nullptr;
+  const bool graph_ok = graph_on && !(dp && dp->world > 1) && !grad_sync && (reinterpret_cast<uintptr_t>(xs) & 15) == 0;
+  bool cursor_ready = false;
+  int s = 0;
+  while (s < n_steps) {
+    const int rows = rows_of(s);
+    int e = s;
+    while (e < n_steps && rows_of(e) == rows) ++e;
+    if (graph_ok && rows > 0 && e - s >= 8) {
+      if ((rc = run_step(s++)) || (rc = run_step(s++))) return rc;
+      if ((rc = mlp_graph_prepare(h, rows, Dp, [&](cudaStream_t cs) -> int {
+             // body of the capture: two steps on the capture stream, reading the staging buffers and the cursor
+             const cudaStream_t keep = st;
+             const int64_t t_keep = h->t, l_keep = h->launches;
+             st = cs;
+             x_over = h->d_xb;
+             y_over = h->d_yb;
+             ctl_arg = h->d_ctl;
+             int r2 = MC_OK;
+             for (int k = 0; k < 2 && r2 == MC_OK; ++k) {
+               mlp_stage_kernel<<<148, 256, 0, cs>>>(h->d_ctl, reinterpret_cast<float4*>(h->d_xb), h->d_yb, rows, Dp / 4);
+               r2 = run_step(s);   // same shapes as step s; its pointers and bias corrections are overridden
+               mlp_advance_kernel<<<1, 1, 0, cs>>>(h->d_ctl);
+             }
+             st = keep;
+             x_over = nullptr;
+             y_over = nullptr;
+             ctl_arg = nullptr;
+             h->t = t_keep;
+             h->launches = l_keep;
+             return r2;
+           })))
+        return rc;
+      if (h->ssq_cur != h->g_parity && (rc = run_step(s++))) return rc;
+      const int pairs = (e - s) / 2;
+      if (pairs > 0) {
+        if (!cursor_ready) {
+          // the call's step table and bias corrections, computed exactly as run_step computes them
+          std::vector<float2> bc((size_t)n_steps);
+          for (int i = 0; i < n_steps; ++i) {
+            const int64_t t_i = h->t - s + i + 1;   // Adam step number of the call's step i
+            bc[(size_t)i] = make_float2((float)(1.0 - pow((double)h->beta1, (double)t_i)),
+                                        (float)sqrt(1.0 - pow((double)h->beta2, (double)t_i)));
+          }
+          if ((rc = grow(&h->d_offs, &h->cap_offs, (int64_t)n_steps + 1)) || (rc = grow(&h->d_bc, &h->cap_bc, (int64_t)n_steps))) return rc;
+          MC_CUDA(cudaMemcpyAsync(h->d_offs, step_offsets, ((size_t)n_steps + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+          MC_CUDA(cudaMemcpyAsync(h->d_bc, bc.data(), (size_t)n_steps * sizeof(float2), cudaMemcpyHostToDevice, st));
+          MC_CUDA(cudaStreamSynchronize(st));   // `bc` is a local: the copy must have left it
+          cursor_ready = true;
+        }
+        const MlpCtl ctl{(long long)s, xs, ys, h->d_offs, h->d_bc};
+        MC_CUDA(cudaMemcpyAsync(h->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+        MC_CUDA(cudaStreamSynchronize(st));     // `ctl` is a local
+        for (int k = 0; k < pairs; ++k) MC_CUDA(cudaGraphLaunch(h->gexec, st));
+        h->t += 2 * pairs;
+        h->launches += (int64_t)pairs * 2 * (2 * L + 4);   // per step: stage, L forward, loss, L backward, Adam, advance
+        h->graph_steps += 2 * pairs;
+        s += 2 * pairs;
+      }
+    }
+    while (s < e)
+      if ((rc = run_step(s++))) return rc;
   }
   if (loss_out_host) {
     double acc[2] = {0.0, 0.0};
@@ -507,6 +642,7 @@ int mc_mlp_set_adam(mc_mlp* h, const float* const* m_w, const float* const* m_b,
 
 int64_t mc_mlp_steps(const mc_mlp* h) { return h ? h->t : 0; }
 int64_t mc_mlp_launches(const mc_mlp* h) { return h ? h->launches : 0; }
+int64_t mc_mlp_graph_steps(const mc_mlp* h) { return h ? h->graph_steps : 0; }
 int64_t mc_mlp_grad_size(const mc_mlp* h) { return h ? h->n_flat + 4 : 0; }
 
 }  // extern "C"

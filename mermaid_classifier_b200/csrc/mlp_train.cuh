@@ -537,6 +537,30 @@ mlp_ssq_kernel(const float* __restrict__ p, MlpSegs segs, float* __restrict__ ss
   block_ssq_store(s, ssq_part + blockIdx.x);
 }
 
+// Device-side cursor of a run of equal-sized Adam steps replayed from a CUDA graph: everything that changes from step to
+// step -- which rows of the call's (xs, ys) form the mini-batch, Adam's bias corrections -- is read through it, so the
+// kernels of a step keep the same arguments and one captured pair of steps can be replayed for the whole run.
+struct MlpCtl {
+  long long step;            // index into offs / bc of the step being executed
+  const float* xs;           // the call's padded, ordered feature rows
+  const int32_t* ys;
+  const int64_t* offs;       // [n_steps + 1] row offsets of the call's steps
+  const float2* bc;          // [n_steps] (1 - beta1^t, sqrt(1 - beta2^t)) computed on the host exactly as for a launched step
+};
+
+// mini-batch of the cursor's step -> the fixed staging buffers the step's kernels read (rows x Dp floats, rows labels)
+__global__ void mlp_stage_kernel(const MlpCtl* __restrict__ ctl, float4* __restrict__ xb, int32_t* __restrict__ yb, int rows,
+                                 int Dp4) {
+  const int64_t off = ctl->offs[ctl->step];
+  const float4* src = reinterpret_cast<const float4*>(ctl->xs) + off * Dp4;
+  const int n4 = rows * Dp4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) xb[i] = src[i];
+  if (blockIdx.x == 0)
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) yb[r] = ctl->ys[off + r];
+}
+
+__global__ void mlp_advance_kernel(MlpCtl* ctl) { ctl->step += 1; }
+
 // Adam step on the flat parameter vector (torch.optim.Adam semantics: eps added to sqrt(v_hat)).
 //   g = G / wsum + (alpha / nrows) * W   for weights,  G / wsum for biases.
 // Block 0 also books the mini-batch loss:  loss_acc += (lsum / wsum + 0.5 * alpha / nrows * ssq_prev) * nrows,
@@ -545,7 +569,12 @@ __global__ void __launch_bounds__(MLP_ADAM_THREADS)
 mlp_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ G,
                 MlpSegs segs, const float* __restrict__ stats, float lr, float alpha, float beta1, float beta2, float eps,
                 float bc1, float bc2_sqrt, const float* __restrict__ ssq_prev, int n_ssq, float* __restrict__ ssq_next,
-                double* __restrict__ loss_acc) {
+                double* __restrict__ loss_acc, const MlpCtl* __restrict__ ctl) {
+  if (ctl != nullptr) {   // graph replay: this step's bias corrections come through the cursor
+    const float2 bc = ctl->bc[ctl->step];
+    bc1 = bc.x;
+    bc2_sqrt = bc.y;
+  }
   const float wsum = stats[0], nrows = stats[2];
   const int64_t i = (int64_t)blockIdx.x * MLP_ADAM_THREADS + threadIdx.x;
   float s = 0.f;

@@ -317,6 +317,12 @@ class TorchMLPClassifier:
         return n + (self._head.launches if getattr(self, "_head", None) is not None else 0)
 
     @property
+    def graph_steps_(self) -> int:
+        """Adam steps taken by CUDA-graph replay (runs of >= 8 equal-sized mini-batches of one process; ``MC_MLP_GRAPH=0``
+        launches every step kernel by kernel)."""
+        return int(_lib.load().mc_mlp_graph_steps(self._h)) if hasattr(self, "_h") else 0
+
+    @property
     def n_steps_(self) -> int:
         return int(_lib.load().mc_mlp_steps(self._h)) if hasattr(self, "_h") else 0
 

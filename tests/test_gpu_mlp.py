@@ -195,3 +195,45 @@ def test_rowlocal_experiment_path_matches_default():
         outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
     np.testing.assert_allclose(outs[1]["loss"], outs[0]["loss"], rtol=2e-5)
     np.testing.assert_allclose(np.asarray(outs[1]["p"]), np.asarray(outs[0]["p"]), atol=2e-5)
+
+
+def test_graph_replay_is_bit_identical_to_launched_steps():
+    """Runs of >= 8 equal-sized Adam steps are replayed from one captured pair of steps (csrc/mlp_api.inl): the same kernels in
+    the same order on a staged copy of each mini-batch, so parameters, Adam moments and the loss curve equal the
+    kernel-by-kernel loop (``MC_MLP_GRAPH=0``, read once per process -> subprocesses) BIT FOR BIT -- ragged tail, class
+    weights, several calls (the graph is reused), a call too short to replay, and an odd run length included."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import json, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from mermaid_classifier_b200.torch_classifier import TorchMLPClassifier\n"
+        "rng = np.random.RandomState(11); c = rng.randn(9, 64) * 3.0; y = rng.randint(0, 9, size=5330)\n"
+        "X = (c[y] + rng.randn(5330, 64) * 1.3).astype(np.float32)\n"
+        "cw = {k: 0.5 + 0.125 * k for k in range(9)}\n"
+        "clf = TorchMLPClassifier(hidden_layer_sizes=(40, 24), learning_rate_init=1e-3, random_state=0, class_weight=cw)\n"
+        "clf.partial_fit(X, y, classes=list(range(9)))\n"          # 26 full steps + a tail of 130
+        "clf.partial_fit(X[:4600], y[:4600])\n"                    # 23 full steps: odd run
+        "clf.partial_fit(X[:900], y[:900])\n"                      # 4 full steps + tail: too short to replay
+        "clf.partial_fit(X, y)\n"
+        "ws, bs = clf._pull_params()\n"
+        "print(json.dumps({'loss': clf.loss_curve_, 'w': [w.tolist() for w in ws], 'b': [b.tolist() for b in bs],"
+        " 'steps': clf.n_steps_, 'graph_steps': clf.graph_steps_}))\n"
+    ) % str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    outs = []
+    for flag in ("0", None):
+        env = {k: v for k, v in os.environ.items() if k not in ("MC_MLP_GRAPH", "MC_MLP_ROWLOCAL")}
+        if flag:
+            env["MC_MLP_GRAPH"] = flag
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    launched, replayed = outs
+    assert launched["graph_steps"] == 0 and replayed["graph_steps"] >= 60, (launched["graph_steps"], replayed["graph_steps"])
+    assert launched["steps"] == replayed["steps"] == 27 + 23 + 5 + 27
+    assert launched["loss"] == replayed["loss"]
+    for a, b in zip(launched["w"] + launched["b"], replayed["w"] + replayed["b"]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
