@@ -1,3 +1,5 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_gpu_mlp.py tests/test_gpu_trainer.py -x -q -m gpu 2>&1 | tail -4
-for g in 1 0; do MC_MLP_GRAPH=$g timeout 120 python tools/bench_train.py --rows 400000 --epochs 2 --cpu-rows 2000 2>&1 | tail -1 | cut -c1-400; done
+T0=$(date +%s)
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/v3_tests.log 2>&1; echo tests rc=$? t=$(( $(date +%s) - T0 )); tail -2 gpurun_out/v3_tests.log | cut -c1-200
+timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -1
+timeout 420 python bench.py > gpurun_out/v3_bench.json 2> gpurun_out/v3_bench.err; echo bench rc=$? t=$(( $(date +%s) - T0 )); cut -c1-200 gpurun_out/v3_bench.json
