@@ -159,6 +159,12 @@ int mc_extractor_pipe_stats(const mc_extractor* h, int64_t* h2d_bytes, int64_t* 
  * SURVEY 8a A2); it is the data-movement rule of the host pipeline, exported so that it can be tested without a GPU. */
 int mc_upload_window(int32_t height, int32_t width, int32_t row, int32_t col, int32_t* r0, int32_t* c0, int32_t* h,
                      int32_t* w);
+/* Host-only.  The upload plan of one image as mc_extract_images_host builds it: the points' windows (mc_upload_window), merged
+ * into bounding boxes while a merge costs fewer bytes than another copy costs time.  windows_out receives up to n rows of
+ * (r0, c0, h, w), index_out[i] the window of point i, *n_windows the number of windows.  Every point's own window lies inside
+ * its planned window, so the patch cropped from the planned window around (row - r0, col - c0) is the patch of the whole image. */
+int mc_plan_uploads(int32_t height, int32_t width, const int32_t* rowcols, int64_t n_points, int32_t* windows_out,
+                    int32_t* index_out, int64_t* n_windows);
 
 /* ---- (f)2: image decode feeding the crop kernel: spacer.storage.load_image (call site
  *      mermaid_classifier/pyspacer/annotation.py:235; inside spacer.tasks.extract_features,

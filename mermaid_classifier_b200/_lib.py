@@ -70,6 +70,7 @@ SIGNATURES = {
     "mc_extract_images_host": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mc_extractor_pipe_stats": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mc_upload_window": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "mc_plan_uploads": (C.c_int, [_i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mc_jpeg_create": (C.c_int, [_i32, _pp]),
     "mc_jpeg_destroy": (C.c_int, [_vp]),
     "mc_jpeg_info": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -75,6 +75,50 @@ def test_upload_window_holds_every_pixel_of_the_patch(hw):
         _lib.check(lib.mc_upload_window(H, W, H, 0, *ptr))
 
 
+@pytest.mark.parametrize("hw,n,spread", [((700, 900), 40, None), ((700, 900), 60, 150), ((260, 1200), 25, None),
+                                         ((100, 500), 12, None), ((1500, 2000), 80, 400)])
+def test_upload_plan_merges_windows_and_keeps_every_patch(hw, n, spread):
+    """mc_plan_uploads (what mc_extract_images_host uploads for a sparsely annotated image): the points' windows merged into
+    bounding boxes.  Every point's own window lies inside its planned window, the patch cropped from the planned window equals
+    the oracle's patch of the whole image byte for byte, clustered points share windows, and a merge never costs more than the
+    stated slack (128 KiB) beyond the point's own window."""
+    from oracle import crop as ocrop
+
+    H, W = hw
+    lib = _lib.load()
+    rng = np.random.default_rng(H + 7 * W + n)
+    im = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    if spread is None:
+        rc = np.stack([rng.integers(0, H, n), rng.integers(0, W, n)], 1)
+    else:   # clustered annotations: overlapping windows
+        centre = np.array([H // 3, W // 3])
+        rc = np.clip(centre + rng.integers(-spread, spread + 1, size=(n, 2)), 0, [H - 1, W - 1])
+    rc[:4] = [(0, 0), (0, W - 1), (H - 1, 0), (H - 1, W - 1)]
+    rc = np.ascontiguousarray(rc, dtype=np.int32)
+    wins = np.zeros((n, 4), np.int32)
+    idx = np.zeros(n, np.int32)
+    nw = C.c_int64()
+    _lib.check(lib.mc_plan_uploads(H, W, rc.ctypes.data, n, wins.ctypes.data, idx.ctypes.data, C.byref(nw)))
+    nw = nw.value
+    assert 1 <= nw <= n and idx.min() >= 0 and idx.max() == nw - 1
+    if spread is not None:
+        assert nw < n // 2          # clustered points share windows
+    want = ocrop.crop_patches(im, [tuple(p) for p in rc])
+    own = (C.c_int32 * 4)()
+    ptr = [C.cast(C.byref(own, 4 * i), C.c_void_p) for i in range(4)]
+    own_bytes = 0
+    for k, (r, c) in enumerate(rc):
+        r0, c0, h, w = (int(v) for v in wins[idx[k]])
+        _lib.check(lib.mc_upload_window(H, W, int(r), int(c), *ptr))
+        assert r0 <= own[0] and c0 <= own[1] and r0 + h >= own[0] + own[2] and c0 + w >= own[1] + own[3]
+        assert 0 <= r0 and r0 + h <= H and 0 <= c0 and c0 + w <= W
+        own_bytes += own[2] * own[3] * 3
+        got = ocrop.crop_patches(np.ascontiguousarray(im[r0:r0 + h, c0:c0 + w]), [(int(r) - r0, int(c) - c0)])[0]
+        assert np.array_equal(got, want[k]), (hw, (r, c), (r0, c0, h, w))
+    planned = int((wins[:nw, 2].astype(np.int64) * wins[:nw, 3] * 3).sum())
+    assert planned <= own_bytes + (n - nw) * 128 * 1024
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
 def test_no_cpu_fallback(backbone_sd):
     from mermaid_classifier_b200.extractor import EfficientNetExtractor
