@@ -126,6 +126,26 @@ def test_image_sharding_covers_all_images_once():
         assert cover == list(range(100))
 
 
+def test_row_sharding_is_a_balanced_contiguous_partition():
+    """C4 scoring shards feature rows in contiguous blocks (bench.py's c4_scoring record): the blocks tile [0, n) in rank
+    order, sizes differ by at most one row, degenerate sizes (fewer rows than ranks, zero rows) included, and concatenating
+    per-rank labels in rank order reproduces the single-process order."""
+    from mermaid_classifier_b200.sharding import rows_for_rank
+
+    for n in (0, 1, 7, 8, 9, 10_000_000, 10_000_003):
+        for world in (1, 2, 4, 8):
+            blocks = [rows_for_rank(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
+    labels = np.arange(1003) % 17
+    parts = [labels[slice(*rows_for_rank(len(labels), r, 4))] for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), labels)
+    with pytest.raises(ValueError):
+        rows_for_rank(10, 2, 2)
+
+
 # ---- trainer-level reductions of the throughput (sharded) mode ---------------------------------------------------
 class _Group:
     """What trainer.MermaidTrainer reads from torch_classifier.DataParallel (which itself needs NCCL + a GPU)."""
