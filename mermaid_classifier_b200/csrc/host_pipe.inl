@@ -106,9 +106,10 @@ int pinned_grow(uint8_t** p, int64_t* cap, int64_t need) {
 inline int win_lo(int centre) { return std::max(0, centre - MC_CROP_HALF); }
 inline int win_hi(int centre, int size) { return std::min(size, centre + MC_CROP_HALF + (centre == 0 ? 1 : 0)); }
 
-// Upload plan of one image: every point's own window, with windows MERGED into their bounding box while that costs less than
-// another copy would -- a 2-D copy costs the calling thread ~7 us whatever its size (at ~25 GB/s that is ~170 KB of transfer),
-// and on annotation-dense images many windows overlap.  A merged box contains each member's own window, touches an image
+// Upload plan of one image: every point's own window, with windows MERGED into their bounding box while that adds few bytes
+// -- on annotation-dense images many windows overlap, and every 2-D copy is a driver call and a DMA descriptor chain of
+// ~224 short rows (measured: 35-55 % fewer copies for the same bytes on the bench's point sets; the end-to-end rate is bound
+// by the strided DMA itself, ~20 GB/s, and did not move).  A merged box contains each member's own window, touches an image
 // border exactly where a member's window was clipped there, and is otherwise never crossed by a member's patch: the reflect
 // argument of a single window carries over.  Greedy, in point order: a point joins the box whose growth is smallest if that
 // growth exceeds the point's own window by at most MC_MERGE_SLACK bytes.
