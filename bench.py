@@ -155,7 +155,11 @@ def ncu_traffic(layer_id: int, mode: str, patches_per_launch: float):
     mb = d.get("traffic_MB_per_launch", {}).get(name)
     if mb is None:
         return None, "no committed ncu capture of this kernel"
-    return mb * 1e6 * patches_per_launch / d["patches_per_launch"], f"profiles/{f.name}:{name} (ncu --set full, {d['patches_per_launch']} patches per launch, scaled)"
+    stamp = d.get("captured_at_commit", {})
+    at = stamp.get(name, stamp.get("others"))
+    return (mb * 1e6 * patches_per_launch / d["patches_per_launch"],
+            f"profiles/{f.name}:{name} (ncu --set full, {d['patches_per_launch']} patches per launch, scaled"
+            + (f"; captured at commit {at}" if at else "") + ")")
 
 
 def measured_peaks() -> tuple[float, str]:

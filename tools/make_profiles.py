@@ -51,7 +51,12 @@ if kf.exists():
     with open(out / f"{tag}_kernels_{mode}.csv", "w") as f:
         f.write("# ncu --set full --clock-control none, one launch each (500 patches); dram_*_MB = dram__bytes_{read,write}.sum per launch\n")
         f.write("\n".join(lines) + "\n")
-json.dump({"mode": mode, "patches_per_launch": 500, "family_time_shares_ncu": shares, "sub_batch_us_ncu": round(tot, 1),
+import subprocess
+try:
+    head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+except OSError:
+    head = ""
+json.dump({"mode": mode, "patches_per_launch": 500, "captured_at_commit": {"others": head}, "family_time_shares_ncu": shares, "sub_batch_us_ncu": round(tot, 1),
            "traffic_MB_per_launch": {d["capture"]: round(float(d["dram_rd_MB"]) + float(d["dram_wr_MB"]), 1) for d in summ}},
           open(out / f"{tag}_summary_{mode}.json", "w"), indent=1)
 print(json.dumps(shares, indent=1)); print(tot)
