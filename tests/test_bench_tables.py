@@ -69,3 +69,27 @@ def test_defaults_follow_the_library(bench, monkeypatch):
     d16 = int(re.search(r"#define MC_FUSE_DEFAULT (0x[0-9A-Fa-f]+)u", src).group(1), 16)
     d32 = int(re.search(r"#define MC_FUSE_DEFAULT_FP32 (0x[0-9A-Fa-f]+)u", src).group(1), 16)
     assert bench.fused_blocks(4) == d32 and bench.fused_blocks(2) == d16
+
+
+def test_reference_arm_contract():
+    """`bench.py --impl reference`: rank 0 alone runs the CPU path and prints ONE JSON line with the arm's keys; any other rank
+    exits 0 without output (the driver launches the arm under torchrun like the B200 arm)."""
+    import json
+    import os
+    import subprocess
+
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29871")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--points", "6"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "point-patches/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "point-patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1
