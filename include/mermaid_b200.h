@@ -281,7 +281,10 @@ int mc_dp_all_reduce_sum(mc_dp* d, float* buf_dev, int64_t n, void* stream);
  * (NULL = single GPU) and then handed to the optional `grad_sync` hook on the stream; the Adam
  * kernel normalises by the GLOBAL statistics, so the update equals the reference's for the
  * global mini-batch.  *loss_out_host receives the loss_curve_ entry (sample-weighted mean of
- * the regularised mini-batch losses, torch_classifier.py:295-301); passing it synchronises. */
+ * the regularised mini-batch losses, torch_classifier.py:295-301); passing it synchronises.
+ * Without `dp` and `grad_sync`, runs of >= 8 equal-sized steps are replayed from a captured CUDA graph of two steps (the
+ * same kernels on a staged copy of each mini-batch: bit-identical parameters; the call then synchronises `stream` once
+ * per run to hand the step table to the device); MC_MLP_GRAPH=0 launches every step kernel by kernel. */
 typedef void (*mc_grad_sync_fn)(float* grad_dev, int64_t n_grad, void* stream, void* user);
 int mc_mlp_partial_fit(mc_mlp* h, const float* x_dev, const int32_t* y_dev, const int64_t* order_dev,
                        const int64_t* step_offsets_host, int32_t n_steps, mc_dp* dp,
